@@ -1,0 +1,518 @@
+// C ABI of libdiagon_b200.so (include/diagon_b200_c_api.h): the reference's query-path bridge
+// (diagon_c_api.cpp:44-62, :615-634, :660-905) re-implemented over dgpu::search, plus the dgpu_* additions.
+#include "../../include/diagon_b200_c_api.h"
+
+#include "search.h"
+
+#include <bit>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace dgpu;
+using namespace dgpu::search;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+void set_error(const std::exception& e) { g_last_error = e.what(); }
+
+IndexReader* as_reader(DiagonIndexReader r) { return static_cast<IndexReader*>(r); }
+IndexSearcher* as_searcher(DiagonIndexSearcher s) { return static_cast<IndexSearcher*>(s); }
+Query* as_query(DiagonQuery q) { return static_cast<Query*>(q); }
+
+void add_clause(DiagonQuery bool_query, DiagonQuery clause, Occur occur) {
+    if (!bool_query || !clause) {
+        set_error("Both bool_query and clause are required");
+        return;
+    }
+    try {
+        auto* builder = static_cast<BooleanQuery::Builder*>(bool_query);
+        // the clause is cloned, the caller keeps ownership of `clause` (diagon_c_api.cpp:797-800)
+        builder->add(std::shared_ptr<Query>(as_query(clause)->clone().release()), occur);
+    } catch (const std::exception& e) {
+        set_error(e);
+    }
+}
+
+// Splits a text batch into lines and parses them on all host threads.
+std::vector<std::unique_ptr<Query>> parse_batch(const char* text, int64_t len) {
+    std::vector<std::pair<const char*, const char*>> lines;
+    const char* p = text;
+    const char* end = text + len;
+    while (p < end) {
+        const char* nl = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(end - p)));
+        const char* e = nl ? nl : end;
+        if (e > p) lines.emplace_back(p, e);
+        p = nl ? nl + 1 : end;
+    }
+    std::vector<std::unique_ptr<Query>> out(lines.size());
+    parallel_for(lines.size(), lines.size() < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) out[i] = parse_query_line(std::string(lines[i].first, lines[i].second));
+    });
+    return out;
+}
+
+void unpack(const std::vector<uint64_t>& keys, const std::vector<int32_t>& counts, int32_t n, int32_t k,
+            int32_t* out_docs, float* out_scores) {
+    for (int32_t q = 0; q < n; ++q)
+        for (int32_t i = 0; i < k; ++i) {
+            size_t idx = static_cast<size_t>(q) * static_cast<size_t>(k) + static_cast<size_t>(i);
+            if (i < counts[static_cast<size_t>(q)]) {
+                uint64_t key = keys[idx];
+                uint32_t bits = dgpu_float_bits_from_orderable(static_cast<uint32_t>(key >> 32));
+                std::memcpy(&out_scores[idx], &bits, 4);
+                out_docs[idx] = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+            } else {
+                out_docs[idx] = -1;
+                out_scores[idx] = 0.0f;
+            }
+        }
+}
+
+// Compiles queries in parallel (per-thread CompiledBatch, then concatenated in order).
+void compile_all(IndexSearcher& s, const std::vector<const Query*>& qs, CompiledBatch& out) {
+    size_t n = qs.size();
+    int threads = n < 512 ? 1 : static_cast<int>(std::min<size_t>(std::thread::hardware_concurrency(), 32));
+    if (threads <= 1) {
+        for (const Query* q : qs) s.compile(*q, out);
+        return;
+    }
+    std::vector<CompiledBatch> parts(static_cast<size_t>(threads));
+    std::vector<size_t> begins(static_cast<size_t>(threads) + 1, 0);
+    parallel_for(n, threads, [&](size_t b, size_t e, int t) {
+        begins[static_cast<size_t>(t)] = b;
+        for (size_t i = b; i < e; ++i) s.compile(*qs[i], parts[static_cast<size_t>(t)]);
+    });
+    for (auto& p : parts) {
+        uint32_t toff = static_cast<uint32_t>(out.terms.size()), foff = static_cast<uint32_t>(out.filters.size());
+        for (auto q : p.queries) {
+            q.term_begin += toff; q.term_end += toff;
+            q.filter_begin += foff; q.filter_end += foff;
+            out.queries.push_back(q);
+        }
+        out.terms.insert(out.terms.end(), p.terms.begin(), p.terms.end());
+        out.filters.insert(out.filters.end(), p.filters.begin(), p.filters.end());
+        out.algorithmic_bytes += p.algorithmic_bytes;
+    }
+}
+
+int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, int32_t* out_docs, float* out_scores,
+              int32_t* out_counts, int64_t* out_total_hits) {
+    if (k <= 0) throw std::invalid_argument("numHits must be > 0");
+    CompiledBatch batch;
+    compile_all(s, qs, batch);
+    size_t n = qs.size();
+    std::vector<uint64_t> keys(n * static_cast<size_t>(k));
+    std::vector<int32_t> counts(n);
+    dgpu_results res{keys.data(), counts.data(), out_total_hits};
+    dgpu_query_batch view = batch.view();
+    if (n && dgpu_engine_search(s.getIndexReader().engine(), &view, k, &res) != 0)
+        throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
+    unpack(keys, counts, static_cast<int32_t>(n), k, out_docs, out_scores);
+    std::memcpy(out_counts, counts.data(), n * sizeof(int32_t));
+    return static_cast<int>(n);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ Part 1
+const char* diagon_last_error(void) { return g_last_error.c_str(); }
+void diagon_clear_error(void) { g_last_error.clear(); }
+
+int64_t diagon_reader_num_docs(DiagonIndexReader reader) {
+    if (!reader) { set_error("Invalid reader"); return -1; }
+    return as_reader(reader)->numDocs();
+}
+int64_t diagon_reader_max_doc(DiagonIndexReader reader) {
+    if (!reader) { set_error("Invalid reader"); return -1; }
+    return as_reader(reader)->maxDoc();
+}
+int diagon_reader_get_segment_count(DiagonIndexReader reader) {
+    if (!reader) { set_error("Invalid reader"); return -1; }
+    return static_cast<int>(as_reader(reader)->segmentCount());
+}
+void diagon_close_index_reader(DiagonIndexReader reader) { delete as_reader(reader); }
+
+DiagonIndexSearcher diagon_create_index_searcher(DiagonIndexReader reader) {
+    if (!reader) { set_error("Invalid reader"); return nullptr; }
+    try {
+        return new IndexSearcher(*as_reader(reader));
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+DiagonTopDocs diagon_search(DiagonIndexSearcher searcher, DiagonQuery query, int num_hits) {
+    if (!searcher || !query) { set_error("Invalid searcher or query"); return nullptr; }
+    try {
+        return new TopDocs(as_searcher(searcher)->search(*as_query(query), num_hits));
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+int diagon_count(DiagonIndexSearcher searcher, DiagonQuery query) {
+    if (!searcher || !query) { set_error("Invalid searcher or query"); return -1; }
+    try {
+        return as_searcher(searcher)->count(*as_query(query));
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+void diagon_free_index_searcher(DiagonIndexSearcher searcher) { delete as_searcher(searcher); }
+
+DiagonTerm diagon_create_term(const char* field, const char* text) {
+    if (!field || !text) { set_error("Invalid field or text"); return nullptr; }
+    try {
+        return new Term(field, text);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+void diagon_free_term(DiagonTerm term) { delete static_cast<Term*>(term); }
+
+DiagonQuery diagon_create_term_query(DiagonTerm term) {
+    if (!term) { set_error("Invalid term"); return nullptr; }
+    try {
+        return static_cast<Query*>(new TermQuery(*static_cast<Term*>(term)));
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+DiagonQuery diagon_create_numeric_range_query(const char* field_name, double lower_value, double upper_value,
+                                              bool include_lower, bool include_upper) {
+    if (!field_name) { set_error("Field name is required"); return nullptr; }
+    try {
+        return static_cast<Query*>(new NumericRangeQuery(field_name, std::bit_cast<int64_t>(lower_value),
+                                                         std::bit_cast<int64_t>(upper_value), include_lower, include_upper));
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+DiagonQuery dgpu_create_long_range_query(const char* field, int64_t lower, int64_t upper, bool include_lower,
+                                         bool include_upper) {
+    if (!field) { set_error("Field name is required"); return nullptr; }
+    try {
+        return static_cast<Query*>(new NumericRangeQuery(field, lower, upper, include_lower, include_upper));
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+DiagonQuery diagon_create_bool_query(void) {
+    try {
+        return new BooleanQuery::Builder();
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+void diagon_bool_query_add_must(DiagonQuery b, DiagonQuery c) { add_clause(b, c, Occur::MUST); }
+void diagon_bool_query_add_should(DiagonQuery b, DiagonQuery c) { add_clause(b, c, Occur::SHOULD); }
+void diagon_bool_query_add_filter(DiagonQuery b, DiagonQuery c) { add_clause(b, c, Occur::FILTER); }
+void diagon_bool_query_add_must_not(DiagonQuery b, DiagonQuery c) { add_clause(b, c, Occur::MUST_NOT); }
+void diagon_bool_query_set_minimum_should_match(DiagonQuery b, int minimum) {
+    if (!b) { set_error("bool_query is required"); return; }
+    static_cast<BooleanQuery::Builder*>(b)->setMinimumNumberShouldMatch(minimum);
+}
+DiagonQuery diagon_bool_query_build(DiagonQuery builder_handle) {
+    if (!builder_handle) { set_error("bool_query_builder is required"); return nullptr; }
+    try {
+        auto* builder = static_cast<BooleanQuery::Builder*>(builder_handle);
+        std::unique_ptr<BooleanQuery> q = builder->build();
+        delete builder;  // consumed, as in diagon_c_api.cpp:885-888
+        return static_cast<Query*>(q.release());
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+void diagon_free_query(DiagonQuery query) { delete as_query(query); }
+void diagon_free_bool_query_builder(DiagonQuery builder) { delete static_cast<BooleanQuery::Builder*>(builder); }
+
+int64_t diagon_top_docs_total_hits(DiagonTopDocs t) {
+    if (!t) { set_error("Invalid top_docs"); return -1; }
+    return static_cast<TopDocs*>(t)->totalHits.value;
+}
+float diagon_top_docs_max_score(DiagonTopDocs t) {
+    if (!t) { set_error("Invalid top_docs"); return 0.0f; }
+    return static_cast<TopDocs*>(t)->maxScore;
+}
+int diagon_top_docs_score_docs_length(DiagonTopDocs t) {
+    if (!t) { set_error("Invalid top_docs"); return -1; }
+    return static_cast<int>(static_cast<TopDocs*>(t)->scoreDocs.size());
+}
+DiagonScoreDoc diagon_top_docs_score_doc_at(DiagonTopDocs t, int index) {
+    if (!t) { set_error("Invalid top_docs"); return nullptr; }
+    auto& docs = static_cast<TopDocs*>(t)->scoreDocs;
+    if (index < 0 || index >= static_cast<int>(docs.size())) { set_error("Index out of bounds"); return nullptr; }
+    return &docs[static_cast<size_t>(index)];
+}
+int diagon_score_doc_get_doc(DiagonScoreDoc d) {
+    if (!d) { set_error("Invalid score_doc"); return -1; }
+    return static_cast<ScoreDoc*>(d)->doc;
+}
+float diagon_score_doc_get_score(DiagonScoreDoc d) {
+    if (!d) { set_error("Invalid score_doc"); return 0.0f; }
+    return static_cast<ScoreDoc*>(d)->score;
+}
+void diagon_free_top_docs(DiagonTopDocs t) { delete static_cast<TopDocs*>(t); }
+
+// ------------------------------------------------------------------ Part 2
+DgpuIndexBuilder dgpu_builder_create(void) {
+    try {
+        return new IndexBuilder();
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+void dgpu_builder_free(DgpuIndexBuilder b) { delete static_cast<IndexBuilder*>(b); }
+
+int dgpu_builder_add_segment(DgpuIndexBuilder b, int32_t max_doc, int32_t doc_base, int32_t is_local) {
+    if (!b) { set_error("Invalid builder"); return -1; }
+    try {
+        return static_cast<IndexBuilder*>(b)->add_segment(max_doc, doc_base, is_local != 0);
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+int dgpu_builder_set_field_stats(DgpuIndexBuilder b, int segment, const char* field, int64_t sum_ttf, int64_t sum_df,
+                                 int32_t doc_count, const int8_t* norms) {
+    if (!b || !field) { set_error("Invalid builder or field"); return -1; }
+    try {
+        static_cast<IndexBuilder*>(b)->set_field_stats(segment, field, sum_ttf, sum_df, doc_count, norms);
+        return 0;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+int dgpu_builder_add_term(DgpuIndexBuilder b, int segment, const char* field, const uint8_t* term, int32_t term_len,
+                          int32_t doc_freq, int64_t ttf, const int32_t* docs, const int32_t* freqs) {
+    if (!b || !field || !term) { set_error("Invalid builder, field or term"); return -1; }
+    try {
+        static_cast<IndexBuilder*>(b)->add_term(segment, field, term, static_cast<size_t>(term_len), doc_freq, ttf, docs, freqs);
+        return 0;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+int dgpu_builder_add_numeric_doc_values(DgpuIndexBuilder b, int segment, const char* field, const int64_t* values) {
+    if (!b || !field || !values) { set_error("Invalid builder, field or values"); return -1; }
+    try {
+        static_cast<IndexBuilder*>(b)->add_numeric_doc_values(segment, field, values);
+        return 0;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+DiagonIndexReader dgpu_builder_finish(DgpuIndexBuilder b, int device) {
+    if (!b) { set_error("Invalid builder"); return nullptr; }
+    try {
+        auto ix = static_cast<IndexBuilder*>(b)->finish();
+        return new IndexReader(ix, device);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+DiagonIndexReader dgpu_open_dump(const char* path, int device, int seg_lo, int seg_hi) {
+    if (!path) { set_error("Invalid path"); return nullptr; }
+    try {
+        return new IndexReader(load_dump(path, seg_lo, seg_hi), device);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+static synth::CorpusSpec to_spec(const dgpu_corpus_spec& s) {
+    synth::CorpusSpec c;
+    c.seed = s.seed; c.num_docs = s.num_docs; c.vocab = s.vocab; c.zipf_s = s.zipf_s; c.len_mu = s.len_mu;
+    c.len_sigma = s.len_sigma; c.len_min = s.len_min; c.len_max = s.len_max; c.num_segments = s.num_segments;
+    c.with_price = s.with_price != 0;
+    return c;
+}
+
+int dgpu_named_corpus(const char* name, double scale, dgpu_corpus_spec* out) {
+    if (!name || !out) { set_error("Invalid arguments"); return -1; }
+    synth::CorpusSpec c = synth::named_corpus(name, scale);
+    if (c.num_docs == 0) { set_error(std::string("unknown corpus ") + name); return -1; }
+    out->seed = c.seed; out->num_docs = c.num_docs; out->vocab = c.vocab; out->zipf_s = c.zipf_s; out->len_mu = c.len_mu;
+    out->len_sigma = c.len_sigma; out->len_min = c.len_min; out->len_max = c.len_max; out->num_segments = c.num_segments;
+    out->with_price = c.with_price ? 1 : 0;
+    return 0;
+}
+
+int dgpu_write_synthetic_dump(const dgpu_corpus_spec* spec, const char* path) {
+    if (!spec || !path) { set_error("Invalid arguments"); return -1; }
+    try {
+        write_synthetic_dump(to_spec(*spec), path);
+        return 0;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+char* dgpu_query_log_text(const char* config, uint32_t vocab, uint32_t num_queries, const char* kind, int64_t* out_len) {
+    if (!config || !kind) { set_error("Invalid arguments"); return nullptr; }
+    try {
+        synth::QueryLogSpec qs = synth::named_query_log(config, vocab, num_queries);
+        if (qs.num_queries == 0) { set_error(std::string("unknown query log ") + config); return nullptr; }
+        synth::QueryLog log = synth::make_query_log(qs);
+        std::string out;
+        out.reserve(static_cast<size_t>(log.size()) * (16 + 9 * log.terms_per_query));
+        for (uint32_t q = 0; q < log.size(); ++q) {
+            out += kind;
+            if (qs.with_range) {
+                out += ' ';
+                out += std::to_string(log.range_lo[q]);
+                out += ' ';
+                out += std::to_string(log.range_hi[q]);
+            }
+            const uint32_t* r = log.query(q);
+            for (uint32_t t = 0; t < log.terms_per_query; ++t) {
+                out += ' ';
+                out += synth::term_text(r[t]);
+            }
+            out += '\n';
+        }
+        char* buf = static_cast<char*>(std::malloc(out.size() + 1));
+        if (!buf) { set_error("out of memory"); return nullptr; }
+        std::memcpy(buf, out.data(), out.size());
+        buf[out.size()] = 0;
+        if (out_len) *out_len = static_cast<int64_t>(out.size());
+        return buf;
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+void dgpu_free_text(char* text) { std::free(text); }
+
+DiagonIndexReader dgpu_open_synthetic(const dgpu_corpus_spec* spec, int device, int seg_lo, int seg_hi) {
+    if (!spec) { set_error("Invalid spec"); return nullptr; }
+    try {
+        return new IndexReader(build_synthetic(to_spec(*spec), seg_lo, seg_hi), device);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+int64_t dgpu_reader_num_terms(DiagonIndexReader r) {
+    if (!r) { set_error("Invalid reader"); return -1; }
+    return as_reader(r)->index().dict.size();
+}
+int dgpu_reader_get_doc_freqs(DiagonIndexReader r, int64_t* out, int64_t n) {
+    if (!r || !out) { set_error("Invalid arguments"); return -1; }
+    auto& df = as_reader(r)->index().term_doc_freq;
+    if (n != static_cast<int64_t>(df.size())) { set_error("size mismatch"); return -1; }
+    std::memcpy(out, df.data(), df.size() * sizeof(int64_t));
+    return 0;
+}
+int dgpu_reader_set_doc_freqs(DiagonIndexReader r, const int64_t* in, int64_t n) {
+    if (!r || !in) { set_error("Invalid arguments"); return -1; }
+    auto& df = as_reader(r)->index().term_doc_freq;
+    if (n != static_cast<int64_t>(df.size())) { set_error("size mismatch"); return -1; }
+    std::memcpy(df.data(), in, df.size() * sizeof(int64_t));
+    return 0;
+}
+int dgpu_reader_get_field_totals(DiagonIndexReader r, const char* field, int64_t* sum_ttf, int64_t* max_doc) {
+    if (!r || !field) { set_error("Invalid arguments"); return -1; }
+    auto& ix = as_reader(r)->index();
+    int f = ix.field_id(field);
+    if (f < 0) { set_error("unknown field"); return -1; }
+    int64_t s = 0, m = 0;
+    for (size_t i = 0; i < ix.segments.size(); ++i) {
+        if (!ix.segments[i].is_local) continue;
+        const auto& fs = ix.field_stats[i][static_cast<size_t>(f)];
+        if (fs.has_terms && fs.sum_total_term_freq > 0) s += fs.sum_total_term_freq;
+        m += ix.segments[i].max_doc;
+    }
+    *sum_ttf = s;
+    *max_doc = m;
+    return 0;
+}
+int dgpu_reader_set_field_totals(DiagonIndexReader r, const char* field, int64_t sum_ttf, int64_t max_doc_total) {
+    if (!r || !field) { set_error("Invalid arguments"); return -1; }
+    try {
+        auto* rd = as_reader(r);
+        auto& ix = rd->index();
+        int f = ix.field_id(field);
+        if (f < 0) { set_error("unknown field"); return -1; }
+        ix.set_global_stats(f, sum_ttf, max_doc_total);
+        // the k table depends on avgdl: refresh the device copy
+        if (dgpu_engine_set_ktab(rd->engine(), ix.image.ktab.data(), ix.image.n_fields) != 0) {
+            set_error(dgpu_engine_last_error());
+            return -1;
+        }
+        return 0;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+int64_t dgpu_reader_image_bytes(DiagonIndexReader r) {
+    if (!r) { set_error("Invalid reader"); return -1; }
+    auto& im = as_reader(r)->index().image;
+    return static_cast<int64_t>(im.data.size() + 16 * im.block_first_doc.size());
+}
+int64_t dgpu_reader_num_postings(DiagonIndexReader r) {
+    if (!r) { set_error("Invalid reader"); return -1; }
+    auto& im = as_reader(r)->index().image;
+    int64_t n = 0;
+    for (uint32_t m : im.block_meta) n += (m & 0xFF) + 1;
+    return n;
+}
+void* dgpu_reader_engine(DiagonIndexReader r) { return r ? as_reader(r)->engine() : nullptr; }
+
+int64_t dgpu_reader_decode_term(DiagonIndexReader r, const char* field, const uint8_t* term, int32_t term_len,
+                                int32_t* out_docs, int32_t* out_freqs, int64_t capacity) {
+    if (!r || !field || !term) { set_error("Invalid arguments"); return -1; }
+    try {
+        auto* rd = as_reader(r);
+        auto& ix = rd->index();
+        int f = ix.field_id(field);
+        if (f < 0) return 0;
+        uint32_t id = ix.dict.find(static_cast<uint16_t>(f), term, static_cast<size_t>(term_len));
+        if (id == TermDictionary::kNotFound) return 0;
+        int64_t n = 0;
+        for (uint32_t b = ix.image.term_block_start[id]; b < ix.image.term_block_start[id + 1]; ++b)
+            n += (ix.image.block_meta[b] & 0xFF) + 1;
+        if (!out_docs || !out_freqs) return n;
+        if (capacity < n) { set_error("capacity too small"); return -1; }
+        uint64_t offs[2];
+        if (dgpu_engine_decode_terms(rd->engine(), &id, 1, out_docs, out_freqs, offs, nullptr) != 0) {
+            set_error(dgpu_engine_last_error());
+            return -1;
+        }
+        return n;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+int dgpu_search_batch(DiagonIndexSearcher searcher, const DiagonQuery* queries, int32_t n, int32_t k, int32_t* out_docs,
+                      float* out_scores, int32_t* out_counts, int64_t* out_total_hits) {
+    if (!searcher || (n > 0 && !queries)) { set_error("Invalid searcher or queries"); return -1; }
+    try {
+        std::vector<const Query*> qs(static_cast<size_t>(n));
+        for (int32_t i = 0; i < n; ++i) {
+            if (!queries[i]) { set_error("NULL query in batch"); return -1; }
+            qs[static_cast<size_t>(i)] = as_query(queries[i]);
+        }
+        return run_batch(*as_searcher(searcher), qs, k, out_docs, out_scores, out_counts, out_total_hits);
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
+                           float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
+    if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
+    try {
+        auto parsed = parse_batch(text, text_len);
+        if (static_cast<int64_t>(parsed.size()) > max_queries) { set_error("more queries than max_queries"); return -1; }
+        std::vector<const Query*> qs;
+        qs.reserve(parsed.size());
+        for (auto& q : parsed) qs.push_back(q.get());
+        return run_batch(*as_searcher(searcher), qs, k, out_docs, out_scores, out_counts, out_total_hits);
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats) {
+    if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
+    try {
+        auto parsed = parse_batch(text, text_len);
+        std::vector<const Query*> qs;
+        for (auto& q : parsed) qs.push_back(q.get());
+        CompiledBatch batch;
+        compile_all(*as_searcher(searcher), qs, batch);
+        dgpu_query_batch view = batch.view();
+        auto* rd = &as_searcher(searcher)->getIndexReader();
+        if (dgpu_engine_stage_batch(rd->engine(), &view, k) != 0) { set_error(dgpu_engine_last_error()); return -1; }
+        if (out_stats) {
+            out_stats[0] = static_cast<int64_t>(batch.queries.size());
+            out_stats[1] = static_cast<int64_t>(batch.algorithmic_bytes);
+            int64_t postings = 0;
+            auto& im = rd->index().image;
+            for (auto& t : batch.terms)
+                for (uint32_t b = im.term_block_start[t.term_id]; b < im.term_block_start[t.term_id + 1]; ++b)
+                    postings += (im.block_meta[b] & 0xFF) + 1;
+            out_stats[2] = postings;
+        }
+        return static_cast<int>(batch.queries.size());
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+DiagonQuery dgpu_parse_query(const char* line) {
+    if (!line) { set_error("Invalid line"); return nullptr; }
+    try {
+        return parse_query_line(line).release();
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Host-side view of an index that has been (or is being) uploaded to one GPU.
+//
+// Mirrors what the reference's read side gives the search layer — segments (leaves) with docBase,
+// per-field collection statistics, a term dictionary with docFreq/totalTermFreq, norms, numeric doc
+// values (/root/reference/src/core/include/diagon/index/IndexReader.h:119-141, :239-312;
+// LeafReaderContext.h:26-52) — but keeps only what query compilation needs on the host; postings,
+// fused norms and doc-values columns go to the device image.
+//
+// Segments may be "remote" (is_local = false): their postings live on another GPU of the box, but their
+// statistics still count, because the reference computes idf/avgdl over ALL leaves
+// (src/search/TermQuery.cpp:195-247).
+#pragma once
+
+#include "index_image.h"
+#include "synth_corpus.h"
+
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace dgpu {
+
+struct FieldSegmentStats {
+    bool has_terms = false;
+    int64_t sum_total_term_freq = -1;
+    int64_t sum_doc_freq = -1;
+    int32_t doc_count = 0;
+};
+
+struct SegmentMeta {
+    int32_t max_doc = 0;
+    int32_t doc_base = 0;
+    bool is_local = true;
+};
+
+// Open-addressing term dictionary: (field id, term bytes) -> dense term id.
+class TermDictionary {
+public:
+    static constexpr uint32_t kNotFound = 0xFFFFFFFFu;
+    uint32_t find(uint16_t field, const uint8_t* bytes, size_t len) const;
+    uint32_t find_or_add(uint16_t field, const uint8_t* bytes, size_t len);
+    uint32_t size() const { return static_cast<uint32_t>(offsets_.size()); }
+    void reserve(size_t n_terms);
+    std::string term_bytes(uint32_t id) const;
+    uint16_t term_field(uint32_t id) const { return fields_[id]; }
+
+private:
+    static uint64_t hash(uint16_t field, const uint8_t* bytes, size_t len);
+    void grow();
+    std::vector<uint32_t> slots_;      // term id + 1, 0 = empty
+    std::vector<uint64_t> offsets_;    // into pool_
+    std::vector<uint32_t> lengths_;
+    std::vector<uint16_t> fields_;
+    std::vector<uint8_t> pool_;
+};
+
+class HostIndex {
+public:
+    // ---- logical content (filled by IndexBuilder / SyntheticIndexSource)
+    std::vector<std::string> fields;
+    std::vector<SegmentMeta> segments;
+    std::vector<std::vector<FieldSegmentStats>> field_stats;  // [segment][field]
+    std::vector<std::string> dv_names;
+    TermDictionary dict;
+    std::vector<int64_t> term_doc_freq;        // GLOBAL docFreq (sum over all leaves)
+    std::vector<int64_t> term_total_term_freq;
+    int64_t max_doc_total = 0;                 // IndexReader::maxDoc() over all leaves
+    IndexImage image;                          // local postings, device layout
+
+    int field_id(const std::string& name) const;
+    int dv_id(const std::string& name) const;
+
+    // Statistics exactly as TermWeight::createScorer derives them (TermQuery.cpp:184-260).
+    float avg_field_length(int field) const;
+    float idf_for(uint32_t term_id, float boost) const;          // term present somewhere
+    float idf_for_missing(float boost) const;                     // df == 0 fallback (:250-253)
+
+    // Overrides for sharded synthetic corpora, where each rank only generates its own documents and
+    // the global numbers come from an all-reduce (bench.py).
+    void set_global_stats(int field, int64_t sum_total_term_freq, int64_t max_doc_total_);
+
+    void finalize_tables();  // ktab per field from avgdl
+
+    // Algorithmic bytes of one term's posting list in the device layout (roofline accounting).
+    uint64_t term_encoded_bytes(uint32_t term_id) const {
+        return term_id < image.term_bytes.size() ? image.term_bytes[term_id] : 0;
+    }
+
+private:
+    std::vector<int64_t> global_sum_ttf_override_;  // per field, -1 = none
+};
+
+// Collects segments / terms handed over by an index reader (the reference's DirectoryReader through
+// the DGPUDMP1 interchange file, or any caller of the dgpu_builder_* C ABI) and produces a HostIndex.
+class IndexBuilder {
+public:
+    IndexBuilder();
+    ~IndexBuilder();
+    int add_segment(int32_t max_doc, int32_t doc_base, bool is_local);
+    void set_field_stats(int seg, const std::string& field, int64_t sum_ttf, int64_t sum_df,
+                         int32_t doc_count, const int8_t* norms /* max_doc bytes or null */);
+    // docs == nullptr: statistics only (remote segment).
+    void add_term(int seg, const std::string& field, const uint8_t* term, size_t term_len, int32_t doc_freq,
+                  int64_t total_term_freq, const int32_t* docs, const int32_t* freqs);
+    void add_numeric_doc_values(int seg, const std::string& name, const int64_t* values);
+    std::shared_ptr<HostIndex> finish(int threads = 0);
+
+private:
+    struct Impl;
+    std::unique_ptr<Impl> impl_;
+};
+
+// Loads a DGPUDMP1 interchange file (written by oracle/ref_driver export from the reference's own
+// DirectoryReader). Segments [seg_lo, seg_hi) are local, the others contribute statistics only.
+std::shared_ptr<HostIndex> load_dump(const std::string& path, int seg_lo = 0, int seg_hi = -1, int threads = 0);
+
+// Builds the postings of a synthetic corpus directly (no text, no reference indexer). Documents of
+// segments [seg_lo, seg_hi) are generated and encoded; df/ttf of the local range are returned in the
+// HostIndex and must be completed with set_global_stats / add_remote_doc_freq when other ranks hold
+// the rest of the corpus.
+std::shared_ptr<HostIndex> build_synthetic(const synth::CorpusSpec& spec, int seg_lo = 0, int seg_hi = -1,
+                                           int threads = 0);
+
+// Writes the synthetic corpus as a DGPUDMP1 file (segment-local doc ids, norms from encode_norm, the
+// statistics the reference's .tmd would hold) without going through any indexer. Test sizes only: the
+// whole corpus is held in memory term-major.
+void write_synthetic_dump(const synth::CorpusSpec& spec, const std::string& path);
+
+void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& body);
+
+}  // namespace dgpu

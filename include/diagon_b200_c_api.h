@@ -1,0 +1,148 @@
+/* diagon_b200_c_api.h — the reference-facing C ABI of libdiagon_b200.so.
+ *
+ * Part 1 re-exports, with the SAME names, signatures, ownership and error conventions, the subset of
+ * the reference's CGO bridge that sits on the query path
+ * (/root/reference/src/core/include/diagon/c_api/diagon_c_api.h — line numbers given per function), so
+ * a Go/CGO caller that today binds diagon_search() can bind this library instead for TermQuery /
+ * BooleanQuery / NumericRangeQuery searches. Handles are opaque void*; every create/open/search
+ * returns an object the caller releases with the matching free/close; on failure functions return
+ * NULL / -1 / false and diagon_last_error() holds a thread-local message (diagon_c_api.cpp:44-62).
+ *
+ * Part 2 (dgpu_*) is what the reference has no equivalent for: handing a segment's postings to the
+ * GPU once (upload), and scoring a whole batch of queries in one call.
+ */
+#ifndef DIAGON_B200_C_API_H
+#define DIAGON_B200_C_API_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* DiagonIndexReader;
+typedef void* DiagonIndexSearcher;
+typedef void* DiagonQuery;
+typedef void* DiagonTopDocs;
+typedef void* DiagonScoreDoc;
+typedef void* DiagonTerm;
+
+/* ------------------------------------------------------------------ Part 1: mirrored entry points */
+const char* diagon_last_error(void);                                   /* diagon_c_api.h:48 */
+void diagon_clear_error(void);                                         /* :53 */
+
+int64_t diagon_reader_num_docs(DiagonIndexReader reader);              /* :328 */
+int64_t diagon_reader_max_doc(DiagonIndexReader reader);               /* :335 */
+int diagon_reader_get_segment_count(DiagonIndexReader reader);         /* :612 */
+void diagon_close_index_reader(DiagonIndexReader reader);              /* :340 */
+
+DiagonIndexSearcher diagon_create_index_searcher(DiagonIndexReader reader);            /* :349 */
+DiagonTopDocs diagon_search(DiagonIndexSearcher searcher, DiagonQuery query, int num_hits); /* :358 */
+int diagon_count(DiagonIndexSearcher searcher, DiagonQuery query);                     /* :368 */
+void diagon_free_index_searcher(DiagonIndexSearcher searcher);                         /* :373 */
+
+DiagonTerm diagon_create_term(const char* field, const char* text);    /* :383 */
+void diagon_free_term(DiagonTerm term);                                /* :388 */
+DiagonQuery diagon_create_term_query(DiagonTerm term);                 /* :395 */
+/* :412 — like the reference, the double arguments are bit-cast to int64 (diagon_c_api.cpp:718-723);
+ * use dgpu_create_long_range_query for LONG columns. */
+DiagonQuery diagon_create_numeric_range_query(const char* field_name, double lower_value, double upper_value,
+                                              bool include_lower, bool include_upper);
+DiagonQuery diagon_create_bool_query(void);                            /* :452 (returns a builder) */
+void diagon_bool_query_add_must(DiagonQuery bool_query, DiagonQuery clause);       /* :460 */
+void diagon_bool_query_add_should(DiagonQuery bool_query, DiagonQuery clause);     /* :468 */
+void diagon_bool_query_add_filter(DiagonQuery bool_query, DiagonQuery clause);     /* :476 */
+void diagon_bool_query_add_must_not(DiagonQuery bool_query, DiagonQuery clause);   /* :484 */
+void diagon_bool_query_set_minimum_should_match(DiagonQuery bool_query, int minimum); /* :492 */
+DiagonQuery diagon_bool_query_build(DiagonQuery bool_query_builder);   /* :500 */
+void diagon_free_query(DiagonQuery query);                             /* :505 */
+void diagon_free_bool_query_builder(DiagonQuery builder);              /* :513 */
+
+int64_t diagon_top_docs_total_hits(DiagonTopDocs top_docs);            /* :522 */
+float diagon_top_docs_max_score(DiagonTopDocs top_docs);               /* :529 */
+int diagon_top_docs_score_docs_length(DiagonTopDocs top_docs);         /* :536 */
+DiagonScoreDoc diagon_top_docs_score_doc_at(DiagonTopDocs top_docs, int index); /* :544 (borrowed) */
+int diagon_score_doc_get_doc(DiagonScoreDoc score_doc);                /* :551 */
+float diagon_score_doc_get_score(DiagonScoreDoc score_doc);            /* :558 */
+void diagon_free_top_docs(DiagonTopDocs top_docs);                     /* :563 */
+
+/* ------------------------------------------------------------------ Part 2: GPU-side additions */
+typedef void* DgpuIndexBuilder;
+
+/* Upload path. A reader-side integration walks its leaves once (terms(field)->iterator(), next(),
+ * docFreq(), totalTermFreq(), postings(), getNormValues()->normsData(), getNumericDocValues()) and
+ * hands every segment here; dgpu_builder_finish encodes the device layout, uploads it to `device` and
+ * returns a DiagonIndexReader usable with diagon_create_index_searcher. Segments must be added in
+ * docBase order. is_local = 0 marks a segment whose postings live on another GPU: only its statistics
+ * are recorded (pass docs = NULL in dgpu_builder_add_term). */
+DgpuIndexBuilder dgpu_builder_create(void);
+void dgpu_builder_free(DgpuIndexBuilder b);
+int dgpu_builder_add_segment(DgpuIndexBuilder b, int32_t max_doc, int32_t doc_base, int32_t is_local);
+int dgpu_builder_set_field_stats(DgpuIndexBuilder b, int segment, const char* field, int64_t sum_total_term_freq,
+                                 int64_t sum_doc_freq, int32_t doc_count, const int8_t* norms);
+int dgpu_builder_add_term(DgpuIndexBuilder b, int segment, const char* field, const uint8_t* term, int32_t term_len,
+                          int32_t doc_freq, int64_t total_term_freq, const int32_t* docs, const int32_t* freqs);
+int dgpu_builder_add_numeric_doc_values(DgpuIndexBuilder b, int segment, const char* field, const int64_t* values);
+DiagonIndexReader dgpu_builder_finish(DgpuIndexBuilder b, int device);
+
+/* Opens a DGPUDMP1 interchange file (oracle/ref_driver export of a reference index); segments
+ * [seg_lo, seg_hi) are uploaded, the rest contribute statistics (seg_hi < 0: all). */
+DiagonIndexReader dgpu_open_dump(const char* path, int device, int seg_lo, int seg_hi);
+
+/* Synthetic corpora of BASELINE.json, built without text or indexer. */
+typedef struct {
+    uint64_t seed;
+    uint32_t num_docs, vocab;
+    double zipf_s, len_mu, len_sigma;
+    uint32_t len_min, len_max, num_segments;
+    int32_t with_price;
+} dgpu_corpus_spec;
+int dgpu_named_corpus(const char* name, double scale, dgpu_corpus_spec* out);
+int dgpu_write_synthetic_dump(const dgpu_corpus_spec* spec, const char* path);   /* DGPUDMP1, test sizes */
+/* Query log of a named configuration as text lines (caller frees with dgpu_free_text). kind: the
+ * line prefix to emit, e.g. "OR body 0", "AND body", "TERM body", "ORF body price" (then lo hi). */
+char* dgpu_query_log_text(const char* config, uint32_t vocab, uint32_t num_queries, const char* kind, int64_t* out_len);
+void dgpu_free_text(char* text);
+DiagonIndexReader dgpu_open_synthetic(const dgpu_corpus_spec* spec, int device, int seg_lo, int seg_hi);
+
+/* Statistics plumbing for sharded indexes (all ranks must agree on idf/avgdl). */
+int64_t dgpu_reader_num_terms(DiagonIndexReader reader);
+int dgpu_reader_get_doc_freqs(DiagonIndexReader reader, int64_t* out, int64_t n);           /* global df per term id */
+int dgpu_reader_set_doc_freqs(DiagonIndexReader reader, const int64_t* df, int64_t n);
+int dgpu_reader_get_field_totals(DiagonIndexReader reader, const char* field, int64_t* sum_total_term_freq, int64_t* max_doc);
+int dgpu_reader_set_field_totals(DiagonIndexReader reader, const char* field, int64_t sum_total_term_freq, int64_t max_doc_total);
+int64_t dgpu_reader_image_bytes(DiagonIndexReader reader);   /* device bytes of postings payloads + headers */
+int64_t dgpu_reader_num_postings(DiagonIndexReader reader);
+void* dgpu_reader_engine(DiagonIndexReader reader);           /* dgpu_engine* of dgpu_engine.h */
+
+/* Decoded postings of one term (K1), for parity against the reference's PostingsEnum.
+ * Returns the docFreq held on this GPU, or -1. Pass NULL arrays to query the size. */
+int64_t dgpu_reader_decode_term(DiagonIndexReader reader, const char* field, const uint8_t* term, int32_t term_len,
+                                int32_t* out_docs, int32_t* out_freqs, int64_t capacity);
+
+/* Batched search. `queries` is an array of DiagonQuery handles. Results land in caller-owned HOST
+ * arrays: out_docs/out_scores [n * k] (best first, unused slots doc = -1), out_counts[n],
+ * out_total_hits[n]. One engine launch scores the whole batch. */
+int dgpu_search_batch(DiagonIndexSearcher searcher, const DiagonQuery* queries, int32_t n, int32_t k,
+                      int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total_hits);
+
+/* Same, from the text form shared with oracle/ref_driver.cpp: one query per line, e.g.
+ * "OR body 0 t0000105 t0000140", "AND body t1 t2", "TERM body t1", "ORF body price 10 99 t1 t2 t3".
+ * Parsing, dictionary lookups, weight creation, H2D, kernels and D2H all happen inside the call. */
+int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k,
+                           int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
+                           int32_t max_queries);
+
+/* Compiles a text batch and keeps it staged on the device (for kernel-only timing and multi-GPU runs).
+ * out_stats: [0] queries, [1] algorithmic posting bytes of the batch, [2] postings of the batch. */
+int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats);
+
+DiagonQuery dgpu_create_long_range_query(const char* field, int64_t lower, int64_t upper, bool include_lower, bool include_upper);
+DiagonQuery dgpu_parse_query(const char* line);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
