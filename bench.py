@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — BM25 top-k queries/sec of the B200 engine on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2] [--scale S]
+
+One "step" = one pass of the hot path over one batch of synthetic queries (C2: 10,000 OR-10 queries,
+top-10, MS-MARCO-passage-shaped corpus of 8,841,823 docs in 8 segments). Prints ONE JSON line:
+
+  value     whole-job queries/s with the batch already staged on the device (kernels only; for N > 1 also the
+            NCCL all-gather of the local top-k and the device merge), CUDA events, max over ranks
+  e2e       the same through the reference-facing C ABI with HOST buffers: query text in host memory ->
+            dgpu_search_batch_text (parse, dictionary lookups, weights, H2D, kernels, D2H) -> host arrays
+  roofline  algorithmic posting bytes of the batch / device time of the search kernel, against the measured
+            HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, its own IndexSearcher) timed on this box's host cores on
+            a bounded sample of the same workload (rank 0, N == 1 only)
+
+--impl reference times only the reference arm and prints the same line shape with "impl": "reference".
+Nothing here reads /root/reference; the reference binaries come prebuilt in oracle/_ref.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (corpus, query log, line prefix, k, default batch)
+    "C2": ("C2", "C2", "OR body 0", 10, 10000),
+    "C3-AND2": ("C2", "C3-AND2", "AND body", 10, 10000),
+    "C3-AND4": ("C2", "C3-AND4", "AND body", 10, 10000),
+    "C4": ("C4", "C4", "ORF body price", 100, 10000),
+    "C5": ("C5", "C5", "OR body 0", 1000, 1000),
+    "C1": ("C1", "C1", "OR body 0", 10, 1000),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="corpus scale (1.0 = the named configuration)")
+    ap.add_argument("--queries", type=int, default=0, help="queries per batch (0 = the named batch size)")
+    ap.add_argument("--log2-window", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--cpu-sample-docs", type=int, default=200000)
+    ap.add_argument("--cpu-sample-queries", type=int, default=400)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def host_has_avx2():
+    try:
+        return " avx2 " in open("/proc/cpuinfo").read()
+    except Exception:
+        return False
+
+
+def reference_arm(args, corpus_name, log_name, kind, k, steps, warmup):
+    """Times the reference's own IndexSearcher (oracle/_ref) on a bounded sample of the workload: the first
+    `cpu_sample_docs` documents of the corpus indexed by its own IndexWriter, the first `cpu_sample_queries`
+    queries of the log, all host threads (one DirectoryReader + IndexSearcher per thread)."""
+    import diagon_b200 as dg
+
+    fast = os.path.join(ROOT, "oracle", "_ref", "ref_driver_fast")
+    plain = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    driver = fast if (host_has_avx2() and os.path.exists(fast)) else plain
+    if not os.path.exists(driver):
+        return None
+    spec = dg.named_corpus(corpus_name, args.scale)
+    docs = min(args.cpu_sample_docs, spec.num_docs)
+    nq = args.cpu_sample_queries
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    tmp = tempfile.mkdtemp(prefix="dgpu_ref_")
+    try:
+        idx = os.path.join(tmp, "idx")
+        cmd = [driver, "index", "--corpus", corpus_name, "--scale", str(args.scale), "--last-doc", str(docs),
+               "--segments", "1", "--dir", idx]
+        if corpus_name == "C4":
+            cmd += ["--price", "1"]
+        t0 = time.time()
+        subprocess.run(cmd, check=True, capture_output=True, text=True)
+        index_s = time.time() - t0
+        text = dg.query_log_text(log_name, spec.vocab, nq, kind)
+        qfile = os.path.join(tmp, "q.txt")
+        with open(qfile, "wb") as f:
+            f.write(text)
+        out = {}
+        for mode, wand in (("exhaustive", 0), ("default", 1)):
+            r = subprocess.run([driver, "search", "--dir", idx, "--queries", qfile, "--k", str(k), "--wand", str(wand),
+                                "--threads", str(threads), "--warmup", str(max(1, min(warmup, 1))), "--repeat", str(max(1, steps))],
+                               check=True, capture_output=True, text=True)
+            out[mode] = json.loads(r.stdout.strip().split("\n")[-1])
+        frac = docs / spec.num_docs
+        return {
+            "value": out["exhaustive"]["qps"], "unit": "queries/s", "cores": threads, "kind": "reference",
+            "sample": (f"reference IndexSearcher ({os.path.basename(driver)}), first {docs} of {spec.num_docs} docs "
+                       f"({100 * frac:.2f}% of the corpus, 1 segment, indexed in {index_s:.1f}s by its own IndexWriter), "
+                       f"first {nq} queries x {max(1, steps)} passes, {threads} threads each with its own reader+searcher, "
+                       f"exhaustive mode (enable_block_max_wand=false, same work as the GPU engine)"),
+            "default_mode_qps": out["default"]["qps"],
+            "corpus_fraction": frac,
+            "exhaustive_qps_scaled_to_full_corpus": out["exhaustive"]["qps"] * frac,
+        }
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    corpus_name, log_name, kind, k, batch = WORKLOADS[args.workload]
+    if args.queries:
+        batch = args.queries
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        base = reference_arm(args, corpus_name, log_name, kind, k, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "bm25_topk_queries_per_sec", "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {corpus_name} corpus scale {args.scale}, {kind.split()[0]}-{log_name} top-{k}"}}
+        if base is None:
+            line["unavailable"] = "oracle/_ref/ref_driver missing (run make -C oracle ref in the build container)"
+        else:
+            line.update({"value": base["value"], "ms_per_step": None, "cpu_baseline": base,
+                         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line))
+        return 0
+
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import diagon_b200 as dg
+    from diagon_b200 import _lib
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device: diagon_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = _lib.load()
+    spec = dg.named_corpus(corpus_name, args.scale)
+    nseg = spec.num_segments
+    seg_lo, seg_hi = nseg * rank // world, nseg * (rank + 1) // world
+    t0 = time.time()
+    reader = dg.IndexReader.synthetic(spec, local_rank, seg_lo, seg_hi)
+    build_s = time.time() - t0
+    if args.log2_window:
+        reader.set_option("log2_window", args.log2_window)
+    if args.ctas_per_sm:
+        reader.set_option("ctas_per_sm", args.ctas_per_sm)
+    if world > 1:
+        # global statistics: idf / avgdl must be identical on every rank
+        df = torch.from_numpy(reader.get_doc_freqs()).cuda()
+        dist.all_reduce(df)
+        ttf, md = reader.get_field_totals("body")
+        tot = torch.tensor([ttf, md], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        reader.set_doc_freqs(df.cpu().numpy())
+        reader.set_field_totals("body", int(tot[0]), int(tot[1]))
+    searcher = dg.IndexSearcher(reader)
+    text = dg.query_log_text(log_name, spec.vocab, batch, kind)
+    nq = text.count(b"\n")
+    stats = searcher.stage_batch_text(text, k)
+    eng = reader.engine()
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    dres = _lib.Results()
+    lib.dgpu_engine_device_results(eng, C.byref(dres))
+    if world > 1:
+        g_keys = torch.zeros((world, nq, k), dtype=torch.int64, device="cuda")
+        g_counts = torch.zeros((world, nq), dtype=torch.int32, device="cuda")
+        g_hits = torch.zeros((world, nq), dtype=torch.int64, device="cuda")
+        m_keys = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
+        m_counts = torch.zeros(nq, dtype=torch.int32, device="cuda")
+        m_hits = torch.zeros(nq, dtype=torch.int64, device="cuda")
+
+    def device_step():
+        """Kernels only (plus, for N > 1, the all-gather and the device merge). Returns nothing; async."""
+        if lib.dgpu_engine_search_staged(eng, sptr) != 0:
+            raise RuntimeError(lib.dgpu_engine_last_error().decode())
+        if world > 1:
+            # local results -> torch views over the engine's device buffers (same stream, no copy)
+            lk = _wrap(dres.keys, (nq, k), torch.int64)
+            lc = _wrap(dres.counts, (nq,), torch.int32)
+            lh = _wrap(dres.total_hits, (nq,), torch.int64)
+            dist.all_gather_into_tensor(g_keys.view(-1), lk.view(-1))
+            dist.all_gather_into_tensor(g_counts.view(-1), lc.view(-1))
+            dist.all_gather_into_tensor(g_hits.view(-1), lh.view(-1))
+            if lib.dgpu_engine_merge_parts(eng, g_keys.data_ptr(), g_counts.data_ptr(), g_hits.data_ptr(), world, nq, k,
+                                           m_keys.data_ptr(), m_counts.data_ptr(), m_hits.data_ptr(), sptr) != 0:
+                raise RuntimeError(lib.dgpu_engine_last_error().decode())
+
+    def _wrap(ptr, shape, dtype):
+        class _CAI:  # __cuda_array_interface__ view of an engine-owned device buffer
+            pass
+        o = _CAI()
+        typestr = {torch.int64: "<i8", torch.int32: "<i4"}[dtype]
+        o.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(o, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps in one timed region
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.dgpu_engine_launch_count(eng)
+    kernel_ms = []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    ev1.record(stream)
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = lib.dgpu_engine_launch_count(eng) - launches0
+    # per-kernel time of the search kernel alone (engine events around the launch), one more untimed step
+    for _ in range(3):
+        device_step()
+        barrier()
+        lib.dgpu_engine_sync(eng)
+        kernel_ms.append(lib.dgpu_engine_last_search_ms(eng))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    ms_per_step = total_ms / args.steps
+    value = nq / (ms_per_step / 1e3)
+
+    # ---- end to end through the C ABI with host buffers
+    out = searcher._alloc(nq, k)
+    e2e_times = []
+    for i in range(max(2, min(args.warmup, 3)) + args.steps):
+        barrier()
+        t1 = time.perf_counter()
+        res = searcher.search_batch_text(text, k, nq, out)
+        if world > 1:
+            device_step()          # sharded: all-gather + merge of the local top-k
+            torch.cuda.synchronize()
+            _ = m_hits.cpu()
+        t2 = time.perf_counter()
+        if i >= max(2, min(args.warmup, 3)):
+            e2e_times.append(t2 - t1)
+    e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = nq * args.steps / float(e2e_t[0])
+    clocks = sampler.stop()
+
+    # ---- roofline of the dominant kernel (search_kernel)
+    peak, peak_src = measured_peak()
+    algo = torch.tensor([stats["algorithmic_bytes"], stats["postings"]], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(algo)
+    k_ms = statistics.median(kernel_ms)
+    kt = torch.tensor([k_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    achieved = stats["algorithmic_bytes"] / (float(kt[0]) / 1e3) / 1e9  # this rank's bytes / its kernel time
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "search_kernel",
+                "kernel_ms": float(kt[0]), "algorithmic_bytes_per_launch": stats["algorithmic_bytes"],
+                "postings_per_launch": stats["postings"],
+                "postings_per_s": stats["postings"] / (float(kt[0]) / 1e3)}
+
+    if rank == 0:
+        h2d = nq * 20 + stats["queries"] * 4 + 12 * int(text.count(b" t"))  # dgpu_query + order + dgpu_qterm
+        d2h = nq * k * 8 + nq * 4 + nq * 8
+        line = {
+            "metric": "bm25_topk_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {batch} x {kind.split()[0]}-{spec.vocab and log_name} top-{k} on the {corpus_name} "
+                                   f"synthetic corpus ({spec.num_docs} docs, vocab {spec.vocab}, {nseg} segments, scale {args.scale})",
+                       "sharding": f"{nseg} segments over {world} GPU(s), {'NCCL all-gather + device merge' if world > 1 else 'single GPU'}",
+                       "l2": "inputs larger than L2 (device image %.0f MB per GPU)" % (reader.image_bytes() / 1e6),
+                       "index_build_s": build_s, "postings_on_gpu": reader.num_postings(), "image_bytes": reader.image_bytes(),
+                       "log2_window": args.log2_window or 14},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "dgpu_search_batch_text (host text -> host results)", "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                base = reference_arm(args, corpus_name, log_name, kind, k, 1, 1)
+                if base:
+                    line["cpu_baseline"] = base
+            except Exception as e:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"error": str(e)[:300]}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

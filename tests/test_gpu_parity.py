@@ -1,0 +1,226 @@
+"""Parity of the CUDA path against the oracle and the reference's golden results. All through the C ABI."""
+import gzip
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import diagon_b200 as dg
+from diagon_b200 import api
+from oracle import oracle as orc
+from tests.util import assert_same_topdocs, read_lines, read_results
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def readers(golden_dir, tmp_path_factory):
+    out = {}
+    tmp = tmp_path_factory.mktemp("dumps")
+    for name in ("g1", "g2"):
+        raw = tmp / f"{name}.dmp"
+        with gzip.open(os.path.join(golden_dir, f"{name}.dmp.gz"), "rb") as f, open(raw, "wb") as g:
+            shutil.copyfileobj(f, g)
+        out[name] = dg.IndexReader.from_dump(str(raw), 0)
+    yield out
+    for r in out.values():
+        r.close()
+
+
+def _dump(name, g1_dump, g2_dump):
+    return g1_dump if name == "g1" else g2_dump
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+def test_decoded_postings_match_reference(readers, name, g1_dump, g2_dump):
+    """K1: every posting list decodes to exactly what the reference's PostingsEnum yielded (docBase applied)."""
+    dump = _dump(name, g1_dump, g2_dump)
+    terms = set()
+    for s in dump.segments:
+        terms |= set(s.fields["body"].terms)
+    assert len(terms) > 500
+    for t in sorted(terms):
+        want_d, want_f = [], []
+        for s in dump.segments:
+            e = s.fields["body"].terms.get(t)
+            if e is not None:
+                want_d.append(e[0] + s.doc_base)
+                want_f.append(e[1])
+        docs, freqs = readers[name].decode_term("body", t)
+        assert np.array_equal(docs, np.concatenate(want_d)), t
+        assert np.array_equal(freqs, np.concatenate(want_f)), t
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+@pytest.mark.parametrize("k", [10, 100])
+def test_search_matches_reference_golden(readers, golden_dir, name, k):
+    """diagon_search(), one query at a time, against the reference's exhaustive results: bit-exact."""
+    searcher = dg.IndexSearcher(readers[name])
+    lines = read_lines(os.path.join(golden_dir, f"{name}_queries.txt"))
+    _, ref = read_results(os.path.join(golden_dir, f"{name}_k{k}_exhaustive.res"))
+    for line, (hits, _, docs) in zip(lines, ref):
+        td = searcher.search(api.parse_line(line), k)
+        assert_same_topdocs(td.totalHits.value, [(s.doc, s.score) for s in td.scoreDocs], hits, docs, line[:70])
+        if docs:
+            assert td.maxScore == max(s for _, s in docs)
+        else:
+            assert np.isnan(td.maxScore)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+@pytest.mark.parametrize("log2_window", [10, 12, 14, 15])
+def test_batched_search_matches_golden_for_every_window_size(readers, golden_dir, name, log2_window):
+    """dgpu_search_batch_text: the whole query file in one launch; window size must not change any result."""
+    readers[name].set_option("log2_window", log2_window)
+    try:
+        searcher = dg.IndexSearcher(readers[name])
+        text = open(os.path.join(golden_dir, f"{name}_queries.txt"), "rb").read()
+        for k in (10, 100):
+            _, ref = read_results(os.path.join(golden_dir, f"{name}_k{k}_exhaustive.res"))
+            res = searcher.search_batch_text(text, k)
+            assert len(res.counts) == len(ref)
+            for q, (hits, _, docs) in enumerate(ref):
+                got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
+                assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
+    finally:
+        readers[name].set_option("log2_window", 14)
+
+
+def test_query_handles_batch_equals_text_batch(readers, golden_dir):
+    searcher = dg.IndexSearcher(readers["g1"])
+    lines = read_lines(os.path.join(golden_dir, "g1_queries.txt"))
+    a = searcher.search_batch([api.parse_line(l) for l in lines], 10)
+    b = searcher.search_batch_text(("\n".join(lines) + "\n").encode(), 10)
+    assert np.array_equal(a.docs, b.docs) and np.array_equal(a.scores, b.scores)
+    assert np.array_equal(a.total_hits, b.total_hits) and np.array_equal(a.counts, b.counts)
+
+
+def test_builder_abi_path_equals_dump_path(readers, golden_dir, g1_dump):
+    """Uploading through dgpu_builder_* (what a reader-side integration calls) gives the same engine."""
+    from diagon_b200.dumpfile import build_reader_from_dump
+
+    r2 = build_reader_from_dump(g1_dump, 0)
+    try:
+        text = open(os.path.join(golden_dir, "g1_queries.txt"), "rb").read()
+        a = dg.IndexSearcher(readers["g1"]).search_batch_text(text, 10)
+        b = dg.IndexSearcher(r2).search_batch_text(text, 10)
+        assert np.array_equal(a.docs, b.docs) and np.array_equal(a.scores, b.scores) and np.array_equal(a.total_hits, b.total_hits)
+        assert r2.maxDoc() == g1_dump.max_doc and r2.segment_count() == 3
+    finally:
+        r2.close()
+
+
+def test_error_behaviour(readers):
+    searcher = dg.IndexSearcher(readers["g1"])
+    q = api.or_query("body", ["t0000001", "t0000002"])
+    with pytest.raises(ValueError):      # numHits <= 0 throws (TopScoreDocCollector.cpp:49-51)
+        searcher.search(q, 0)
+    mixed = api.BooleanQuery.Builder().add(api.TermQuery(api.Term("body", "t0000001")), api.Occur.MUST) \
+        .add(api.TermQuery(api.Term("body", "t0000002")), api.Occur.SHOULD).build()
+    with pytest.raises(ValueError):      # no CPU fallback for shapes outside the supported set
+        searcher.search(mixed, 10)
+    td = searcher.search(api.TermQuery(api.Term("body", "nosuchterm")), 10)
+    assert td.totalHits.value == 0 and td.scoreDocs == [] and np.isnan(td.maxScore)
+    assert searcher.count(api.TermQuery(api.Term("body", "t0000001"))) > 0
+
+
+def test_top_k_larger_than_hits_and_large_k(readers, g1_dump):
+    ox = orc.OracleIndex(g1_dump)
+    searcher = dg.IndexSearcher(readers["g1"])
+    for line, k in (("TERM body t0000900", 100), ("OR body 0 t0000001 t0000002 t0000003", 1000),
+                    ("OR body 0 t0000001 t0000002 t0000003", 4096), ("AND body t0000001 t0000002", 2000)):
+        q = api.parse_line(line)
+        td = searcher.search(q, k)
+        h, sd, _ = ox.search(q, k)
+        assert_same_topdocs(td.totalHits.value, [(s.doc, s.score) for s in td.scoreDocs], h, sd, line)
+
+
+@pytest.fixture(scope="module")
+def synth(tmp_path_factory):
+    """C2-shaped corpus at 1% scale (88K docs, 8 segments, price column): product index + oracle view."""
+    spec = dg.named_corpus("C4", 0.01)
+    tmp = tmp_path_factory.mktemp("synth")
+    p = tmp / "c2s.dmp"
+    dg.write_synthetic_dump(spec, str(p))
+    dump = dg.read_dump(p)
+    reader = dg.IndexReader.synthetic(spec, 0)
+    yield spec, dump, reader
+    reader.close()
+
+
+@pytest.mark.parametrize("shape,kind,k", [("C2", "OR body 0", 10), ("C3-AND2", "AND body", 10), ("C3-AND4", "AND body", 10),
+                                          ("C4", "ORF body price", 100), ("C5", "OR body 0", 1000)])
+def test_named_query_shapes_on_scaled_corpus(synth, shape, kind, k):
+    """The BASELINE.json query shapes (OR-10 top-10, AND-2/4, OR-5+range top-100, OR-20 top-1000) on a scaled
+    corpus built by the synthetic path bench.py uses: bit-exact against the oracle."""
+    spec, dump, reader = synth
+    ox = orc.OracleIndex(dump)
+    text = dg.query_log_text(shape, spec.vocab, 150, kind)
+    res = dg.IndexSearcher(reader).search_batch_text(text, k)
+    lines = text.decode().strip().split("\n")
+    assert len(lines) == 150 == len(res.counts)
+    nonempty = 0
+    for q, line in enumerate(lines):
+        h, sd, _ = ox.search(api.parse_line(line), k)
+        got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
+        assert_same_topdocs(int(res.total_hits[q]), got, h, sd, line[:70])
+        nonempty += h > 0
+    assert nonempty > 10
+
+
+def test_sharded_search_and_device_merge_equal_whole(synth):
+    """Segment sharding: two readers holding 4 segments each, global statistics shared, local
+    top-k merged by the device merge kernel == one reader holding everything."""
+    import ctypes as C
+
+    import torch
+
+    from diagon_b200 import _lib
+
+    spec, dump, whole = synth
+    k = 10
+    text = dg.query_log_text("C2", spec.vocab, 200, "OR body 0")
+    want = dg.IndexSearcher(whole).search_batch_text(text, k)
+    parts = [dg.IndexReader.synthetic(spec, 0, 0, 4), dg.IndexReader.synthetic(spec, 0, 4, 8)]
+    try:
+        df = sum(p.get_doc_freqs() for p in parts)
+        totals = [p.get_field_totals("body") for p in parts]
+        for p in parts:
+            p.set_doc_freqs(df)
+            p.set_field_totals("body", sum(t[0] for t in totals), sum(t[1] for t in totals))
+        lib = _lib.load()
+        n = 200
+        keys = torch.zeros((2, n, k), dtype=torch.int64, device="cuda")
+        counts = torch.zeros((2, n), dtype=torch.int32, device="cuda")
+        hits = torch.zeros((2, n), dtype=torch.int64, device="cuda")
+        for i, p in enumerate(parts):
+            s = dg.IndexSearcher(p)
+            s.stage_batch_text(text, k)
+            assert lib.dgpu_engine_search_staged(p.engine(), None) == 0
+            assert lib.dgpu_engine_sync(p.engine()) == 0
+            r = _lib.Results()
+            lib.dgpu_engine_device_results(p.engine(), C.byref(r))
+            hk = np.zeros((n, k), dtype=np.uint64); hc = np.zeros(n, dtype=np.int32); hh = np.zeros(n, dtype=np.int64)
+            hr = _lib.Results(hk.ctypes.data, hc.ctypes.data, hh.ctypes.data)
+            assert lib.dgpu_engine_fetch_results(p.engine(), C.byref(hr)) == 0
+            keys[i] = torch.from_numpy(hk.view(np.int64)).cuda()
+            counts[i] = torch.from_numpy(hc).cuda()
+            hits[i] = torch.from_numpy(hh).cuda()
+        ok = torch.zeros((n, k), dtype=torch.int64, device="cuda")
+        oc = torch.zeros(n, dtype=torch.int32, device="cuda")
+        oh = torch.zeros(n, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        assert lib.dgpu_engine_merge_parts(parts[0].engine(), keys.data_ptr(), counts.data_ptr(), hits.data_ptr(), 2, n, k,
+                                           ok.data_ptr(), oc.data_ptr(), oh.data_ptr(), None) == 0
+        assert lib.dgpu_engine_sync(parts[0].engine()) == 0
+        mk = ok.cpu().numpy().view(np.uint64)
+        docs = (0xFFFFFFFF - (mk & 0xFFFFFFFF)).astype(np.int64)
+        assert np.array_equal(oh.cpu().numpy(), want.total_hits)
+        assert np.array_equal(oc.cpu().numpy(), want.counts)
+        for q in range(n):
+            c = int(want.counts[q])
+            assert np.array_equal(docs[q, :c], want.docs[q, :c]), q
+    finally:
+        for p in parts:
+            p.close()
