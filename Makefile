@@ -1,8 +1,8 @@
 # Builds libdiagon_b200.so (CUDA engine + C++20 host layer + C ABI) for sm_100a, in-tree.
 #   make            -> diagon_b200/libdiagon_b200.so
 #   make oracle     -> oracle/_build/liboracle.so (+ oracle/_ref when /root/reference is present)
-NVCC     ?= nvcc
-CXX      ?= g++
+NVCC     := nvcc -ccbin /usr/bin/g++
+CXX      := /usr/bin/g++
 CUDA_HOME ?= /usr/local/cuda
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v

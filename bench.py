@@ -250,7 +250,8 @@ def main():
     nq = text.count(b"\n")
     stats = searcher.stage_batch_text(text, k)
     eng = reader.engine()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream shared by the engine launches,
+    torch.cuda.set_stream(stream)         # the NCCL collectives and the timing events
     sptr = C.c_void_p(stream.cuda_stream)
 
     dres = _lib.Results()

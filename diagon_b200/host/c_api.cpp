@@ -113,6 +113,7 @@ int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, 
     std::vector<int32_t> counts(n);
     dgpu_results res{keys.data(), counts.data(), out_total_hits};
     dgpu_query_batch view = batch.view();
+    if (n && !s.getIndexReader().engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
     if (n && dgpu_engine_search(s.getIndexReader().engine(), &view, k, &res) != 0)
         throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
     unpack(keys, counts, static_cast<int32_t>(n), k, out_docs, out_scores);
@@ -412,7 +413,7 @@ int dgpu_reader_set_field_totals(DiagonIndexReader r, const char* field, int64_t
         if (f < 0) { set_error("unknown field"); return -1; }
         ix.set_global_stats(f, sum_ttf, max_doc_total);
         // the k table depends on avgdl: refresh the device copy
-        if (dgpu_engine_set_ktab(rd->engine(), ix.image.ktab.data(), ix.image.n_fields) != 0) {
+        if (rd->engine() && dgpu_engine_set_ktab(rd->engine(), ix.image.ktab.data(), ix.image.n_fields) != 0) {
             set_error(dgpu_engine_last_error());
             return -1;
         }
@@ -493,6 +494,7 @@ int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_
         compile_all(*as_searcher(searcher), qs, batch);
         dgpu_query_batch view = batch.view();
         auto* rd = &as_searcher(searcher)->getIndexReader();
+        if (!rd->engine()) { set_error("host-only reader: no GPU engine, and there is no CPU fallback"); return -1; }
         if (dgpu_engine_stage_batch(rd->engine(), &view, k) != 0) { set_error(dgpu_engine_last_error()); return -1; }
         if (out_stats) {
             out_stats[0] = static_cast<int64_t>(batch.queries.size());

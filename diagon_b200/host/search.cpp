@@ -55,6 +55,7 @@ std::unique_ptr<Query> BooleanQuery::clone() const {
 
 // ------------------------------------------------------------------ reader
 IndexReader::IndexReader(std::shared_ptr<HostIndex> index, int device) : index_(std::move(index)) {
+    if (device < 0) return;  // host-only reader: statistics and query compilation, no engine (tests, tools)
     if (dgpu_engine_create(device, &engine_) != 0)
         throw std::runtime_error(std::string("dgpu engine: ") + dgpu_engine_last_error());
     dgpu_index_image v = index_->image.view();
@@ -219,6 +220,7 @@ std::vector<TopDocs> IndexSearcher::search(const std::vector<const Query*>& quer
     std::vector<int64_t> hits(n);
     dgpu_results res{keys.data(), counts.data(), hits.data()};
     dgpu_query_batch view = batch.view();
+    if (n && !reader_.engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
     if (n && dgpu_engine_search(reader_.engine(), &view, numHits, &res) != 0)
         throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
     std::vector<TopDocs> out;

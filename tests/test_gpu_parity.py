@@ -166,7 +166,7 @@ def test_named_query_shapes_on_scaled_corpus(synth, shape, kind, k):
         got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
         assert_same_topdocs(int(res.total_hits[q]), got, h, sd, line[:70])
         nonempty += h > 0
-    assert nonempty > 10
+    assert nonempty >= (1 if shape == "C3-AND4" else 10)   # AND-4 is mostly empty on a 1% corpus
 
 
 def test_sharded_search_and_device_merge_equal_whole(synth):
