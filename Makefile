@@ -21,7 +21,7 @@ $(BUILD)/%.o: diagon_b200/host/%.cpp $(HOST_HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(BUILD)/engine.o: diagon_b200/csrc/engine.cu include/dgpu_engine.h
+$(BUILD)/engine.o: diagon_b200/csrc/engine.cu diagon_b200/csrc/kernels.cuh include/dgpu_engine.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/ptxas.log || (cat $(BUILD)/ptxas.log; false)
 
