@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=0, help="queries per batch (0 = the named batch size)")
     ap.add_argument("--log2-window", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=0, help="3 = batched decode_score + accumulate_topk (default), 2 = fused windows")
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -236,6 +238,10 @@ def main():
         reader.set_option("log2_window", args.log2_window)
     if args.ctas_per_sm:
         reader.set_option("ctas_per_sm", args.ctas_per_sm)
+    if args.warps:
+        reader.set_option("warps", args.warps)
+    if args.kernel:
+        reader.set_option("kernel", args.kernel)
     if world > 1:
         # global statistics: idf / avgdl must be identical on every rank
         df = torch.from_numpy(reader.get_doc_freqs()).cuda()
@@ -301,7 +307,7 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.dgpu_engine_launch_count(eng)
-    kernel_ms = []
+    kernel_ms, phase_ms = [], []
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
@@ -316,6 +322,11 @@ def main():
         barrier()
         lib.dgpu_engine_sync(eng)
         kernel_ms.append(lib.dgpu_engine_last_search_ms(eng))
+        ph = (C.c_float * 3)()
+        lib.dgpu_engine_last_phase_ms(eng, C.byref(ph))
+        phase_ms.append([float(x) for x in ph])
+    bstats = (C.c_uint64 * 6)()
+    lib.dgpu_engine_batch_stats(eng, C.byref(bstats))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -343,21 +354,34 @@ def main():
     e2e_value = nq * args.steps / float(e2e_t[0])
     clocks = sampler.stop()
 
-    # ---- roofline of the dominant kernel (search_kernel)
+    # ---- roofline of the dominant kernel: accumulate_topk_kernel (batched path) or search_kernel (fused path)
     peak, peak_src = measured_peak()
     algo = torch.tensor([stats["algorithmic_bytes"], stats["postings"]], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(algo)
-    k_ms = statistics.median(kernel_ms)
-    kt = torch.tensor([k_ms], dtype=torch.float64, device="cuda")
+    med = [statistics.median(p[i] for p in phase_ms) for i in range(3)]
+    batched = (args.kernel or 3) == 3
+    k_ms = med[1] if batched else statistics.median(kernel_ms)
+    kt = torch.tensor([k_ms, med[0]], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     achieved = stats["algorithmic_bytes"] / (float(kt[0]) / 1e3) / 1e9  # this rank's bytes / its kernel time
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "search_kernel",
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "accumulate_topk_kernel" if batched else "search_kernel",
                 "kernel_ms": float(kt[0]), "algorithmic_bytes_per_launch": stats["algorithmic_bytes"],
                 "postings_per_launch": stats["postings"],
-                "postings_per_s": stats["postings"] / (float(kt[0]) / 1e3)}
+                "postings_per_s": stats["postings"] / (float(kt[0]) / 1e3),
+                "step_ms_by_kernel": {"decode_score_kernel": med[0], "accumulate_topk_kernel": med[1], "merge_parts_kernel": med[2]}}
+    if batched and med[0] > 0:
+        # K1 alone: reads the compressed blocks of the distinct terms once, writes 8 B per decoded posting slot
+        rd, wr = int(bstats[4]), int(bstats[2]) * 8
+        roofline["decode_score_kernel"] = {
+            "distinct_terms": int(bstats[0]), "read_bytes": rd, "write_bytes": wr, "kernel_ms": float(kt[1]),
+            "achieved": (rd + wr) / (float(kt[1]) / 1e3) / 1e9, "unit": "GB/s",
+            "frac": (rd + wr) / (float(kt[1]) / 1e3) / 1e9 / peak}
+        roofline["window_docs"] = int(bstats[5])
+        roofline["doc_range_splits"] = int(bstats[3])
 
     if rank == 0:
         h2d = nq * 20 + stats["queries"] * 4 + 12 * int(text.count(b" t"))  # dgpu_query + order + dgpu_qterm
@@ -371,7 +395,7 @@ def main():
                        "sharding": f"{nseg} segments over {world} GPU(s), {'NCCL all-gather + device merge' if world > 1 else 'single GPU'}",
                        "l2": "inputs larger than L2 (device image %.0f MB per GPU)" % (reader.image_bytes() / 1e6),
                        "index_build_s": build_s, "postings_on_gpu": reader.num_postings(), "image_bytes": reader.image_bytes(),
-                       "log2_window": args.log2_window or 14},
+                       "kernel_path": "batched" if batched else "fused-windows"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": "dgpu_search_batch_text (host text -> host results)", "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},

@@ -46,6 +46,7 @@ int fail(const char* fmt, ...) {
 }  // namespace
 
 #include "kernels.cuh"
+#include "batch_kernels.cuh"
 
 namespace {
 
@@ -84,6 +85,7 @@ struct dgpu_engine {
     uint64_t n_blocks = 0;
     std::vector<uint32_t> h_term_block_start;
     std::vector<uint32_t> h_block_meta;
+    std::vector<uint32_t> h_block_off;
     std::vector<void*> owned;  // device allocations of the index
     // staged batch
     DevBuf<dgpu_query> d_queries;
@@ -98,12 +100,36 @@ struct dgpu_engine {
     uint32_t max_terms = 1;
     bool need_cnt = false;
     int k = 0;
+    // staged batch, batched path: distinct terms -> (doc, score) runs in the scratch
+    DevBuf<DTerm> d_dterms;
+    DevBuf<DItem> d_items;
+    DevBuf<QTermRun> d_qruns;
+    DevBuf<uint32_t> d_run_docs;
+    DevBuf<float> d_run_scores;
+    DevBuf<uint64_t> d_part_keys;
+    DevBuf<int32_t> d_part_counts;
+    DevBuf<int64_t> d_part_hits;
+    uint32_t n_dterms = 0, n_ditems = 0;
+    uint64_t run_entries = 0;
+    uint32_t n_splits = 1, split_docs = 0;
+    uint64_t distinct_bytes = 0;        // compressed bytes (payload + 16 B skip row per block) of the distinct terms
+    uint32_t last_window = 0;
+    std::vector<uint32_t> h_slot;       // term id -> distinct slot of the batch being staged (epoch stamped)
+    std::vector<uint32_t> h_slot_epoch;
+    uint32_t epoch = 0;
     // options
     int logw = 15;
-    int ctas_per_sm = 1;
+    int ctas_per_sm = 3;
+    int warps = 4;
+    int kernel = 3;          // 3 = batched (decode_score + accumulate_topk), 2 = per-query fused windows
+    int force_splits = 0;    // 0 = automatic
+    int window_docs = 0;     // 0 = the largest window that fits; else an upper bound (tests)
+    int stage_log2 = 0;      // 0 = automatic; else log2 of the staged entries per term (tests)
     // stats
     uint64_t launches = 0;
     float last_ms = 0.f;
+    float phase_ms[3] = {0.f, 0.f, 0.f};  // decode_score, accumulate_topk, merge
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
 
 template <class T>
@@ -137,6 +163,8 @@ int dgpu_engine_create(int device, dgpu_engine** out) {
     CU(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&eng->ev0));
     CU(cudaEventCreate(&eng->ev1));
+    CU(cudaEventCreate(&eng->ev_a));
+    CU(cudaEventCreate(&eng->ev_b));
     *out = eng;
     return 0;
 }
@@ -147,8 +175,12 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     for (void* p : e->owned) cudaFree(p);
     e->d_queries.release(); e->d_terms.release(); e->d_filters.release(); e->d_order.release();
     e->d_counter.release(); e->d_keys.release(); e->d_counts.release(); e->d_hits.release();
+    e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_run_docs.release(); e->d_run_scores.release();
+    e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_a) cudaEventDestroy(e->ev_a);
+    if (e->ev_b) cudaEventDestroy(e->ev_b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -169,6 +201,31 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->ctas_per_sm = static_cast<int>(value);
         return 0;
     }
+    if (!std::strcmp(name, "warps")) {
+        if (value != 4 && value != 8) return fail("warps must be 4 or 8");
+        e->warps = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "kernel")) {
+        if (value != 2 && value != 3) return fail("kernel must be 2 (fused windows) or 3 (batched)");
+        e->kernel = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "window_docs")) {
+        if (value != 0 && (value < 64 || value > 65536)) return fail("window_docs must be 0 or in [64, 65536]");
+        e->window_docs = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "stage_log2")) {
+        if (value < 0 || value > 5) return fail("stage_log2 must be in [0, 5]");
+        e->stage_log2 = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "splits")) {
+        if (value < 0 || value > 64) return fail("splits must be in [0, 64]");
+        e->force_splits = static_cast<int>(value);
+        return 0;
+    }
     return fail("unknown option %s", name);
 }
 
@@ -180,6 +237,7 @@ int dgpu_engine_upload(dgpu_engine* e, const dgpu_index_image* im) {
     e->n_fields = im->n_fields;
     e->h_term_block_start.assign(im->term_block_start, im->term_block_start + im->n_terms + 1);
     e->h_block_meta.assign(im->block_meta, im->block_meta + im->n_blocks);
+    e->h_block_off.assign(im->block_data_off, im->block_data_off + im->n_blocks + 1);
     if (upload_array(e, im->term_block_start, static_cast<size_t>(im->n_terms) + 1, &e->ix.term_block_start)) return -1;
     if (upload_array(e, im->block_first_doc, im->n_blocks, &e->ix.first)) return -1;
     if (upload_array(e, im->block_last_doc, im->n_blocks, &e->ix.last)) return -1;
@@ -257,18 +315,24 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     if (k > DGPU_MAX_K) return fail("numHits %d exceeds DGPU_MAX_K", k);
     e->n_queries = b->n_queries;
     e->k = k;
-    CU(e->d_queries.ensure(b->n_queries));
-    CU(e->d_terms.ensure(b->n_terms));
-    CU(e->d_filters.ensure(b->n_filters));
-    CU(e->d_order.ensure(b->n_queries));
-    CU(e->d_counter.ensure(1));
-    CU(e->d_keys.ensure(static_cast<size_t>(b->n_queries) * k));
-    CU(e->d_counts.ensure(b->n_queries));
-    CU(e->d_hits.ensure(b->n_queries));
-    // order by decreasing cost (number of posting blocks) so the long queries start first
+    // ---- validation, per-query cost (posting blocks), distinct terms of the batch
     std::vector<uint64_t> cost(b->n_queries, 0);
     uint32_t max_terms = 1;
     bool need_cnt = false;
+    if (e->h_slot_epoch.size() != e->n_terms) {
+        e->h_slot.assign(e->n_terms, 0);
+        e->h_slot_epoch.assign(e->n_terms, 0);
+        e->epoch = 0;
+    }
+    if (++e->epoch == 0) {  // wrapped: stamps are ambiguous again
+        std::fill(e->h_slot_epoch.begin(), e->h_slot_epoch.end(), 0u);
+        e->epoch = 1;
+    }
+    std::vector<DTerm> dterms;
+    std::vector<DItem> items;
+    std::vector<QTermRun> qruns(b->n_terms);
+    uint64_t run_entries = kRunPad;  // [0, kRunPad) is the empty run (terms absent on this GPU)
+    uint64_t distinct_bytes = 0;
     for (uint32_t q = 0; q < b->n_queries; ++q) {
         const dgpu_query& qd = b->queries[q];
         if (qd.term_end < qd.term_begin || qd.term_end > b->n_terms) return fail("query %u: bad term slice", q);
@@ -280,33 +344,131 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         for (uint32_t t = qd.term_begin; t < qd.term_end; ++t) {
             const dgpu_qterm& qt = b->terms[t];
             if (qt.role == DGPU_ROLE_MUST_NOT) need_cnt = true;
-            if (qt.term_id == kNoTerm) continue;
-            if (qt.term_id >= e->n_terms) return fail("query %u: term id out of range", q);
-            if (qt.field >= 0xFFFF) return fail("query %u: bad field", q);
-            cost[q] += e->h_term_block_start[qt.term_id + 1] - e->h_term_block_start[qt.term_id];
+            QTermRun run{0u, 0u, qt.role, 0u};
+            if (qt.term_id != kNoTerm) {
+                if (qt.term_id >= e->n_terms) return fail("query %u: term id out of range", q);
+                if (qt.field >= e->n_fields) return fail("query %u: bad field", q);
+                const uint32_t nb = e->h_term_block_start[qt.term_id + 1] - e->h_term_block_start[qt.term_id];
+                cost[q] += nb;
+                // distinct (term, idf, field): the first use of a term id in this batch claims its slot; a later use
+                // with another idf / field (a boosted clause) gets a slot of its own
+                uint32_t slot = 0xFFFFFFFFu;
+                if (e->h_slot_epoch[qt.term_id] == e->epoch) {
+                    const DTerm& d = dterms[e->h_slot[qt.term_id]];
+                    uint32_t a, c;
+                    std::memcpy(&a, &d.idf, 4);
+                    std::memcpy(&c, &qt.idf, 4);
+                    if (a == c && d.field == qt.field) slot = e->h_slot[qt.term_id];
+                }
+                if (slot == 0xFFFFFFFFu && nb > 0) {
+                    slot = static_cast<uint32_t>(dterms.size());
+                    if (e->h_slot_epoch[qt.term_id] != e->epoch) {
+                        e->h_slot_epoch[qt.term_id] = e->epoch;
+                        e->h_slot[qt.term_id] = slot;
+                    }
+                    dterms.push_back(DTerm{qt.term_id, qt.idf, qt.field, static_cast<uint32_t>(run_entries)});
+                    const uint32_t b0 = e->h_term_block_start[qt.term_id];
+                    distinct_bytes += 16ull * (e->h_block_off[b0 + nb] - e->h_block_off[b0]) + 16ull * nb;
+                    for (uint32_t rel = 0; rel < nb; rel += kItemBlocks) items.push_back(DItem{slot, rel});
+                    run_entries += (static_cast<uint64_t>(nb) + kPadBlocks) * DGPU_BLOCK_POSTINGS;
+                    if (run_entries > 0xFFFFFFFFull - 4096)
+                        return fail("batch decodes to more than 2^32 postings; split the batch");
+                }
+                if (slot != 0xFFFFFFFFu) {
+                    run.base = dterms[slot].out_base;
+                    run.len = nb * DGPU_BLOCK_POSTINGS;
+                }
+            }
+            qruns[t] = run;
         }
         for (uint32_t f = qd.filter_begin; f < qd.filter_end; ++f)
             if (b->filters[f].column < 0) return fail("query %u: bad filter column", q);
     }
-    std::vector<uint32_t> order(b->n_queries);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
     e->max_terms = max_terms;
     e->need_cnt = need_cnt;
+    e->n_dterms = static_cast<uint32_t>(dterms.size());
+    e->n_ditems = static_cast<uint32_t>(items.size());
+    e->run_entries = run_entries;
+    e->distinct_bytes = distinct_bytes;
+
+    // ---- doc-range splits: a small batch is cut so that every SM has work
+    const uint32_t doc_range = e->ix.doc_hi - e->ix.doc_lo;
+    uint32_t n_splits = 1;
+    if (e->kernel == 3 && b->n_queries) {
+        const uint64_t target = static_cast<uint64_t>(e->sm_count) * e->ctas_per_sm;
+        n_splits = e->force_splits ? static_cast<uint32_t>(e->force_splits)
+                                   : static_cast<uint32_t>(std::min<uint64_t>(32, target / b->n_queries));
+        n_splits = std::max(1u, std::min(n_splits, doc_range / 8192u));
+    }
+    uint32_t split_docs = ((doc_range + n_splits - 1) / n_splits + 31u) & ~31u;
+    if (split_docs == 0) split_docs = 32;
+    n_splits = std::max(1u, (doc_range + split_docs - 1) / split_docs);
+    e->n_splits = n_splits;
+    e->split_docs = split_docs;
+
+    // ---- work order: decreasing cost so the long queries start first
+    const uint32_t n_items = b->n_queries * n_splits;
+    std::vector<uint32_t> order(n_items);
+    {
+        std::vector<uint32_t> qorder(b->n_queries);
+        std::iota(qorder.begin(), qorder.end(), 0u);
+        std::stable_sort(qorder.begin(), qorder.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+        if (e->kernel == 3) {
+            for (uint32_t i = 0; i < b->n_queries; ++i)
+                for (uint32_t sp = 0; sp < n_splits; ++sp) order[i * n_splits + sp] = qorder[i] * n_splits + sp;
+        } else {
+            order = qorder;
+        }
+    }
+
+    CU(e->d_queries.ensure(b->n_queries));
+    CU(e->d_terms.ensure(b->n_terms));
+    CU(e->d_filters.ensure(b->n_filters));
+    CU(e->d_order.ensure(n_items));
+    CU(e->d_counter.ensure(1));
+    CU(e->d_keys.ensure(static_cast<size_t>(b->n_queries) * k));
+    CU(e->d_counts.ensure(b->n_queries));
+    CU(e->d_hits.ensure(b->n_queries));
+    CU(e->d_dterms.ensure(dterms.size()));
+    CU(e->d_items.ensure(items.size()));
+    CU(e->d_qruns.ensure(b->n_terms));
+    if (n_splits > 1) {
+        CU(e->d_part_keys.ensure(static_cast<size_t>(n_items) * k));
+        CU(e->d_part_counts.ensure(n_items));
+        CU(e->d_part_hits.ensure(n_items));
+    }
+    if (e->kernel == 3) {
+        const size_t want = static_cast<size_t>(run_entries) + 1024;  // tail slack for look-ahead loads
+        if (want > e->d_run_docs.cap) {
+            // grow with headroom: the scratch is reused by every batch
+            const size_t cap = want + want / 4;
+            if (e->d_run_docs.ensure(cap) != cudaSuccess || e->d_run_scores.ensure(cap) != cudaSuccess)
+                return fail("cannot allocate %zu MB of decode scratch (%s); split the batch", cap * 8 >> 20,
+                            cudaGetErrorString(cudaGetLastError()));
+        }
+        CU(cudaMemsetAsync(e->d_run_docs.p, 0xFF, sizeof(uint32_t) * kRunPad, e->stream));
+    }
     if (b->n_queries) {
         CU(cudaMemcpyAsync(e->d_queries.p, b->queries, sizeof(dgpu_query) * b->n_queries, cudaMemcpyHostToDevice, e->stream));
-        if (b->n_terms) CU(cudaMemcpyAsync(e->d_terms.p, b->terms, sizeof(dgpu_qterm) * b->n_terms, cudaMemcpyHostToDevice, e->stream));
+        if (b->n_terms) {
+            CU(cudaMemcpyAsync(e->d_terms.p, b->terms, sizeof(dgpu_qterm) * b->n_terms, cudaMemcpyHostToDevice, e->stream));
+            CU(cudaMemcpyAsync(e->d_qruns.p, qruns.data(), sizeof(QTermRun) * b->n_terms, cudaMemcpyHostToDevice, e->stream));
+        }
         if (b->n_filters) CU(cudaMemcpyAsync(e->d_filters.p, b->filters, sizeof(dgpu_qfilter) * b->n_filters, cudaMemcpyHostToDevice, e->stream));
-        CU(cudaMemcpyAsync(e->d_order.p, order.data(), 4 * b->n_queries, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->d_order.p, order.data(), 4 * order.size(), cudaMemcpyHostToDevice, e->stream));
+        if (!dterms.empty()) {
+            CU(cudaMemcpyAsync(e->d_dterms.p, dterms.data(), sizeof(DTerm) * dterms.size(), cudaMemcpyHostToDevice, e->stream));
+            CU(cudaMemcpyAsync(e->d_items.p, items.data(), sizeof(DItem) * items.size(), cudaMemcpyHostToDevice, e->stream));
+        }
     }
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
     return 0;
 }
 
-int dgpu_engine_search_staged(dgpu_engine* e, void* stream_v) {
-    CU(cudaSetDevice(e->device));
-    cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : e->stream;
-    if (e->n_queries == 0) return 0;
+}  // extern "C"
+
+// kernel = 2: per-query fused windows (decode inside the query loop; no sharing between queries)
+static int launch_fused(dgpu_engine* e, cudaStream_t stream) {
     SearchParams P{};
     P.queries = e->d_queries.p;
     P.terms = e->d_terms.p;
@@ -347,6 +509,112 @@ int dgpu_engine_search_staged(dgpu_engine* e, void* stream_v) {
     return 0;
 }
 
+template <int WARPS>
+static int launch_accumulate(dgpu_engine* e, const AccumParams& P, size_t smem, int grid, cudaStream_t stream) {
+    auto kern = e->need_cnt ? accumulate_topk_kernel<WARPS, true> : accumulate_topk_kernel<WARPS, false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, WARPS * 32, smem, stream>>>(e->ix, P);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// kernel = 3: decode + score every distinct term of the batch once, then accumulate + top-k per query
+static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
+    AccumParams P{};
+    P.queries = e->d_queries.p;
+    P.terms = e->d_qruns.p;
+    P.filters = e->d_filters.p;
+    P.order = e->d_order.p;
+    P.n_queries = e->n_queries;
+    P.n_splits = e->n_splits;
+    P.split_docs = e->split_docs;
+    P.n_items = e->n_queries * e->n_splits;
+    P.work_counter = e->d_counter.p;
+    P.run_docs = e->d_run_docs.p;
+    P.run_scores = e->d_run_scores.p;
+    P.k = e->k;
+    P.max_terms = (e->max_terms + 3u) & ~3u;
+    uint32_t chlog = 5;   // staged entries per term: 32 up to 64 terms, halved for every doubling after that
+    while (chlog > 1 && (static_cast<size_t>(P.max_terms) << chlog) * 8 > 16384) --chlog;
+    if (e->stage_log2) chlog = std::min<uint32_t>(chlog, static_cast<uint32_t>(e->stage_log2));
+    P.chlog = chlog;
+    const uint32_t threads = static_cast<uint32_t>(e->warps) * 32u;
+    uint32_t cap = 256;
+    while (cap < 2u * static_cast<uint32_t>(e->k) || cap < static_cast<uint32_t>(e->k) + threads) cap <<= 1;
+    P.cand_cap = cap;
+    P.list_cap = 2048;
+    // window: what is left of this CTA's share of the SM's shared memory
+    const size_t per_sm = 228 * 1024;
+    size_t budget = std::min<size_t>(per_sm / e->ctas_per_sm - 1024, static_cast<size_t>(e->max_smem_optin));
+    const size_t fixed = accum_smem_bytes(0, cap, P.max_terms, chlog, P.list_cap, e->need_cnt);
+    const size_t per_doc = e->need_cnt ? 5 : 4;
+    if (budget < fixed + per_doc * 1024) budget = static_cast<size_t>(e->max_smem_optin);
+    if (budget < fixed + per_doc * 1024)
+        return fail("search needs %zu bytes of shared memory, device allows %d", fixed + per_doc * 1024, e->max_smem_optin);
+    uint32_t W = static_cast<uint32_t>(std::min<size_t>((budget - fixed) / per_doc, 65536)) & ~31u;
+    if (e->window_docs) W = std::min<uint32_t>(W, static_cast<uint32_t>(e->window_docs) & ~31u);
+    P.W = W;
+    e->last_window = W;
+    const size_t smem = accum_smem_bytes(W, cap, P.max_terms, chlog, P.list_cap, e->need_cnt);
+    const bool split = e->n_splits > 1;
+    P.out_keys = split ? e->d_part_keys.p : e->d_keys.p;
+    P.out_counts = split ? e->d_part_counts.p : e->d_counts.p;
+    P.out_hits = split ? e->d_part_hits.p : e->d_hits.p;
+
+    CU(cudaMemsetAsync(e->d_counter.p, 0, 4, stream));
+    CU(cudaEventRecord(e->ev0, stream));
+    if (e->n_ditems) {
+        const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * 8));
+        decode_score_kernel<<<grid, kDecodeThreads, 0, stream>>>(e->ix, e->d_dterms.p, e->d_items.p, e->n_ditems,
+                                                                 e->d_run_docs.p, e->d_run_scores.p);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(e->ev_a, stream));
+    const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(per_sm / (smem + 1024), 32)));
+    const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * ctas, P.n_items));
+    if (e->warps == 8) {
+        if (launch_accumulate<8>(e, P, smem, grid, stream)) return -1;
+    } else {
+        if (launch_accumulate<4>(e, P, smem, grid, stream)) return -1;
+    }
+    e->launches++;
+    CU(cudaEventRecord(e->ev_b, stream));
+    if (split) {
+        merge_parts_kernel<<<e->n_queries, 128, 0, stream>>>(e->d_part_keys.p, e->d_part_counts.p, e->d_part_hits.p,
+                                                             static_cast<int>(e->n_splits), e->n_queries, e->k, e->d_keys.p,
+                                                             e->d_counts.p, e->d_hits.p);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(e->ev1, stream));
+    return 0;
+}
+
+extern "C" {
+
+int dgpu_engine_search_staged(dgpu_engine* e, void* stream_v) {
+    CU(cudaSetDevice(e->device));
+    cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : e->stream;
+    if (e->n_queries == 0) return 0;
+    return e->kernel == 3 ? launch_batched(e, stream) : launch_fused(e, stream);
+}
+
+static int read_timers(dgpu_engine* e) {
+    if (!e->n_queries) return 0;
+    CU(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    if (e->kernel == 3) {
+        CU(cudaEventElapsedTime(&e->phase_ms[0], e->ev0, e->ev_a));
+        CU(cudaEventElapsedTime(&e->phase_ms[1], e->ev_a, e->ev_b));
+        CU(cudaEventElapsedTime(&e->phase_ms[2], e->ev_b, e->ev1));
+    } else {
+        e->phase_ms[0] = 0.f;
+        e->phase_ms[1] = e->last_ms;
+        e->phase_ms[2] = 0.f;
+    }
+    return 0;
+}
+
 int dgpu_engine_device_results(dgpu_engine* e, dgpu_results* out) {
     out->keys = e->d_keys.p;
     out->counts = e->d_counts.p;
@@ -362,14 +630,27 @@ int dgpu_engine_fetch_results(dgpu_engine* e, dgpu_results* out) {
         CU(cudaMemcpyAsync(out->total_hits, e->d_hits.p, sizeof(int64_t) * e->n_queries, cudaMemcpyDeviceToHost, e->stream));
     }
     CU(cudaStreamSynchronize(e->stream));
-    if (e->n_queries) CU(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
-    return 0;
+    return read_timers(e);
 }
 
 int dgpu_engine_sync(dgpu_engine* e) {
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
-    if (e->n_queries) CU(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    return read_timers(e);
+}
+
+int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]) {
+    for (int i = 0; i < 3; ++i) out[i] = e->phase_ms[i];
+    return 0;
+}
+
+int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[6]) {
+    out[0] = e->n_dterms;
+    out[1] = e->n_ditems;
+    out[2] = e->run_entries;
+    out[3] = e->n_splits;
+    out[4] = e->distinct_bytes;
+    out[5] = e->last_window;
     return 0;
 }
 

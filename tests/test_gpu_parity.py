@@ -68,13 +68,21 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
             assert np.isnan(td.maxScore)
 
 
+# (window_docs, stage_log2, splits, warps): small windows walk many windows per query, stage_log2 = 1 pushes almost every
+# term through the dense (global-memory continuation) path, splits exercises the doc-range split + device merge
+_TUNINGS = [(0, 0, 0, 4), (1024, 0, 1, 4), (256, 1, 1, 4), (4096, 2, 3, 8), (64, 3, 7, 8), (2048, 0, 16, 4)]
+
+
 @pytest.mark.parametrize("name", ["g1", "g2"])
-@pytest.mark.parametrize("log2_window", [10, 12, 14, 15])
-def test_batched_search_matches_golden_for_every_window_size(readers, golden_dir, name, log2_window):
-    """dgpu_search_batch_text: the whole query file in one launch; window size must not change any result."""
-    readers[name].set_option("log2_window", log2_window)
+@pytest.mark.parametrize("window_docs,stage_log2,splits,warps", _TUNINGS)
+def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, name, window_docs, stage_log2, splits, warps):
+    """dgpu_search_batch_text: the whole query file in one launch; window size, staging depth, doc-range splits and
+    CTA width must not change any result."""
+    r = readers[name]
+    for opt, v in (("window_docs", window_docs), ("stage_log2", stage_log2), ("splits", splits), ("warps", warps)):
+        r.set_option(opt, v)
     try:
-        searcher = dg.IndexSearcher(readers[name])
+        searcher = dg.IndexSearcher(r)
         text = open(os.path.join(golden_dir, f"{name}_queries.txt"), "rb").read()
         for k in (10, 100):
             _, ref = read_results(os.path.join(golden_dir, f"{name}_k{k}_exhaustive.res"))
@@ -84,7 +92,25 @@ def test_batched_search_matches_golden_for_every_window_size(readers, golden_dir
                 got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
                 assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
     finally:
-        readers[name].set_option("log2_window", 14)
+        for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4)):
+            r.set_option(opt, v)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+def test_fused_window_kernel_matches_golden(readers, golden_dir, name):
+    """The per-query fused kernel (option kernel=2, no decode sharing) stays bit-exact too."""
+    r = readers[name]
+    r.set_option("kernel", 2)
+    try:
+        searcher = dg.IndexSearcher(r)
+        text = open(os.path.join(golden_dir, f"{name}_queries.txt"), "rb").read()
+        _, ref = read_results(os.path.join(golden_dir, f"{name}_k10_exhaustive.res"))
+        res = searcher.search_batch_text(text, 10)
+        for q, (hits, _, docs) in enumerate(ref):
+            got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
+            assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
+    finally:
+        r.set_option("kernel", 3)
 
 
 def test_query_handles_batch_equals_text_batch(readers, golden_dir):
