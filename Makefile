@@ -5,7 +5,7 @@ NVCC     := nvcc -ccbin /usr/bin/g++
 CXX      := /usr/bin/g++
 CUDA_HOME ?= /usr/local/cuda
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v
+NVFLAGS  := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v -maxrregcount=128 $(EXTRA_NVFLAGS)
 # host arithmetic must match the reference's IEEE build: no fast-math, no FMA contraction
 CXXFLAGS := -std=c++20 -O2 -fPIC -Wall -Wextra -ffp-contract=off -fno-fast-math -pthread
 OUT      := diagon_b200/libdiagon_b200.so
@@ -21,7 +21,7 @@ $(BUILD)/%.o: diagon_b200/host/%.cpp $(HOST_HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(BUILD)/engine.o: diagon_b200/csrc/engine.cu diagon_b200/csrc/kernels.cuh include/dgpu_engine.h
+$(BUILD)/engine.o: diagon_b200/csrc/engine.cu $(wildcard diagon_b200/csrc/*.cuh) include/dgpu_engine.h Makefile
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/ptxas.log || (cat $(BUILD)/ptxas.log; false)
 

@@ -114,6 +114,9 @@ struct dgpu_engine {
     uint32_t n_splits = 1, split_docs = 0;
     uint64_t distinct_bytes = 0;        // compressed bytes (payload + 16 B skip row per block) of the distinct terms
     uint32_t last_window = 0;
+    // launch plan of the batched path (made by stage_batch: the host sizes the per-term rings with it)
+    uint32_t plan_cap = 0, plan_list = 0, plan_ring = 0, plan_W = 0;
+    size_t plan_smem = 0;
     std::vector<uint32_t> h_slot;       // term id -> distinct slot of the batch being staged (epoch stamped)
     std::vector<uint32_t> h_slot_epoch;
     uint32_t epoch = 0;
@@ -124,7 +127,7 @@ struct dgpu_engine {
     int kernel = 3;          // 3 = batched (decode_score + accumulate_topk), 2 = per-query fused windows
     int force_splits = 0;    // 0 = automatic
     int window_docs = 0;     // 0 = the largest window that fits; else an upper bound (tests)
-    int stage_log2 = 0;      // 0 = automatic; else log2 of the staged entries per term (tests)
+    int ring_entries = 2048; // shared-memory ring area per CTA (entries of 8 bytes), grown for queries with many terms
     // stats
     uint64_t launches = 0;
     float last_ms = 0.f;
@@ -140,6 +143,65 @@ static int upload_array(dgpu_engine* e, const T* host, size_t n, const T** dev) 
     if (n) CU(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
     *dev = static_cast<const T*>(p);
     return 0;
+}
+
+// Launch geometry of accumulate_topk_kernel for the staged batch: candidate pool, touched list, ring area and the
+// window that fills what is left of the CTA's share of shared memory.
+static int plan_batched(dgpu_engine* e) {
+    const uint32_t max_terms = (e->max_terms + 3u) & ~3u;
+    const uint32_t threads = static_cast<uint32_t>(e->warps) * 32u;
+    uint32_t cap = 256;
+    while (cap < 2u * static_cast<uint32_t>(e->k) || cap < static_cast<uint32_t>(e->k) + threads) cap <<= 1;
+    uint32_t ring = static_cast<uint32_t>(e->ring_entries);
+    while (ring < 16u * max_terms) ring <<= 1;   // every term needs a ring of at least 16 entries
+    const uint32_t list_cap = 2048;
+    const size_t per_sm = 228 * 1024;
+    const size_t optin = static_cast<size_t>(e->max_smem_optin) - 512;   // the kernel's static shared memory
+    size_t budget = std::min<size_t>(per_sm / e->ctas_per_sm - 1024, optin);
+    const size_t fixed = accum_smem_bytes(0, cap, max_terms, ring, list_cap, e->need_cnt);
+    const size_t per_doc = e->need_cnt ? 5 : 4;
+    if (budget < fixed + per_doc * 2048) budget = optin;
+    if (budget < fixed + per_doc * 1024)
+        return fail("search needs %zu bytes of shared memory, device allows %d", fixed + per_doc * 1024, e->max_smem_optin);
+    uint32_t W = static_cast<uint32_t>(std::min<size_t>((budget - fixed) / per_doc, 65536)) & ~31u;
+    if (e->window_docs) W = std::min<uint32_t>(W, static_cast<uint32_t>(e->window_docs) & ~31u);
+    e->plan_cap = cap;
+    e->plan_list = list_cap;
+    e->plan_ring = ring;
+    e->plan_W = W;
+    e->plan_smem = accum_smem_bytes(W, cap, max_terms, ring, list_cap, e->need_cnt);
+    e->last_window = W;
+    return 0;
+}
+
+// Ring sizes of one query: a power of two per term, about three windows of its expected postings, at least `rmin`,
+// halving the largest until the sum fits the ring area.
+static void plan_rings(QTermRun* runs, uint32_t nt, uint32_t ring_entries, uint32_t W, uint32_t doc_range) {
+    if (nt == 0) return;
+    uint32_t rmin = 128;
+    while (rmin > 16 && static_cast<uint64_t>(rmin) * nt > ring_entries) rmin >>= 1;
+    uint32_t lg[1024];
+    uint64_t sum = 0;
+    for (uint32_t t = 0; t < nt; ++t) {
+        const uint64_t est = static_cast<uint64_t>(runs[t].len) * W / std::max(1u, doc_range);  // postings per window
+        uint32_t l = 4;
+        while ((1u << l) < rmin || ((1ull << l) < 3 * est && l < 13)) ++l;
+        lg[t] = l;
+        sum += 1ull << l;
+    }
+    while (sum > ring_entries) {
+        uint32_t best = 0;
+        for (uint32_t t = 1; t < nt; ++t)
+            if (lg[t] > lg[best]) best = t;
+        sum -= 1ull << (lg[best] - 1);
+        --lg[best];
+    }
+    uint32_t off = 0;
+    for (uint32_t t = 0; t < nt; ++t) {
+        runs[t].meta = (runs[t].meta & 0xFFu) | (lg[t] << 8);
+        runs[t].ring_off = off;
+        off += 1u << lg[t];
+    }
 }
 
 extern "C" {
@@ -216,9 +278,9 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->window_docs = static_cast<int>(value);
         return 0;
     }
-    if (!std::strcmp(name, "stage_log2")) {
-        if (value < 0 || value > 5) return fail("stage_log2 must be in [0, 5]");
-        e->stage_log2 = static_cast<int>(value);
+    if (!std::strcmp(name, "ring_entries")) {
+        if (value < 64 || value > 16384 || (value & (value - 1))) return fail("ring_entries must be a power of two in [64, 16384]");
+        e->ring_entries = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "splits")) {
@@ -390,6 +452,12 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->n_ditems = static_cast<uint32_t>(items.size());
     e->run_entries = run_entries;
     e->distinct_bytes = distinct_bytes;
+    if (plan_batched(e)) return -1;
+    for (uint32_t q = 0; q < b->n_queries; ++q) {
+        const dgpu_query& qd = b->queries[q];
+        plan_rings(qruns.data() + qd.term_begin, qd.term_end - qd.term_begin, e->plan_ring, e->plan_W,
+                   e->ix.doc_hi - e->ix.doc_lo);
+    }
 
     // ---- doc-range splits: a small batch is cut so that every SM has work
     const uint32_t doc_range = e->ix.doc_hi - e->ix.doc_lo;
@@ -438,7 +506,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         CU(e->d_part_hits.ensure(n_items));
     }
     if (e->kernel == 3) {
-        const size_t want = static_cast<size_t>(run_entries) + 1024;  // tail slack for look-ahead loads
+        const size_t want = static_cast<size_t>(run_entries) + 16384;  // tail slack for ring look-ahead loads
         if (want > e->d_run_docs.cap) {
             // grow with headroom: the scratch is reused by every batch
             const size_t cap = want + want / 4;
@@ -534,28 +602,12 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.run_scores = e->d_run_scores.p;
     P.k = e->k;
     P.max_terms = (e->max_terms + 3u) & ~3u;
-    uint32_t chlog = 5;   // staged entries per term: 32 up to 64 terms, halved for every doubling after that
-    while (chlog > 1 && (static_cast<size_t>(P.max_terms) << chlog) * 8 > 16384) --chlog;
-    if (e->stage_log2) chlog = std::min<uint32_t>(chlog, static_cast<uint32_t>(e->stage_log2));
-    P.chlog = chlog;
-    const uint32_t threads = static_cast<uint32_t>(e->warps) * 32u;
-    uint32_t cap = 256;
-    while (cap < 2u * static_cast<uint32_t>(e->k) || cap < static_cast<uint32_t>(e->k) + threads) cap <<= 1;
-    P.cand_cap = cap;
-    P.list_cap = 2048;
-    // window: what is left of this CTA's share of the SM's shared memory
+    P.cand_cap = e->plan_cap;
+    P.list_cap = e->plan_list;
+    P.ring_entries = e->plan_ring;
+    P.W = e->plan_W;
     const size_t per_sm = 228 * 1024;
-    size_t budget = std::min<size_t>(per_sm / e->ctas_per_sm - 1024, static_cast<size_t>(e->max_smem_optin));
-    const size_t fixed = accum_smem_bytes(0, cap, P.max_terms, chlog, P.list_cap, e->need_cnt);
-    const size_t per_doc = e->need_cnt ? 5 : 4;
-    if (budget < fixed + per_doc * 1024) budget = static_cast<size_t>(e->max_smem_optin);
-    if (budget < fixed + per_doc * 1024)
-        return fail("search needs %zu bytes of shared memory, device allows %d", fixed + per_doc * 1024, e->max_smem_optin);
-    uint32_t W = static_cast<uint32_t>(std::min<size_t>((budget - fixed) / per_doc, 65536)) & ~31u;
-    if (e->window_docs) W = std::min<uint32_t>(W, static_cast<uint32_t>(e->window_docs) & ~31u);
-    P.W = W;
-    e->last_window = W;
-    const size_t smem = accum_smem_bytes(W, cap, P.max_terms, chlog, P.list_cap, e->need_cnt);
+    const size_t smem = e->plan_smem;
     const bool split = e->n_splits > 1;
     P.out_keys = split ? e->d_part_keys.p : e->d_keys.p;
     P.out_counts = split ? e->d_part_counts.p : e->d_counts.p;
