@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--log2-window", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
-    ap.add_argument("--ring-entries", type=int, default=0)
+    ap.add_argument("--warps-per-sm", type=int, default=0)
+    ap.add_argument("--window-docs", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="3 = batched decode_score + accumulate_topk (default), 2 = fused windows")
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
@@ -241,8 +242,10 @@ def main():
         reader.set_option("ctas_per_sm", args.ctas_per_sm)
     if args.warps:
         reader.set_option("warps", args.warps)
-    if args.ring_entries:
-        reader.set_option("ring_entries", args.ring_entries)
+    if args.warps_per_sm:
+        reader.set_option("warps_per_sm", args.warps_per_sm)
+    if args.window_docs:
+        reader.set_option("window_docs", args.window_docs)
     if args.kernel:
         reader.set_option("kernel", args.kernel)
     if world > 1:

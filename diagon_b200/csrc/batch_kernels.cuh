@@ -17,7 +17,7 @@ namespace {
 
 constexpr uint32_t kDocEnd = 0xFFFFFFFFu;   // doc id of the padding entries after a run (doc ids are < 2^31)
 constexpr int kItemBlocks = 64;             // posting blocks per decode work item
-constexpr int kPadBlocks = 5;               // kDocEnd blocks after every run: readers look up to 64 * (WARPS + 1) entries ahead
+constexpr int kPadBlocks = 1;               // kDocEnd blocks after every run: readers look at most 64 entries past a real one
 constexpr int kRunPad = kPadBlocks * DGPU_BLOCK_POSTINGS;  // scratch[0, kRunPad) is the empty run
 constexpr int kDecodeThreads = 256;
 
@@ -36,8 +36,8 @@ struct DItem {          // up to kItemBlocks consecutive blocks of one distinct 
 struct QTermRun {       // one query term, resolved to its run in the scratch
     uint32_t base;      // first scratch entry
     uint32_t len;       // entries that may hold postings (padding after them is readable)
-    uint32_t meta;      // DGPU_ROLE_* | log2(ring entries) << 8
-    uint32_t ring_off;  // first entry of its ring in the CTA's ring area
+    uint32_t meta;      // DGPU_ROLE_*
+    uint32_t pad;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -87,104 +87,125 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
 // ------------------------------------------------------------------------------------------------
 // K3b + K4
 // ------------------------------------------------------------------------------------------------
+struct WorkItem {       // one (query, doc range) scored by one warp
+    uint32_t query;
+    uint32_t doc_lo, doc_hi;
+    uint32_t pad;
+};
+
 struct AccumParams {
     const dgpu_query* queries;
     const QTermRun* terms;
     const dgpu_qfilter* filters;
-    const uint32_t* order;      // work items (query * n_splits + split) by decreasing cost
+    const WorkItem* items;
+    const uint32_t* order;      // item ids by decreasing cost
     uint32_t n_items;
-    uint32_t n_queries;
-    uint32_t n_splits;          // doc-range splits per query (small batches)
-    uint32_t split_docs;        // docs per split
     uint32_t* work_counter;
     const uint32_t* run_docs;
     const float* run_scores;
     int k;
     uint32_t W;                 // docs per window (multiple of 32, <= 65536)
-    uint32_t ring_entries;      // shared-memory ring area (entries) shared by the terms of one query
+    uint32_t chlog;             // log2 of the staged entries per term (1..5)
     uint32_t max_terms;         // multiple of 4
-    uint32_t cand_cap;          // power of two, >= 2k and >= k + threads
+    uint32_t cand_cap;          // power of two, >= 2k and >= k + 32
     uint32_t list_cap;          // touched-list capacity (entries)
-    uint64_t* out_keys;         // [split][query][k]
-    int32_t* out_counts;        // [split][query]
-    int64_t* out_hits;          // [split][query]
+    uint32_t warp_smem;         // bytes of shared memory owned by one warp (multiple of 16)
+    uint64_t* out_keys;         // [item][k]
+    int32_t* out_counts;        // [item]
+    int64_t* out_hits;          // [item]
 };
 
-constexpr int kTermWords = 6;   // per-term shared-memory state: cursor, advance, tail, previous tail, issue window, ring meta
-
-__host__ __device__ inline size_t accum_smem_bytes(uint32_t W, uint32_t cap, uint32_t max_terms, uint32_t ring_entries,
-                                                   uint32_t list_cap, bool need_cnt) {
+__host__ __device__ inline size_t accum_warp_smem_bytes(uint32_t W, uint32_t cap, uint32_t max_terms, uint32_t chlog,
+                                                        uint32_t list_cap, bool need_cnt) {
     size_t b = 0;
     b += sizeof(uint64_t) * cap;                          // candidate pool
-    b += 2 * sizeof(uint32_t) * ring_entries;             // rings: docs + scores
     b += sizeof(float) * W;                               // window accumulators
-    b += kTermWords * sizeof(uint32_t) * max_terms;       // per-term state
+    b += 2 * sizeof(uint32_t) * (static_cast<size_t>(max_terms) << chlog);  // staged docs + scores
+    b += sizeof(uint32_t) * max_terms;                    // cursors
     b += sizeof(uint16_t) * list_cap;                     // touched list
+    b += need_cnt ? max_terms : 0;                        // roles
     b += need_cnt ? W : 0;                                // match counts
-    return b + 16;
+    return (b + 15) & ~static_cast<size_t>(15);
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
-// The per-query pipeline (one CTA owns one (query, doc-range split) at a time):
-//   * every query term is a run of (doc, score) entries sorted by doc. The CTA keeps a cursor per term and a
-//     shared-memory RING per term (sizes proportional to the term's density, planned on the host) that is refilled
-//     with 16-byte cp.async copies one window ahead of use: copies issued at the end of window v are waited for at
-//     the end of window v + 1 (cp.async.wait_group 1), so their latency overlaps a whole window of work. A term
-//     that outruns its ring (too dense for the ring area) continues straight from global memory;
+// Descending bitonic sort of `n` keys (a power of two) in shared memory by one warp.
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* keys, uint32_t n, int lane) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncwarp();
+            for (uint32_t i = lane; i < n / 2; i += 32) {
+                const uint32_t lo = 2 * i - (i & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// One WARP owns one work item (a query, or a doc range of a long query) from start to finish: its own cursors,
+// window accumulators, touched list and candidate pool in its slice of shared memory. Warps never wait for each
+// other: no CTA barrier, no shared-memory atomics; the latency of one warp's loads is covered by the others.
+//   * every query term is a run of (doc, score) entries sorted by doc (decode_score_kernel). The warp keeps a cursor
+//     per term and the next CH = 2^chlog entries of every term staged in shared memory (cp.async; a term is restaged
+//     right after it has been applied, so the copy overlaps the rest of the window and the harvest);
 //   * a window starts at the smallest next doc of any term and covers W docs; empty doc ranges are never visited;
-//   * terms are applied in clause order (BooleanQuery.cpp:119-126, :232-241). A term with fewer than 32 entries
-//     in the window ("sparse" here) is applied by warp 0; consecutive sparse terms need no CTA barrier. Any other
-//     term ("dense") is applied by every warp, 64 entries per warp at a time, until a chunk crosses the window end;
+//   * terms are applied in clause order (BooleanQuery.cpp:119-126, :232-241): one scatter-add pass over the staged
+//     entries that fall into the window and, when all of them do, over the following 32-entry chunks of the run
+//     straight from global memory (coalesced, next chunk prefetched) until a chunk crosses the window end. One warp
+//     applying one term at a time gives every accumulator its clauses in order: bit-exact float sums;
 //   * every first touch of an accumulator appends the doc to the touched list, so the harvest costs O(postings),
 //     never O(W); a window with more touched docs than the list holds is harvested by a dense scan;
 //   * the harvest evaluates required-match counts and doc-value filters, counts hits and pushes candidates above the
-//     running threshold into the pool; the pool is pruned to the best k (bitonic sort) whenever it may overflow.
-template <int WARPS, bool NEED_CNT>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+//     running threshold into the pool; the pool is pruned to the best k (warp bitonic sort) whenever it may overflow.
+template <bool NEED_CNT>
+__global__ void __launch_bounds__(256, 1)
 accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
-    constexpr int T = WARPS * 32;
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t W = P.W;
+    const uint32_t chlog = P.chlog, CH = 1u << chlog;
     uint64_t* cand;
     float* acc;
-    uint32_t *rdoc, *pos, *adv, *tail, *tprev, *iwin, *rmeta;
-    float* rsc;
+    uint32_t *sdoc, *pos;
+    float* ssc;
     uint16_t* tlist;
-    uint8_t* cnt;
+    uint8_t *role, *cnt;
     {
-        uint8_t* sp = smem_raw;
+        uint8_t* sp = smem_raw + static_cast<size_t>(warp) * P.warp_smem;
         cand = reinterpret_cast<uint64_t*>(sp);  sp += sizeof(uint64_t) * P.cand_cap;
-        rdoc = reinterpret_cast<uint32_t*>(sp);  sp += sizeof(uint32_t) * P.ring_entries;
-        rsc = reinterpret_cast<float*>(sp);      sp += sizeof(float) * P.ring_entries;
         acc = reinterpret_cast<float*>(sp);      sp += sizeof(float) * W;
+        sdoc = reinterpret_cast<uint32_t*>(sp);  sp += sizeof(uint32_t) * (static_cast<size_t>(P.max_terms) << chlog);
+        ssc = reinterpret_cast<float*>(sp);      sp += sizeof(float) * (static_cast<size_t>(P.max_terms) << chlog);
         pos = reinterpret_cast<uint32_t*>(sp);   sp += sizeof(uint32_t) * P.max_terms;
-        adv = reinterpret_cast<uint32_t*>(sp);   sp += sizeof(uint32_t) * P.max_terms;
-        tail = reinterpret_cast<uint32_t*>(sp);  sp += sizeof(uint32_t) * P.max_terms;
-        tprev = reinterpret_cast<uint32_t*>(sp); sp += sizeof(uint32_t) * P.max_terms;
-        iwin = reinterpret_cast<uint32_t*>(sp);  sp += sizeof(uint32_t) * P.max_terms;
-        rmeta = reinterpret_cast<uint32_t*>(sp); sp += sizeof(uint32_t) * P.max_terms;  // ring offset | log2 size << 16 | role << 24
         tlist = reinterpret_cast<uint16_t*>(sp); sp += sizeof(uint16_t) * P.list_cap;
+        role = sp;                               sp += NEED_CNT ? P.max_terms : 0;
         cnt = sp;
     }
-    __shared__ uint32_t s_item, s_cand, s_nlist, s_hits;
-    __shared__ uint32_t s_amask[32];
-    __shared__ uint64_t s_thresh;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* acc_bits = reinterpret_cast<uint32_t*>(acc);
 
-    for (uint32_t i = tid; i < W; i += T) {
+    for (uint32_t i = lane; i < W; i += 32) {
         acc_bits[i] = kSentinel;
         if (NEED_CNT) cnt[i] = 0;
     }
+
+    // staged entry e of term t: rows are rotated by t so that "entry 0 of every term" is a conflict-free access
+    auto sidx = [&](uint32_t t, uint32_t e) -> uint32_t { return (t << chlog) + ((e + t) & (CH - 1u)); };
+
+    uint32_t n_list = 0;   // touched docs of the current window (warp-uniform)
 
     // scatter-add of up to 32 entries of one term (distinct docs); appends first touches to the touched list
     auto apply = [&](bool in, uint32_t r, float s, uint32_t rl) {
@@ -206,96 +227,33 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
             }
         }
         const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
-        if (fm) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_nlist, static_cast<uint32_t>(__popc(fm)));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (first) {
-                const uint32_t idx = base + __popc(fm & lt_mask);
-                if (idx < P.list_cap) tlist[idx] = static_cast<uint16_t>(r);
-            }
+        if (first) {
+            const uint32_t idx = n_list + __popc(fm & lt_mask);
+            if (idx < P.list_cap) tlist[idx] = static_cast<uint16_t>(r);
         }
-    };
-
-    auto prune = [&](uint32_t have) {  // CTA-wide: keep the best k of the pool, raise the threshold
-        const uint32_t n = min(P.cand_cap, pow2_at_least(have));
-        for (uint32_t i = have + tid; i < n; i += T) cand[i] = 0;
-        bitonic_sort_desc(cand, n);
-        if (tid == 0) {
-            s_cand = min(have, static_cast<uint32_t>(P.k));
-            s_thresh = (have >= static_cast<uint32_t>(P.k)) ? cand[P.k - 1] : 0ull;
-        }
-        __syncthreads();
-    };
-
-    // copy entries [from, to) of a run into the term's ring (both multiples of 4 entries)
-    auto ring_copy = [&](uint32_t roff, uint32_t rmask, uint32_t from, uint32_t to) {
-        for (uint32_t i = from + 4u * lane; i < to; i += 128u) {
-            cp_async16(rdoc + roff + (i & rmask), P.run_docs + i);
-            cp_async16(rsc + roff + (i & rmask), P.run_scores + i);
-        }
-    };
-
-    // window-end bookkeeping of term t (one warp): fold the advance into the cursor and top the ring up
-    auto refill_term = [&](uint32_t t, uint32_t v) {
-        uint32_t head = 0;
-        if (lane == 0) {
-            head = pos[t] + adv[t];
-            pos[t] = head;
-            adv[t] = 0;
-        }
-        head = __shfl_sync(0xFFFFFFFFu, head, 0);
-        const uint32_t meta = rmeta[t];
-        const uint32_t roff = meta & 0xFFFFu, R = 1u << ((meta >> 16) & 0xFFu), unit = R >> 2;
-        const uint32_t hf = head & ~(unit - 1u);
-        uint32_t tl = tail[t];
-        bool changed = false;
-        if (hf > tl) {
-            // the term outran its ring (it continued from global memory): restart the ring at the cursor. This warp
-            // issued every copy of this term, so waiting for its own copies makes the slots safe to overwrite.
-            cp_async_wait_all();
-            tl = hf;
-            changed = true;
-        }
-        const uint32_t old_tail = tl;
-        while (tl + unit <= hf + R) {
-            ring_copy(roff, R - 1u, tl, tl + unit);
-            tl += unit;
-            changed = true;
-        }
-        if (changed && lane == 0) {
-            tprev[t] = old_tail;   // everything before it was issued at least one window ago
-            tail[t] = tl;
-            iwin[t] = v;
-        }
+        n_list += __popc(fm);
     };
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            s_item = atomicAdd(P.work_counter, 1u);
-            s_cand = 0;
-            s_hits = 0;
-            s_nlist = 0;
-            s_thresh = 0;
-        }
-        __syncthreads();
-        if (s_item >= P.n_items) break;
-        const uint32_t item = P.order[s_item];
-        const uint32_t q = item / P.n_splits, split = item - q * P.n_splits;
-        const dgpu_query qd = P.queries[q];
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(P.work_counter, 1u);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (slot >= P.n_items) break;
+        const uint32_t item = P.order[slot];
+        const WorkItem wi = P.items[item];
+        const dgpu_query qd = P.queries[wi.query];
         const QTermRun* qt = P.terms + qd.term_begin;
         const uint32_t nt = qd.term_end - qd.term_begin;
         const uint32_t nf = qd.filter_end - qd.filter_begin;
         const dgpu_qfilter* qf = P.filters + qd.filter_begin;
-        const uint32_t lo = ix.doc_lo + split * P.split_docs;
-        const uint32_t hi = (split + 1 == P.n_splits) ? ix.doc_hi : min(lo + P.split_docs, ix.doc_hi);
+        const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
         const uint32_t n_groups = (nt + 31u) >> 5;
 
-        for (uint32_t t = tid; t < nt; t += T) {
+        __syncwarp();
+        for (uint32_t t = lane; t < nt; t += 32) {
             const QTermRun r = qt[t];
             uint32_t p = r.base;
-            if (split > 0) {  // first entry with doc >= lo
+            if (lo > ix.doc_lo) {  // first entry with doc >= lo
                 uint32_t a = 0, b = r.len;
                 while (a < b) {
                     const uint32_t mid = (a + b) >> 1;
@@ -303,212 +261,204 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                 }
                 p = r.base + a;
             }
-            const uint32_t R = 1u << ((r.meta >> 8) & 0xFFu), unit = R >> 2;
             pos[t] = p;
-            adv[t] = 0;
-            tail[t] = p & ~(unit - 1u);   // nothing issued yet; the first refill fills the whole ring
-            tprev[t] = 0;
-            iwin[t] = 0;
-            rmeta[t] = (r.ring_off & 0xFFFFu) | (((r.meta >> 8) & 0xFFu) << 16) | ((r.meta & 0xFFu) << 24);
+            if (NEED_CNT) role[t] = static_cast<uint8_t>(r.meta);
         }
-        __syncthreads();
-        for (uint32_t t = warp; t < nt; t += WARPS) refill_term(t, 0u);
+        __syncwarp();
+        for (uint32_t t = 0; t < nt; ++t) {
+            const uint32_t p = pos[t];
+            if (static_cast<uint32_t>(lane) < CH) {
+                cp_async4(sdoc + sidx(t, lane), P.run_docs + p + lane);
+                cp_async4(ssc + sidx(t, lane), P.run_scores + p + lane);
+            }
+        }
         cp_async_commit();
         cp_async_wait_all();
-        __syncthreads();
-        uint32_t my_hits = 0;
+        __syncwarp();
 
-        // v counts windows; copies issued at the end of window u are complete from window u + 2 on
-        for (uint32_t v = 2;; ++v) {
-            // The pool count is only written during a harvest; it is read here, a whole phase away from the next
-            // push, so that every thread sees the same value.
-            uint32_t have = s_cand;
+        uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
+        uint64_t thresh = 0;        // key of the k-th best so far (0 until the pool has been pruned once with >= k)
+        uint32_t hits = 0;          // per lane
+
+        auto prune = [&]() {   // keep the best k of the pool, raise the threshold
+            const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
+            for (uint32_t i = n_cand + lane; i < n; i += 32) cand[i] = 0;
+            warp_bitonic_sort_desc(cand, n, lane);
+            if (n_cand >= static_cast<uint32_t>(P.k)) {
+                thresh = cand[P.k - 1];
+                n_cand = P.k;
+            }
+        };
+
+        for (;;) {
             // ---- window start: the smallest next doc of any term
             uint32_t m = kDocEnd;
-            for (uint32_t t = lane; t < nt; t += 32) {
-                const uint32_t head = pos[t], meta = rmeta[t];
-                const uint32_t ready = (iwin[t] + 2u <= v) ? tail[t] : tprev[t];
-                const uint32_t d = head < ready ? rdoc[(meta & 0xFFFFu) + (head & ((1u << ((meta >> 16) & 0xFFu)) - 1u))]
-                                                : __ldg(P.run_docs + head);
-                m = min(m, d);
-            }
+            for (uint32_t t = lane; t < nt; t += 32) m = min(m, sdoc[sidx(t, 0)]);
             m = __reduce_min_sync(0xFFFFFFFFu, m);
             if (m >= hi) break;
             const uint32_t ws = m;
             const uint32_t we = (hi - ws > W) ? ws + W : hi;
+            n_list = 0;
 
-            // ---- rounds in clause order
-            bool pending_sparse = false;
+            // ---- terms in clause order
             for (uint32_t g = 0; g < n_groups; ++g) {
                 const uint32_t t = (g << 5) + lane;
-                uint32_t d_first = kDocEnd, d_32 = 0, head_t = 0, meta_t = 0, ready_t = 0;
+                uint32_t d_first = kDocEnd, d_last = kDocEnd;
                 if (t < nt) {
-                    head_t = pos[t];
-                    meta_t = rmeta[t];
-                    ready_t = (iwin[t] + 2u <= v) ? tail[t] : tprev[t];
-                    const uint32_t roff = meta_t & 0xFFFFu, rmask = (1u << ((meta_t >> 16) & 0xFFu)) - 1u;
-                    d_first = head_t < ready_t ? rdoc[roff + (head_t & rmask)] : __ldg(P.run_docs + head_t);
-                    // sparse needs its first 32 entries in the ring and the 32nd of them past the window
-                    d_32 = head_t + 32u <= ready_t ? rdoc[roff + ((head_t + 31u) & rmask)] : 0u;
+                    d_first = sdoc[sidx(t, 0)];
+                    d_last = sdoc[sidx(t, CH - 1u)];
                 }
-                const uint32_t active = __ballot_sync(0xFFFFFFFFu, d_first < we);
-                const uint32_t dense = __ballot_sync(0xFFFFFFFFu, d_32 < we);
-                if (tid == 0) s_amask[g] = active;
-                uint32_t rem = active;
+                uint32_t rem = __ballot_sync(0xFFFFFFFFu, d_first < we);
+                const uint32_t dense = __ballot_sync(0xFFFFFFFFu, d_last < we);
                 while (rem) {
                     const int b = __ffs(rem) - 1;
                     rem &= rem - 1;
                     const uint32_t tt = (g << 5) + b;
-                    const uint32_t head = __shfl_sync(0xFFFFFFFFu, head_t, b);
-                    const uint32_t meta = __shfl_sync(0xFFFFFFFFu, meta_t, b);
-                    const uint32_t roff = meta & 0xFFFFu, rmask = (1u << ((meta >> 16) & 0xFFu)) - 1u;
-                    const uint32_t rl = meta >> 24;
-                    if (!((dense >> b) & 1u)) {
-                        if (warp == 0) {
-                            const uint32_t i = head + lane;
-                            const uint32_t d = rdoc[roff + (i & rmask)];
-                            const float s = rsc[roff + (i & rmask)];
+                    const uint32_t rl = NEED_CNT ? role[tt] : 0u;
+                    uint32_t d = kDocEnd;
+                    float s = 0.f;
+                    if (static_cast<uint32_t>(lane) < CH) {
+                        d = sdoc[sidx(tt, lane)];
+                        s = ssc[sidx(tt, lane)];
+                    }
+                    uint32_t p = pos[tt];
+                    {
+                        const bool in = d < we;
+                        const uint32_t im = __ballot_sync(0xFFFFFFFFu, in);
+                        apply(in, d - ws, s, rl);
+                        p += __popc(im);
+                    }
+                    if ((dense >> b) & 1u) {
+                        // every staged entry was inside the window: go on with the run in global memory
+                        d = __ldg(P.run_docs + p + lane);
+                        s = __ldg(P.run_scores + p + lane);
+                        for (;;) {
                             const bool in = d < we;
                             const uint32_t im = __ballot_sync(0xFFFFFFFFu, in);
-                            apply(in, d - ws, s, rl);
-                            if (lane == 0) adv[tt] = __popc(im);
-                        }
-                        pending_sparse = true;
-                    } else {
-                        const uint32_t ready = __shfl_sync(0xFFFFFFFFu, ready_t, b);
-                        if (pending_sparse) {
-                            __syncthreads();
-                            pending_sparse = false;
-                        }
-                        // chunk c = entries [head + 64c, head + 64c + 64): from the ring when all of it has landed
-                        auto load2 = [&](uint32_t c, uint32_t& d0, float& s0, uint32_t& d1, float& s1) {
-                            const uint32_t i = head + 64u * c + lane;
-                            if (i - lane + 64u <= ready) {
-                                d0 = rdoc[roff + (i & rmask)];
-                                s0 = rsc[roff + (i & rmask)];
-                                d1 = rdoc[roff + ((i + 32u) & rmask)];
-                                s1 = rsc[roff + ((i + 32u) & rmask)];
-                            } else {
-                                d0 = __ldg(P.run_docs + i);
-                                s0 = __ldg(P.run_scores + i);
-                                d1 = __ldg(P.run_docs + i + 32u);
-                                s1 = __ldg(P.run_scores + i + 32u);
+                            uint32_t d_next = 0;
+                            float s_next = 0.f;
+                            if (im == 0xFFFFFFFFu) {   // the run continues inside the window: prefetch the next chunk
+                                d_next = __ldg(P.run_docs + p + 32u + lane);
+                                s_next = __ldg(P.run_scores + p + 32u + lane);
                             }
-                        };
-                        uint32_t n_in = 0, c = warp, d0, d1;
-                        float s0, s1;
-                        load2(c, d0, s0, d1, s1);
-                        for (;;) {
-                            const bool in0 = d0 < we, in1 = d1 < we;
-                            const uint32_t im0 = __ballot_sync(0xFFFFFFFFu, in0);
-                            const uint32_t im1 = __ballot_sync(0xFFFFFFFFu, in1);
-                            uint32_t e0 = 0, e1 = 0;
-                            float f0 = 0.f, f1 = 0.f;
-                            if (im1 == 0xFFFFFFFFu) load2(c + WARPS, e0, f0, e1, f1);  // prefetch this warp's next chunk
-                            apply(in0, d0 - ws, s0, rl);
-                            if (im1) apply(in1, d1 - ws, s1, rl);
-                            n_in += __popc(im0) + __popc(im1);
-#ifdef DGPU_DEBUG
-                            if (lane == 0) printf("v=%u t=%u warp=%d c=%u head=%u ready=%u d0=%u d1=%u im0=%08x im1=%08x ws=%u we=%u\n", v, tt, warp, c, head, ready, d0, d1, im0, im1, ws, we);
-#endif
-                            if (im1 != 0xFFFFFFFFu) break;
-                            c += WARPS;
-                            d0 = e0; s0 = f0; d1 = e1; s1 = f1;
+                            apply(in, d - ws, s, rl);
+                            p += __popc(im);
+                            if (im != 0xFFFFFFFFu) break;
+                            d = d_next;
+                            s = s_next;
                         }
-                        if (lane == 0 && n_in) atomicAdd(&adv[tt], n_in);
-                        __syncthreads();
                     }
-                }
-            }
-            __syncthreads();
-
-            // ---- top the rings of the terms that advanced up (the copies overlap the harvest and the next window)
-            for (uint32_t g = 0; g < n_groups; ++g) {
-                uint32_t rem = s_amask[g];
-                while (rem) {
-                    const int b = __ffs(rem) - 1;
-                    rem &= rem - 1;
-                    const uint32_t tt = (g << 5) + b;
-                    if ((tt % WARPS) == static_cast<uint32_t>(warp)) refill_term(tt, v);
+                    // restage the term at its new cursor; the copy lands while the rest of the window is processed
+                    __syncwarp();
+                    if (lane == 0) pos[tt] = p;
+                    if (static_cast<uint32_t>(lane) < CH) {
+                        cp_async4(sdoc + sidx(tt, lane), P.run_docs + p + lane);
+                        cp_async4(ssc + sidx(tt, lane), P.run_scores + p + lane);
+                    }
                 }
             }
             cp_async_commit();
+            __syncwarp();
 
             // ---- harvest
-            const uint32_t n_list = s_nlist;
-#ifdef DGPU_DEBUG
-            if (tid == 0) printf("v=%u harvest n_list=%u ws=%u we=%u\n", v, n_list, ws, we);
-#endif
             const bool dense_scan = n_list > P.list_cap;
             const uint32_t total = dense_scan ? (we - ws) : n_list;
-            uint64_t thresh = s_thresh;
-            uint32_t base = 0;
-            while (base < total) {
-                const uint32_t remaining = total - base;
-                const uint32_t take = min(remaining, P.cand_cap - have);
-                if (take < min(remaining, static_cast<uint32_t>(T))) {
-                    prune(have);
-                    have = min(have, static_cast<uint32_t>(P.k));
-                    thresh = s_thresh;
-                    continue;
-                }
-                const uint32_t thresh_hi = static_cast<uint32_t>(thresh >> 32);
-                for (uint32_t i = base + tid; i < base + take; i += T) {
+            for (uint32_t base = 0; base < total; base += 32) {
+                if (n_cand + 32u > P.cand_cap) prune();
+                const uint32_t i = base + lane;
+                bool push = false;
+                uint64_t key = 0;
+                if (i < total) {
                     const uint32_t r = dense_scan ? i : tlist[i];
                     const uint32_t bits = acc_bits[r];
                     const uint8_t c = NEED_CNT ? cnt[r] : 0;
-                    if (dense_scan && bits == kSentinel && c == 0) continue;
-                    bool match = bits != kSentinel;  // touched only by an excluded term otherwise
-                    if (NEED_CNT && match) match = (c != 255) && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
-                    const uint32_t doc = ws + r;
-                    float score = __uint_as_float(bits);
-                    for (uint32_t f = 0; f < nf && match; ++f) {
-                        const int64_t val = ix.dv[qf[f].column][doc - ix.doc_lo];
-                        match = (val >= qf[f].lo) && (val <= qf[f].hi);
-                        score = __fadd_rn(score, 1.0f);  // constant score of the range clause (NumericRangeQuery.cpp:117-120)
-                    }
-                    if (match) {
-                        const uint32_t sb = __float_as_uint(score);
-                        const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
-                        // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:171-174)
-                        if (ord >= thresh_hi && (sb & 0x7F800000u) != 0x7F800000u) {
-                            const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
-                            if (key > thresh) cand[atomicAdd(&s_cand, 1u)] = key;
+                    if (!(dense_scan && bits == kSentinel && c == 0)) {
+                        bool match = bits != kSentinel;  // touched only by an excluded term otherwise
+                        if (NEED_CNT && match) match = (c != 255) && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
+                        const uint32_t doc = ws + r;
+                        float score = __uint_as_float(bits);
+                        for (uint32_t f = 0; f < nf && match; ++f) {
+                            const int64_t val = ix.dv[qf[f].column][doc - ix.doc_lo];
+                            match = (val >= qf[f].lo) && (val <= qf[f].hi);
+                            score = __fadd_rn(score, 1.0f);  // constant score of the range clause (NumericRangeQuery.cpp:117-120)
                         }
-                        ++my_hits;  // TopScoreDocCollector.cpp:165-168
+                        if (match) {
+                            const uint32_t sb = __float_as_uint(score);
+                            const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+                            // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:171-174)
+                            key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
+                            push = key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+                            ++hits;  // TopScoreDocCollector.cpp:165-168
+                        }
+                        acc_bits[r] = kSentinel;
+                        if (NEED_CNT) cnt[r] = 0;
                     }
-                    acc_bits[r] = kSentinel;
-                    if (NEED_CNT) cnt[r] = 0;
                 }
-                base += take;
-                __syncthreads();                 // the pushes of this sub-batch are done
-                if (base < total) {
-                    have = s_cand;
-                    __syncthreads();             // everybody has read the count before anyone pushes again
-                }
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
+                if (push) cand[n_cand + __popc(pm & lt_mask)] = key;
+                n_cand += __popc(pm);
             }
-            if (tid == 0) s_nlist = 0;
-            cp_async_wait_but_last();
-            __syncthreads();
+            cp_async_wait_all();
+            __syncwarp();
         }
 
         // ---- final select
-        cp_async_wait_all();   // nothing may still be landing in the rings when the next item re-plans them
-        __syncthreads();
-        if (my_hits) atomicAdd(&s_hits, my_hits);
-        __syncthreads();
-        const uint32_t have = s_cand;
-        const uint32_t nsort = min(P.cand_cap, pow2_at_least(have));
-        for (uint32_t i = have + tid; i < nsort; i += T) cand[i] = 0;
-        bitonic_sort_desc(cand, nsort);
-        const uint32_t n_out = min(have, static_cast<uint32_t>(P.k));
-        const size_t slot = static_cast<size_t>(split) * P.n_queries + q;
-        for (uint32_t i = tid; i < static_cast<uint32_t>(P.k); i += T)
-            P.out_keys[slot * P.k + i] = i < n_out ? cand[i] : 0ull;
-        if (tid == 0) {
-            P.out_counts[slot] = static_cast<int32_t>(n_out);
-            P.out_hits[slot] = static_cast<int64_t>(s_hits);
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xFFFFFFFFu, hits, o);
+        const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
+        for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;
+        warp_bitonic_sort_desc(cand, nsort, lane);
+        const uint32_t n_out = min(n_cand, static_cast<uint32_t>(P.k));
+        for (uint32_t i = lane; i < static_cast<uint32_t>(P.k); i += 32)
+            P.out_keys[static_cast<size_t>(item) * P.k + i] = i < n_out ? cand[i] : 0ull;
+        if (lane == 0) {
+            P.out_counts[item] = static_cast<int32_t>(n_out);
+            P.out_hits[item] = static_cast<int64_t>(hits);
         }
+        __syncwarp();
+    }
+}
+
+// Merge of the parts of every query (doc-range splits, consecutive items [part_off[q], part_off[q + 1])): every key
+// finds its rank by binary search in the other parts' sorted lists; keys are unique (distinct docs).
+__global__ void merge_items_kernel(const uint64_t* __restrict__ part_keys, const int32_t* __restrict__ part_counts,
+                                   const int64_t* __restrict__ part_hits, const uint32_t* __restrict__ part_off,
+                                   uint32_t n_queries, int k, uint64_t* __restrict__ out_keys,
+                                   int32_t* __restrict__ out_counts, int64_t* __restrict__ out_hits) {
+    const uint32_t q = blockIdx.x;
+    if (q >= n_queries) return;
+    const uint32_t p0 = part_off[q], n_parts = part_off[q + 1] - p0;
+    int total = 0;
+    int64_t hits = 0;
+    for (uint32_t p = 0; p < n_parts; ++p) {
+        total += part_counts[p0 + p];
+        hits += part_hits[p0 + p];
+    }
+    const int n_out = min(total, k);
+    for (int i = threadIdx.x; i < k; i += blockDim.x)
+        if (i >= n_out) out_keys[static_cast<size_t>(q) * k + i] = 0ull;
+    for (uint32_t e = threadIdx.x; e < n_parts * static_cast<uint32_t>(k); e += blockDim.x) {
+        const uint32_t p = e / k;
+        const int i = static_cast<int>(e % k);
+        if (i >= part_counts[p0 + p]) continue;
+        const uint64_t key = part_keys[static_cast<size_t>(p0 + p) * k + i];
+        int rank = i;
+        for (uint32_t o = 0; o < n_parts; ++o) {
+            if (o == p) continue;
+            const uint64_t* ok = part_keys + static_cast<size_t>(p0 + o) * k;
+            int a = 0, b = part_counts[p0 + o];
+            while (a < b) {  // number of keys in part o greater than key
+                const int mid = (a + b) >> 1;
+                if (ok[mid] > key) a = mid + 1; else b = mid;
+            }
+            rank += a;
+        }
+        if (rank < k) out_keys[static_cast<size_t>(q) * k + rank] = key;
+    }
+    if (threadIdx.x == 0) {
+        out_counts[q] = n_out;
+        out_hits[q] = hits;
     }
 }
 

@@ -111,23 +111,28 @@ struct dgpu_engine {
     DevBuf<int64_t> d_part_hits;
     uint32_t n_dterms = 0, n_ditems = 0;
     uint64_t run_entries = 0;
-    uint32_t n_splits = 1, split_docs = 0;
+    uint32_t n_splits = 1;              // average doc-range parts per query of the staged batch (reporting only)
     uint64_t distinct_bytes = 0;        // compressed bytes (payload + 16 B skip row per block) of the distinct terms
     uint32_t last_window = 0;
     // launch plan of the batched path (made by stage_batch: the host sizes the per-term rings with it)
-    uint32_t plan_cap = 0, plan_list = 0, plan_ring = 0, plan_W = 0;
-    size_t plan_smem = 0;
+    uint32_t plan_cap = 0, plan_list = 0, plan_chlog = 5, plan_W = 0, plan_wpc = 4, plan_ctas = 1, plan_warp_smem = 0;
+    DevBuf<WorkItem> d_witems;
+    DevBuf<uint32_t> d_part_off;
+    uint32_t n_witems = 0;
+    bool split_any = false;
     std::vector<uint32_t> h_slot;       // term id -> distinct slot of the batch being staged (epoch stamped)
     std::vector<uint32_t> h_slot_epoch;
     uint32_t epoch = 0;
     // options
     int logw = 15;
     int ctas_per_sm = 3;
-    int warps = 4;
+    int warps = 4;           // warps per CTA of accumulate_topk_kernel
     int kernel = 3;          // 3 = batched (decode_score + accumulate_topk), 2 = per-query fused windows
     int force_splits = 0;    // 0 = automatic
     int window_docs = 0;     // 0 = the largest window that fits; else an upper bound (tests)
-    int ring_entries = 2048; // shared-memory ring area per CTA (entries of 8 bytes), grown for queries with many terms
+    int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
+    int warps_per_sm = 16;   // independent scoring warps per SM (each owns 1/n of the shared memory)
+    int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
     // stats
     uint64_t launches = 0;
     float last_ms = 0.f;
@@ -145,62 +150,42 @@ static int upload_array(dgpu_engine* e, const T* host, size_t n, const T** dev) 
     return 0;
 }
 
-// Launch geometry of accumulate_topk_kernel for the staged batch: candidate pool, touched list, ring area and the
-// window that fills what is left of the CTA's share of shared memory.
+// Launch geometry of accumulate_topk_kernel for the staged batch: every warp gets an equal slice of the SM's shared
+// memory; what the candidate pool, the staged entries and the touched list leave of it is the doc window.
 static int plan_batched(dgpu_engine* e) {
     const uint32_t max_terms = (e->max_terms + 3u) & ~3u;
-    const uint32_t threads = static_cast<uint32_t>(e->warps) * 32u;
-    uint32_t cap = 256;
-    while (cap < 2u * static_cast<uint32_t>(e->k) || cap < static_cast<uint32_t>(e->k) + threads) cap <<= 1;
-    uint32_t ring = static_cast<uint32_t>(e->ring_entries);
-    while (ring < 16u * max_terms) ring <<= 1;   // every term needs a ring of at least 16 entries
-    const uint32_t list_cap = 2048;
-    const size_t per_sm = 228 * 1024;
-    const size_t optin = static_cast<size_t>(e->max_smem_optin) - 512;   // the kernel's static shared memory
-    size_t budget = std::min<size_t>(per_sm / e->ctas_per_sm - 1024, optin);
-    const size_t fixed = accum_smem_bytes(0, cap, max_terms, ring, list_cap, e->need_cnt);
+    uint32_t cap = 64;
+    while (cap < 2u * static_cast<uint32_t>(e->k) || cap < static_cast<uint32_t>(e->k) + 32u) cap <<= 1;
+    uint32_t chlog = 5;   // staged entries per term: 32 up to 16 terms, halved for every doubling after that
+    while (chlog > 1 && (static_cast<size_t>(max_terms) << chlog) * 8 > 4096) --chlog;
+    if (e->stage_log2) chlog = std::min<uint32_t>(chlog, static_cast<uint32_t>(e->stage_log2));
+    const uint32_t list_cap = 512;
     const size_t per_doc = e->need_cnt ? 5 : 4;
-    if (budget < fixed + per_doc * 2048) budget = optin;
-    if (budget < fixed + per_doc * 1024)
-        return fail("search needs %zu bytes of shared memory, device allows %d", fixed + per_doc * 1024, e->max_smem_optin);
-    uint32_t W = static_cast<uint32_t>(std::min<size_t>((budget - fixed) / per_doc, 65536)) & ~31u;
-    if (e->window_docs) W = std::min<uint32_t>(W, static_cast<uint32_t>(e->window_docs) & ~31u);
-    e->plan_cap = cap;
-    e->plan_list = list_cap;
-    e->plan_ring = ring;
-    e->plan_W = W;
-    e->plan_smem = accum_smem_bytes(W, cap, max_terms, ring, list_cap, e->need_cnt);
-    e->last_window = W;
-    return 0;
-}
-
-// Ring sizes of one query: a power of two per term, about three windows of its expected postings, at least `rmin`,
-// halving the largest until the sum fits the ring area.
-static void plan_rings(QTermRun* runs, uint32_t nt, uint32_t ring_entries, uint32_t W, uint32_t doc_range) {
-    if (nt == 0) return;
-    uint32_t rmin = 128;
-    while (rmin > 16 && static_cast<uint64_t>(rmin) * nt > ring_entries) rmin >>= 1;
-    uint32_t lg[1024];
-    uint64_t sum = 0;
-    for (uint32_t t = 0; t < nt; ++t) {
-        const uint64_t est = static_cast<uint64_t>(runs[t].len) * W / std::max(1u, doc_range);  // postings per window
-        uint32_t l = 4;
-        while ((1u << l) < rmin || ((1ull << l) < 3 * est && l < 13)) ++l;
-        lg[t] = l;
-        sum += 1ull << l;
-    }
-    while (sum > ring_entries) {
-        uint32_t best = 0;
-        for (uint32_t t = 1; t < nt; ++t)
-            if (lg[t] > lg[best]) best = t;
-        sum -= 1ull << (lg[best] - 1);
-        --lg[best];
-    }
-    uint32_t off = 0;
-    for (uint32_t t = 0; t < nt; ++t) {
-        runs[t].meta = (runs[t].meta & 0xFFu) | (lg[t] << 8);
-        runs[t].ring_off = off;
-        off += 1u << lg[t];
+    const size_t fixed = accum_warp_smem_bytes(0, cap, max_terms, chlog, list_cap, e->need_cnt);
+    const size_t per_sm = 227 * 1024;
+    const size_t optin = static_cast<size_t>(e->max_smem_optin) - 256;
+    // warps per SM: the requested number, fewer when a warp's fixed part (large k, many terms) needs the room
+    uint32_t wpc = static_cast<uint32_t>(e->warps);          // warps per CTA
+    uint32_t ctas = std::max(1u, static_cast<uint32_t>(e->warps_per_sm) / wpc);
+    for (;;) {
+        const size_t cta_budget = std::min(per_sm / ctas - 1024, optin);
+        const size_t warp_budget = (cta_budget / wpc) & ~static_cast<size_t>(15);
+        if (warp_budget >= fixed + per_doc * 512) {
+            uint32_t W = static_cast<uint32_t>(std::min<size_t>((warp_budget - fixed) / per_doc, 65536)) & ~31u;
+            if (e->window_docs) W = std::min<uint32_t>(W, static_cast<uint32_t>(e->window_docs) & ~31u);
+            e->plan_cap = cap;
+            e->plan_list = list_cap;
+            e->plan_chlog = chlog;
+            e->plan_W = W;
+            e->plan_wpc = wpc;
+            e->plan_ctas = ctas;
+            e->plan_warp_smem = static_cast<uint32_t>(accum_warp_smem_bytes(W, cap, max_terms, chlog, list_cap, e->need_cnt));
+            e->last_window = W;
+            return 0;
+        }
+        if (ctas > 1) --ctas;
+        else if (wpc > 1) wpc >>= 1;
+        else return fail("search needs %zu bytes of shared memory per warp, device allows %zu", fixed + per_doc * 512, optin);
     }
 }
 
@@ -239,6 +224,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     e->d_counter.release(); e->d_keys.release(); e->d_counts.release(); e->d_hits.release();
     e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_run_docs.release(); e->d_run_scores.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
+    e->d_witems.release(); e->d_part_off.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_a) cudaEventDestroy(e->ev_a);
@@ -264,7 +250,7 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         return 0;
     }
     if (!std::strcmp(name, "warps")) {
-        if (value != 4 && value != 8) return fail("warps must be 4 or 8");
+        if (value != 1 && value != 2 && value != 4 && value != 8) return fail("warps (per CTA) must be 1, 2, 4 or 8");
         e->warps = static_cast<int>(value);
         return 0;
     }
@@ -278,14 +264,24 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->window_docs = static_cast<int>(value);
         return 0;
     }
-    if (!std::strcmp(name, "ring_entries")) {
-        if (value < 64 || value > 16384 || (value & (value - 1))) return fail("ring_entries must be a power of two in [64, 16384]");
-        e->ring_entries = static_cast<int>(value);
+    if (!std::strcmp(name, "stage_log2")) {
+        if (value < 0 || value > 5) return fail("stage_log2 must be in [0, 5]");
+        e->stage_log2 = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "warps_per_sm")) {
+        if (value < 1 || value > 64) return fail("warps_per_sm must be in [1, 64]");
+        e->warps_per_sm = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "splits")) {
         if (value < 0 || value > 64) return fail("splits must be in [0, 64]");
         e->force_splits = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "max_parts")) {
+        if (value < 0 || value > 64) return fail("max_parts must be in [0, 64]");
+        e->max_parts = static_cast<int>(value);
         return 0;
     }
     return fail("unknown option %s", name);
@@ -453,41 +449,49 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->run_entries = run_entries;
     e->distinct_bytes = distinct_bytes;
     if (plan_batched(e)) return -1;
-    for (uint32_t q = 0; q < b->n_queries; ++q) {
-        const dgpu_query& qd = b->queries[q];
-        plan_rings(qruns.data() + qd.term_begin, qd.term_end - qd.term_begin, e->plan_ring, e->plan_W,
-                   e->ix.doc_hi - e->ix.doc_lo);
-    }
 
-    // ---- doc-range splits: a small batch is cut so that every SM has work
+    // ---- work items: one warp scores one (query, doc range). A long query is cut into doc-range parts so that no
+    // single warp becomes the tail of the batch and a small batch still fills the GPU; parts are merged on the device.
     const uint32_t doc_range = e->ix.doc_hi - e->ix.doc_lo;
-    uint32_t n_splits = 1;
-    if (e->kernel == 3 && b->n_queries) {
-        const uint64_t target = static_cast<uint64_t>(e->sm_count) * e->ctas_per_sm;
-        n_splits = e->force_splits ? static_cast<uint32_t>(e->force_splits)
-                                   : static_cast<uint32_t>(std::min<uint64_t>(32, target / b->n_queries));
-        n_splits = std::max(1u, std::min(n_splits, doc_range / 8192u));
-    }
-    uint32_t split_docs = ((doc_range + n_splits - 1) / n_splits + 31u) & ~31u;
-    if (split_docs == 0) split_docs = 32;
-    n_splits = std::max(1u, (doc_range + split_docs - 1) / split_docs);
-    e->n_splits = n_splits;
-    e->split_docs = split_docs;
-
-    // ---- work order: decreasing cost so the long queries start first
-    const uint32_t n_items = b->n_queries * n_splits;
-    std::vector<uint32_t> order(n_items);
-    {
-        std::vector<uint32_t> qorder(b->n_queries);
-        std::iota(qorder.begin(), qorder.end(), 0u);
-        std::stable_sort(qorder.begin(), qorder.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
-        if (e->kernel == 3) {
-            for (uint32_t i = 0; i < b->n_queries; ++i)
-                for (uint32_t sp = 0; sp < n_splits; ++sp) order[i * n_splits + sp] = qorder[i] * n_splits + sp;
-        } else {
-            order = qorder;
+    std::vector<WorkItem> witems;
+    std::vector<uint32_t> part_off(b->n_queries + 1, 0);
+    std::vector<uint64_t> item_cost;
+    bool split_any = false;
+    if (e->kernel == 3) {
+        uint64_t total_cost = 0;
+        for (uint32_t q = 0; q < b->n_queries; ++q) total_cost += cost[q];
+        const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) * e->plan_ctas * e->plan_wpc;
+        const uint64_t target = std::max<uint64_t>(64, total_cost / (n_warps * 4) + 1);   // posting blocks per item
+        const uint32_t cap_parts = e->max_parts ? static_cast<uint32_t>(e->max_parts) : 64u;
+        witems.reserve(b->n_queries);
+        for (uint32_t q = 0; q < b->n_queries; ++q) {
+            uint32_t parts = e->force_splits ? static_cast<uint32_t>(e->force_splits)
+                                             : static_cast<uint32_t>(std::min<uint64_t>(cap_parts, (cost[q] + target - 1) / target));
+            parts = std::max(1u, std::min(parts, std::max(1u, doc_range / 1024u)));
+            const uint32_t step = ((doc_range + parts - 1) / parts + 31u) & ~31u;
+            part_off[q] = static_cast<uint32_t>(witems.size());
+            for (uint32_t lo = 0; lo < doc_range || lo == 0; lo += step) {
+                const uint32_t hi = std::min(doc_range, lo + step);
+                witems.push_back(WorkItem{q, e->ix.doc_lo + lo, e->ix.doc_lo + hi, 0u});
+                item_cost.push_back(cost[q] / parts);
+                if (hi >= doc_range) break;
+            }
+            if (witems.size() - part_off[q] > 1) split_any = true;
         }
+        part_off[b->n_queries] = static_cast<uint32_t>(witems.size());
     }
+    e->n_witems = static_cast<uint32_t>(witems.size());
+    e->split_any = split_any;
+    e->n_splits = b->n_queries ? static_cast<uint32_t>((witems.size() + b->n_queries - 1) / b->n_queries) : 1;
+
+    // ---- work order: decreasing cost so the long items start first
+    const uint32_t n_items = e->kernel == 3 ? e->n_witems : b->n_queries;
+    std::vector<uint32_t> order(n_items);
+    std::iota(order.begin(), order.end(), 0u);
+    if (e->kernel == 3)
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return item_cost[a] > item_cost[c]; });
+    else
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
 
     CU(e->d_queries.ensure(b->n_queries));
     CU(e->d_terms.ensure(b->n_terms));
@@ -500,11 +504,13 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     CU(e->d_dterms.ensure(dterms.size()));
     CU(e->d_items.ensure(items.size()));
     CU(e->d_qruns.ensure(b->n_terms));
-    if (n_splits > 1) {
+    if (split_any) {
         CU(e->d_part_keys.ensure(static_cast<size_t>(n_items) * k));
         CU(e->d_part_counts.ensure(n_items));
         CU(e->d_part_hits.ensure(n_items));
+        CU(e->d_part_off.ensure(part_off.size()));
     }
+    CU(e->d_witems.ensure(witems.size()));
     if (e->kernel == 3) {
         const size_t want = static_cast<size_t>(run_entries) + 16384;  // tail slack for ring look-ahead loads
         if (want > e->d_run_docs.cap) {
@@ -524,6 +530,10 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         }
         if (b->n_filters) CU(cudaMemcpyAsync(e->d_filters.p, b->filters, sizeof(dgpu_qfilter) * b->n_filters, cudaMemcpyHostToDevice, e->stream));
         CU(cudaMemcpyAsync(e->d_order.p, order.data(), 4 * order.size(), cudaMemcpyHostToDevice, e->stream));
+        if (!witems.empty())
+            CU(cudaMemcpyAsync(e->d_witems.p, witems.data(), sizeof(WorkItem) * witems.size(), cudaMemcpyHostToDevice, e->stream));
+        if (split_any)
+            CU(cudaMemcpyAsync(e->d_part_off.p, part_off.data(), 4 * part_off.size(), cudaMemcpyHostToDevice, e->stream));
         if (!dterms.empty()) {
             CU(cudaMemcpyAsync(e->d_dterms.p, dterms.data(), sizeof(DTerm) * dterms.size(), cudaMemcpyHostToDevice, e->stream));
             CU(cudaMemcpyAsync(e->d_items.p, items.data(), sizeof(DItem) * items.size(), cudaMemcpyHostToDevice, e->stream));
@@ -577,26 +587,15 @@ static int launch_fused(dgpu_engine* e, cudaStream_t stream) {
     return 0;
 }
 
-template <int WARPS>
-static int launch_accumulate(dgpu_engine* e, const AccumParams& P, size_t smem, int grid, cudaStream_t stream) {
-    auto kern = e->need_cnt ? accumulate_topk_kernel<WARPS, true> : accumulate_topk_kernel<WARPS, false>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, WARPS * 32, smem, stream>>>(e->ix, P);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// kernel = 3: decode + score every distinct term of the batch once, then accumulate + top-k per query
+// kernel = 3: decode + score every distinct term of the batch once, then accumulate + top-k, one warp per item
 static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     AccumParams P{};
     P.queries = e->d_queries.p;
     P.terms = e->d_qruns.p;
     P.filters = e->d_filters.p;
+    P.items = e->d_witems.p;
     P.order = e->d_order.p;
-    P.n_queries = e->n_queries;
-    P.n_splits = e->n_splits;
-    P.split_docs = e->split_docs;
-    P.n_items = e->n_queries * e->n_splits;
+    P.n_items = e->n_witems;
     P.work_counter = e->d_counter.p;
     P.run_docs = e->d_run_docs.p;
     P.run_scores = e->d_run_scores.p;
@@ -604,11 +603,11 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.max_terms = (e->max_terms + 3u) & ~3u;
     P.cand_cap = e->plan_cap;
     P.list_cap = e->plan_list;
-    P.ring_entries = e->plan_ring;
+    P.chlog = e->plan_chlog;
     P.W = e->plan_W;
-    const size_t per_sm = 228 * 1024;
-    const size_t smem = e->plan_smem;
-    const bool split = e->n_splits > 1;
+    P.warp_smem = e->plan_warp_smem;
+    const size_t smem = static_cast<size_t>(e->plan_warp_smem) * e->plan_wpc;
+    const bool split = e->split_any;
     P.out_keys = split ? e->d_part_keys.p : e->d_keys.p;
     P.out_counts = split ? e->d_part_counts.p : e->d_counts.p;
     P.out_hits = split ? e->d_part_hits.p : e->d_hits.p;
@@ -623,19 +622,19 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(e->ev_a, stream));
-    const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(per_sm / (smem + 1024), 32)));
-    const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * ctas, P.n_items));
-    if (e->warps == 8) {
-        if (launch_accumulate<8>(e, P, smem, grid, stream)) return -1;
-    } else {
-        if (launch_accumulate<4>(e, P, smem, grid, stream)) return -1;
-    }
+    auto kern = e->need_cnt ? accumulate_topk_kernel<true> : accumulate_topk_kernel<false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const uint64_t want_ctas = (static_cast<uint64_t>(P.n_items) + e->plan_wpc - 1) / e->plan_wpc;
+    const int grid = static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * e->plan_ctas, want_ctas)));
+    kern<<<grid, e->plan_wpc * 32, smem, stream>>>(e->ix, P);
+    CU(cudaGetLastError());
     e->launches++;
     CU(cudaEventRecord(e->ev_b, stream));
     if (split) {
-        merge_parts_kernel<<<e->n_queries, 128, 0, stream>>>(e->d_part_keys.p, e->d_part_counts.p, e->d_part_hits.p,
-                                                             static_cast<int>(e->n_splits), e->n_queries, e->k, e->d_keys.p,
-                                                             e->d_counts.p, e->d_hits.p);
+        merge_items_kernel<<<e->n_queries, 128, 0, stream>>>(e->d_part_keys.p, e->d_part_counts.p, e->d_part_hits.p,
+                                                             e->d_part_off.p, e->n_queries, e->k, e->d_keys.p, e->d_counts.p,
+                                                             e->d_hits.p);
         e->launches++;
         CU(cudaGetLastError());
     }

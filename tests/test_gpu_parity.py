@@ -68,18 +68,20 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
             assert np.isnan(td.maxScore)
 
 
-# (window_docs, ring_entries, splits, warps): small windows walk many windows per query, a small ring area pushes the
-# terms through the global-memory continuation and ring-restart paths, splits exercises the doc-range split + merge
-_TUNINGS = [(0, 2048, 0, 4), (1024, 2048, 1, 4), (256, 64, 1, 4), (4096, 256, 3, 8), (64, 4096, 7, 8), (2048, 512, 16, 4)]
+# (window_docs, stage_log2, splits, warps per CTA, warps per SM): small windows walk many windows per query, stage_log2 = 1
+# pushes almost every term through the global-memory continuation, splits exercises doc-range parts + the device merge
+_TUNINGS = [(0, 0, 0, 4, 16), (1024, 0, 1, 4, 16), (256, 1, 1, 8, 32), (4096, 2, 3, 2, 8), (64, 3, 7, 1, 4), (2048, 0, 16, 4, 12)]
 
 
 @pytest.mark.parametrize("name", ["g1", "g2"])
-@pytest.mark.parametrize("window_docs,ring_entries,splits,warps", _TUNINGS)
-def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, name, window_docs, ring_entries, splits, warps):
-    """dgpu_search_batch_text: the whole query file in one launch; window size, ring area, doc-range splits and
-    CTA width must not change any result."""
+@pytest.mark.parametrize("window_docs,stage_log2,splits,warps,warps_per_sm", _TUNINGS)
+def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, name, window_docs, stage_log2, splits, warps,
+                                                        warps_per_sm):
+    """dgpu_search_batch_text: the whole query file in one launch; window size, staging depth, doc-range parts and
+    the warp layout must not change any result."""
     r = readers[name]
-    for opt, v in (("window_docs", window_docs), ("ring_entries", ring_entries), ("splits", splits), ("warps", warps)):
+    for opt, v in (("window_docs", window_docs), ("stage_log2", stage_log2), ("splits", splits), ("warps", warps),
+                   ("warps_per_sm", warps_per_sm)):
         r.set_option(opt, v)
     try:
         searcher = dg.IndexSearcher(r)
@@ -92,7 +94,7 @@ def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, nam
                 got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
                 assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
     finally:
-        for opt, v in (("window_docs", 0), ("ring_entries", 2048), ("splits", 0), ("warps", 4)):
+        for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4), ("warps_per_sm", 16)):
             r.set_option(opt, v)
 
 

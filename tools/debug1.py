@@ -10,11 +10,11 @@ with gzip.open(os.path.join(root, "tests/golden/g1.dmp.gz"), "rb") as f, open(ra
 r = dg.IndexReader.from_dump(raw, 0)
 s = dg.IndexSearcher(r)
 q = api.parse_line(sys.argv[1] if len(sys.argv) > 1 else "TERM body t0000001")
-for ring, win, warps in ((2048, 0, 4), (64, 0, 4), (2048, 512, 4), (64, 512, 4), (4096, 0, 8), (2048, 64, 4)):
-    r.set_option("ring_entries", ring); r.set_option("window_docs", win); r.set_option("warps", warps)
+for wps, win, warps in ((16, 0, 4), (8, 0, 2), (16, 512, 4), (32, 512, 8), (16, 64, 4)):
+    r.set_option("warps_per_sm", wps); r.set_option("window_docs", win); r.set_option("warps", warps)
     td = s.search(q, 10)
     docs = [x.doc for x in td.scoreDocs]
-    print("ring", ring, "win", win, "warps", warps, "hits", td.totalHits.value, docs, flush=True)
+    print("wps", wps, "win", win, "warps", warps, "hits", td.totalHits.value, docs, flush=True)
 r.set_option("kernel", 2)
 td = s.search(q, 10)
 print("fused", td.totalHits.value, [x.doc for x in td.scoreDocs])
