@@ -1,0 +1,107 @@
+"""The N > 1 path on CPU: two `gloo` ranks, segments sharded 4 + 4.
+
+What runs on the host in a sharded search is (1) the statistics exchange that makes idf / avgdl identical on every
+rank (TermQuery.cpp:184-260 uses global numbers), and (2) the protocol around the single exchange step: local top-k
+lists as 64-bit keys, one all_gather, a k-way merge, totalHits = sum of the local counts. Both are exercised here
+with host-only readers (no engine: nothing is scored by the product on CPU — the local lists come from the oracle,
+which is the checker). The CUDA merge kernel itself is covered by tests/test_gpu_parity.py.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K = 10
+N_QUERIES = 40
+
+
+def _keys(docs_scores):
+    """TopDocs -> descending 64-bit keys, the engine's result encoding (include/dgpu_engine.h: dgpu_results)."""
+    out = np.zeros(K, dtype=np.uint64)
+    for i, (d, s) in enumerate(docs_scores[:K]):
+        b = int(np.float32(s).view(np.uint32))
+        o = (~b & 0xFFFFFFFF) if b & 0x80000000 else (b | 0x80000000)
+        out[i] = (o << 32) | (0xFFFFFFFF - d)
+    return out
+
+
+def _merge(all_keys, all_counts):
+    """numpy mirror of merge_parts_kernel: best K of the union, keys are unique."""
+    cat = np.concatenate([all_keys[p][: all_counts[p]] for p in range(len(all_keys))])
+    return np.sort(cat)[::-1][:K]
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    import diagon_b200 as dg
+    from diagon_b200 import api
+    from oracle import oracle as orc
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        import torch
+
+        spec = dg.named_corpus("C2", 0.002)
+        nseg = spec.num_segments
+        lo, hi = nseg * rank // world, nseg * (rank + 1) // world
+        local = dg.IndexReader.synthetic(spec, -1, lo, hi)   # host-only: dictionary + statistics, no engine
+        whole = dg.IndexReader.synthetic(spec, -1)
+
+        # (1) statistics exchange
+        df = torch.from_numpy(local.get_doc_freqs().copy())
+        dist.all_reduce(df)
+        ttf, md = local.get_field_totals("body")
+        tot = torch.tensor([ttf, md], dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert np.array_equal(df.numpy(), whole.get_doc_freqs()), "global docFreq differs from the unsharded index"
+        assert (int(tot[0]), int(tot[1])) == whole.get_field_totals("body")
+        local.set_doc_freqs(df.numpy())
+        local.set_field_totals("body", int(tot[0]), int(tot[1]))
+        assert np.array_equal(local.get_doc_freqs(), whole.get_doc_freqs())
+
+        # (2) gather + merge of local top-k lists. Local list of a shard = the best K among the hits whose doc lies in
+        # the shard's segments, scored with GLOBAL statistics: exactly what a rank's engine returns.
+        path = os.path.join(tmp, "c2s.dmp")
+        if rank == 0:
+            dg.write_synthetic_dump(spec, path)
+        dist.barrier()
+        dump = dg.read_dump(path)
+        ox = orc.OracleIndex(dump)
+        doc_lo = dump.segments[lo].doc_base
+        doc_hi = dump.segments[hi - 1].doc_base + dump.segments[hi - 1].max_doc
+        lines = dg.query_log_text("C2", spec.vocab, N_QUERIES, "OR body 0").decode().strip().split("\n")
+        for line in lines:
+            q = api.parse_line(line)
+            hits_all, everything, _ = ox.search(q, dump.max_doc)          # every hit, best first
+            mine = [(d, s) for d, s in everything if doc_lo <= d < doc_hi]
+            keys = torch.from_numpy(_keys(mine).view(np.int64).copy())
+            meta = torch.tensor([min(len(mine), K), len(mine)], dtype=torch.int64)
+            g_keys = [torch.zeros(K, dtype=torch.int64) for _ in range(world)]
+            g_meta = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(g_keys, keys)
+            dist.all_gather(g_meta, meta)
+            merged = _merge([k.numpy().view(np.uint64) for k in g_keys], [int(m[0]) for m in g_meta])
+            want_hits, want, _ = ox.search(q, K)
+            assert sum(int(m[1]) for m in g_meta) == want_hits == hits_all, line
+            assert np.array_equal(merged, _keys(want)[: len(want)]), line
+        local.close()
+        whole.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_statistics_exchange_and_topk_merge(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
