@@ -372,8 +372,17 @@ def main():
     if dist is not None:
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     achieved = stats["algorithmic_bytes"] / (float(kt[0]) / 1e3) / 1e9  # this rank's bytes / its kernel time
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu launch list (same workload only)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj["workload"] == args.workload and args.scale == 1.0 and not args.queries and world == 1 and batched \
+                and tj["kernel"] == "accumulate_topk_kernel":
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": "accumulate_topk_kernel" if batched else "search_kernel",
                 "kernel_ms": float(kt[0]), "algorithmic_bytes_per_launch": stats["algorithmic_bytes"],
                 "postings_per_launch": stats["postings"],
