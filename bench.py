@@ -200,7 +200,7 @@ def main():
             return 0
         base = reference_arm(args, corpus_name, log_name, kind, k, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "bm25_topk_queries_per_sec", "unit": "queries/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {corpus_name} corpus scale {args.scale}, {kind.split()[0]}-{log_name} top-{k}"}}
         if base is None:
@@ -403,7 +403,7 @@ def main():
         d2h = nq * k * 8 + nq * 4 + nq * 8
         line = {
             "metric": "bm25_topk_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {batch} x {kind.split()[0]}-{spec.vocab and log_name} top-{k} on the {corpus_name} "
                                    f"synthetic corpus ({spec.num_docs} docs, vocab {spec.vocab}, {nseg} segments, scale {args.scale})",

@@ -278,7 +278,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
 
         uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
         uint64_t thresh = 0;        // key of the k-th best so far (0 until the pool has been pruned once with >= k)
-        uint32_t hits = 0;          // per lane
+        uint32_t hits = 0;          // docs collected so far (warp-uniform)
 
         auto prune = [&]() {   // keep the best k of the pool, raise the threshold
             const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
@@ -360,43 +360,47 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
             cp_async_commit();
             __syncwarp();
 
-            // ---- harvest
-            const bool dense_scan = n_list > P.list_cap;
-            const uint32_t total = dense_scan ? (we - ws) : n_list;
-            for (uint32_t base = 0; base < total; base += 32) {
-                if (n_cand + 32u > P.cand_cap) prune();
-                const uint32_t i = base + lane;
-                bool push = false;
-                uint64_t key = 0;
-                if (i < total) {
-                    const uint32_t r = dense_scan ? i : tlist[i];
-                    const uint32_t bits = acc_bits[r];
-                    const uint8_t c = NEED_CNT ? cnt[r] : 0;
-                    if (!(dense_scan && bits == kSentinel && c == 0)) {
-                        bool match = bits != kSentinel;  // touched only by an excluded term otherwise
-                        if (NEED_CNT && match) match = (c != 255) && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
-                        const uint32_t doc = ws + r;
-                        float score = __uint_as_float(bits);
+            // ---- harvest: every touched doc once; the accumulator goes back to the sentinel as it is read
+            {
+                const bool dense_scan = n_list > P.list_cap;
+                const uint32_t total = dense_scan ? (we - ws) : n_list;
+                for (uint32_t base = 0; base < total; base += 32) {
+                    if (n_cand + 32u > P.cand_cap) prune();
+                    const uint32_t i = base + lane;
+                    uint32_t rr = 0, bits = kSentinel;
+                    uint8_t c = 0;
+                    if (i < total) {
+                        rr = dense_scan ? i : tlist[i];
+                        bits = acc_bits[rr];
+                        acc_bits[rr] = kSentinel;
+                        if (NEED_CNT) {
+                            c = cnt[rr];
+                            cnt[rr] = 0;
+                        }
+                    }
+                    bool match = bits != kSentinel;  // untouched, or touched only by an excluded term
+                    if (NEED_CNT && match) match = (c != 255) && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
+                    const uint32_t doc = ws + rr;
+                    float score = __uint_as_float(bits);
+                    if (nf) {
                         for (uint32_t f = 0; f < nf && match; ++f) {
                             const int64_t val = ix.dv[qf[f].column][doc - ix.doc_lo];
                             match = (val >= qf[f].lo) && (val <= qf[f].hi);
                             score = __fadd_rn(score, 1.0f);  // constant score of the range clause (NumericRangeQuery.cpp:117-120)
                         }
-                        if (match) {
-                            const uint32_t sb = __float_as_uint(score);
-                            const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
-                            // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:171-174)
-                            key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
-                            push = key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
-                            ++hits;  // TopScoreDocCollector.cpp:165-168
-                        }
-                        acc_bits[r] = kSentinel;
-                        if (NEED_CNT) cnt[r] = 0;
+                    }
+                    const uint32_t sb = __float_as_uint(score);
+                    const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+                    const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
+                    // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
+                    const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+                    hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
+                    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
+                    if (pm) {
+                        if (push) cand[n_cand + __popc(pm & lt_mask)] = key;
+                        n_cand += __popc(pm);
                     }
                 }
-                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
-                if (push) cand[n_cand + __popc(pm & lt_mask)] = key;
-                n_cand += __popc(pm);
             }
             cp_async_wait_all();
             __syncwarp();
@@ -404,8 +408,6 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
 
         // ---- final select
         __syncwarp();
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xFFFFFFFFu, hits, o);
         const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
         for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;
         warp_bitonic_sort_desc(cand, nsort, lane);

@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -706,9 +708,18 @@ int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[6]) {
 }
 
 int dgpu_engine_search(dgpu_engine* e, const dgpu_query_batch* batch, int32_t k, dgpu_results* host_out) {
+    static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     if (dgpu_engine_stage_batch(e, batch, k)) return -1;
+    const auto t1 = std::chrono::steady_clock::now();
     if (dgpu_engine_search_staged(e, nullptr)) return -1;
-    return dgpu_engine_fetch_results(e, host_out);
+    const int rc = dgpu_engine_fetch_results(e, host_out);
+    if (trace) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[dgpu trace] stage %.3f ms, kernels + fetch %.3f ms (device %.3f ms)\n", ms(t0, t1),
+                     ms(t1, std::chrono::steady_clock::now()), e->last_ms);
+    }
+    return rc;
 }
 
 int dgpu_engine_merge_parts(dgpu_engine* e, const uint64_t* part_keys, const int32_t* part_counts,

@@ -6,6 +6,9 @@
 
 #include <bit>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <sstream>
@@ -106,8 +109,11 @@ void compile_all(IndexSearcher& s, const std::vector<const Query*>& qs, Compiled
 int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, int32_t* out_docs, float* out_scores,
               int32_t* out_counts, int64_t* out_total_hits) {
     if (k <= 0) throw std::invalid_argument("numHits must be > 0");
+    static const bool trace = std::getenv("DGPU_TRACE") != nullptr;   // host-phase timings on stderr
+    auto t0 = std::chrono::steady_clock::now();
     CompiledBatch batch;
     compile_all(s, qs, batch);
+    auto t1 = std::chrono::steady_clock::now();
     size_t n = qs.size();
     std::vector<uint64_t> keys(n * static_cast<size_t>(k));
     std::vector<int32_t> counts(n);
@@ -116,8 +122,14 @@ int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, 
     if (n && !s.getIndexReader().engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
     if (n && dgpu_engine_search(s.getIndexReader().engine(), &view, k, &res) != 0)
         throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
+    auto t2 = std::chrono::steady_clock::now();
     unpack(keys, counts, static_cast<int32_t>(n), k, out_docs, out_scores);
     std::memcpy(out_counts, counts.data(), n * sizeof(int32_t));
+    if (trace) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[dgpu trace] compile %.3f ms, engine search %.3f ms, unpack %.3f ms\n", ms(t0, t1), ms(t1, t2),
+                     ms(t2, std::chrono::steady_clock::now()));
+    }
     return static_cast<int>(n);
 }
 
@@ -475,7 +487,11 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
                            float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
     if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
     try {
+        auto tp = std::chrono::steady_clock::now();
         auto parsed = parse_batch(text, text_len);
+        if (std::getenv("DGPU_TRACE"))
+            std::fprintf(stderr, "[dgpu trace] parse %.3f ms\n",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count());
         if (static_cast<int64_t>(parsed.size()) > max_queries) { set_error("more queries than max_queries"); return -1; }
         std::vector<const Query*> qs;
         qs.reserve(parsed.size());
