@@ -42,13 +42,13 @@ struct QTermRun {       // one query term, resolved to its run in the scratch
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K3a: StreamVByte block decode fused with BM25 scoring, one warp per 128-posting block.
-// Reads the compressed block (128-bit aligned payload, 2.2-3.5 B/posting), writes 4 postings per lane as one
-// 128-bit store of doc ids and one of scores. kPadBlocks blocks after the last one of a term are filled with
-// kDocEnd so that readers never need an end-of-run check.
+// Reads the compressed block (128-bit aligned payload, 2.2-3.5 B/posting), writes 4 postings per lane as two
+// 128-bit stores of (doc, score) entries. kPadBlocks blocks after the last one of a term are filled with kDocEnd so
+// that readers never need an end-of-run check.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kDecodeThreads)
 decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DItem* __restrict__ items, uint32_t n_items,
-                    uint32_t* __restrict__ run_docs, float* __restrict__ run_scores) {
+                    uint2* __restrict__ runs) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const DItem it = items[item];
@@ -60,24 +60,22 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
         for (uint32_t rel = it.first_rel + warp; rel < rel_end; rel += kDecodeThreads / 32) {
             uint32_t doc[4], code[4];
             const uint32_t n = warp_decode_block(ix, tb + rel, lane, doc, code);
-            uint4 dv;
-            float4 sv;
-            uint32_t* dp = &dv.x;
-            float* sp = &sv.x;
+            uint32_t ev[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const bool valid = 4u * lane + j < n;
-                dp[j] = valid ? doc[j] : kDocEnd;
-                sp[j] = valid ? bm25_score(dt.idf, ktab, code[j]) : 0.0f;
+                ev[2 * j] = valid ? doc[j] : kDocEnd;
+                ev[2 * j + 1] = valid ? __float_as_uint(bm25_score(dt.idf, ktab, code[j])) : 0u;
             }
-            const size_t o = static_cast<size_t>(dt.out_base) + static_cast<size_t>(rel) * DGPU_BLOCK_POSTINGS + 4u * lane;
-            *reinterpret_cast<uint4*>(run_docs + o) = dv;
-            *reinterpret_cast<float4*>(run_scores + o) = sv;
+            uint4* o = reinterpret_cast<uint4*>(runs + static_cast<size_t>(dt.out_base) +
+                                                static_cast<size_t>(rel) * DGPU_BLOCK_POSTINGS + 4u * lane);
+            o[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
+            o[1] = make_uint4(ev[4], ev[5], ev[6], ev[7]);
             if (rel + 1 == nb) {
 #pragma unroll
                 for (int pb = 1; pb <= kPadBlocks; ++pb) {
-                    *reinterpret_cast<uint4*>(run_docs + o + pb * DGPU_BLOCK_POSTINGS) = make_uint4(kDocEnd, kDocEnd, kDocEnd, kDocEnd);
-                    *reinterpret_cast<float4*>(run_scores + o + pb * DGPU_BLOCK_POSTINGS) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    o[pb * (DGPU_BLOCK_POSTINGS / 2)] = make_uint4(kDocEnd, 0u, kDocEnd, 0u);
+                    o[pb * (DGPU_BLOCK_POSTINGS / 2) + 1] = make_uint4(kDocEnd, 0u, kDocEnd, 0u);
                 }
             }
         }
@@ -101,8 +99,7 @@ struct AccumParams {
     const uint32_t* order;      // item ids by decreasing cost
     uint32_t n_items;
     uint32_t* work_counter;
-    const uint32_t* run_docs;
-    const float* run_scores;
+    const uint2* runs;          // (doc, score bits) entries of every distinct term of the batch
     int k;
     uint32_t W;                 // docs per window (multiple of 32, <= 65536)
     uint32_t chlog;             // log2 of the staged entries per term (1..5)
@@ -120,17 +117,16 @@ __host__ __device__ inline size_t accum_warp_smem_bytes(uint32_t W, uint32_t cap
     size_t b = 0;
     b += sizeof(uint64_t) * cap;                          // candidate pool
     b += sizeof(float) * W;                               // window accumulators
-    b += 2 * sizeof(uint32_t) * (static_cast<size_t>(max_terms) << chlog);  // staged docs + scores
-    b += sizeof(uint32_t) * max_terms;                    // cursors
+    b += sizeof(uint2) * (static_cast<size_t>(max_terms) << chlog);  // staged entries
+    b += 2 * sizeof(uint32_t) * max_terms;                // cursors, row anchors
     b += sizeof(uint16_t) * list_cap;                     // touched list
     b += need_cnt ? max_terms : 0;                        // roles
     b += need_cnt ? W : 0;                                // match counts
     return (b + 15) & ~static_cast<size_t>(15);
 }
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
@@ -159,13 +155,15 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* keys, uint32_t 
 // window accumulators, touched list and candidate pool in its slice of shared memory. Warps never wait for each
 // other: no CTA barrier, no shared-memory atomics; the latency of one warp's loads is covered by the others.
 //   * every query term is a run of (doc, score) entries sorted by doc (decode_score_kernel). The warp keeps a cursor
-//     per term and the next CH = 2^chlog entries of every term staged in shared memory (cp.async; a term is restaged
-//     right after it has been applied, so the copy overlaps the rest of the window and the harvest);
+//     per term and a ROW of CH = 2^chlog entries of every term staged in shared memory, anchored at `anc`. A row is
+//     restaged (one 8-byte cp.async per lane) only when at least half of it has been consumed, so a sparse term is
+//     copied once per ~CH/2 postings, not once per window; the copy overlaps the rest of the window and the harvest;
 //   * a window starts at the smallest next doc of any term and covers W docs; empty doc ranges are never visited;
 //   * terms are applied in clause order (BooleanQuery.cpp:119-126, :232-241): one scatter-add pass over the staged
-//     entries that fall into the window and, when all of them do, over the following 32-entry chunks of the run
-//     straight from global memory (coalesced, next chunk prefetched) until a chunk crosses the window end. One warp
-//     applying one term at a time gives every accumulator its clauses in order: bit-exact float sums;
+//     entries that fall into the window and, when the row runs out inside the window, over the following 32-entry
+//     chunks of the run straight from global memory (coalesced 8-byte loads, next chunk prefetched) until a chunk
+//     crosses the window end. One warp applying one term at a time gives every accumulator its clauses in order:
+//     bit-exact float sums;
 //   * every first touch of an accumulator appends the doc to the touched list, so the harvest costs O(postings),
 //     never O(W); a window with more touched docs than the list holds is harvested by a dense scan;
 //   * the harvest evaluates required-match counts and doc-value filters, counts hits and pushes candidates above the
@@ -179,30 +177,32 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
     const uint32_t chlog = P.chlog, CH = 1u << chlog;
     uint64_t* cand;
     float* acc;
-    uint32_t *sdoc, *pos;
-    float* ssc;
+    uint2* srow;
+    uint32_t *pos, *anc;
     uint16_t* tlist;
     uint8_t *role, *cnt;
     {
         uint8_t* sp = smem_raw + static_cast<size_t>(warp) * P.warp_smem;
         cand = reinterpret_cast<uint64_t*>(sp);  sp += sizeof(uint64_t) * P.cand_cap;
+        srow = reinterpret_cast<uint2*>(sp);     sp += sizeof(uint2) * (static_cast<size_t>(P.max_terms) << chlog);
         acc = reinterpret_cast<float*>(sp);      sp += sizeof(float) * W;
-        sdoc = reinterpret_cast<uint32_t*>(sp);  sp += sizeof(uint32_t) * (static_cast<size_t>(P.max_terms) << chlog);
-        ssc = reinterpret_cast<float*>(sp);      sp += sizeof(float) * (static_cast<size_t>(P.max_terms) << chlog);
         pos = reinterpret_cast<uint32_t*>(sp);   sp += sizeof(uint32_t) * P.max_terms;
+        anc = reinterpret_cast<uint32_t*>(sp);   sp += sizeof(uint32_t) * P.max_terms;
         tlist = reinterpret_cast<uint16_t*>(sp); sp += sizeof(uint16_t) * P.list_cap;
         role = sp;                               sp += NEED_CNT ? P.max_terms : 0;
         cnt = sp;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* acc_bits = reinterpret_cast<uint32_t*>(acc);
+    const uint32_t* sdoc = reinterpret_cast<const uint32_t*>(srow);   // doc of staged entry i is sdoc[2 * i]
+    const uint32_t srow_s = static_cast<uint32_t>(__cvta_generic_to_shared(srow));
 
     for (uint32_t i = lane; i < W; i += 32) {
         acc_bits[i] = kSentinel;
         if (NEED_CNT) cnt[i] = 0;
     }
 
-    // staged entry e of term t: rows are rotated by t so that "entry 0 of every term" is a conflict-free access
+    // staged entry e of term t: rows are rotated by t so that "the same column of every row" spreads over the banks
     auto sidx = [&](uint32_t t, uint32_t e) -> uint32_t { return (t << chlog) + ((e + t) & (CH - 1u)); };
 
     uint32_t n_list = 0;   // touched docs of the current window (warp-uniform)
@@ -234,6 +234,11 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
         n_list += __popc(fm);
     };
 
+    // copy entries [p, p + CH) of a run into term t's row
+    auto stage_row = [&](uint32_t t, uint32_t p) {
+        if (static_cast<uint32_t>(lane) < CH) cp_async8(srow_s + 8u * sidx(t, lane), P.runs + p + lane);
+    };
+
     for (;;) {
         uint32_t slot = 0;
         if (lane == 0) slot = atomicAdd(P.work_counter, 1u);
@@ -257,21 +262,16 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                 uint32_t a = 0, b = r.len;
                 while (a < b) {
                     const uint32_t mid = (a + b) >> 1;
-                    if (__ldg(P.run_docs + r.base + mid) < lo) a = mid + 1; else b = mid;
+                    if (__ldg(&P.runs[r.base + mid].x) < lo) a = mid + 1; else b = mid;
                 }
                 p = r.base + a;
             }
             pos[t] = p;
+            anc[t] = p;
             if (NEED_CNT) role[t] = static_cast<uint8_t>(r.meta);
         }
         __syncwarp();
-        for (uint32_t t = 0; t < nt; ++t) {
-            const uint32_t p = pos[t];
-            if (static_cast<uint32_t>(lane) < CH) {
-                cp_async4(sdoc + sidx(t, lane), P.run_docs + p + lane);
-                cp_async4(ssc + sidx(t, lane), P.run_scores + p + lane);
-            }
-        }
+        for (uint32_t t = 0; t < nt; ++t) stage_row(t, pos[t]);
         cp_async_commit();
         cp_async_wait_all();
         __syncwarp();
@@ -291,9 +291,9 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
         };
 
         for (;;) {
-            // ---- window start: the smallest next doc of any term
+            // ---- window start: the smallest next doc of any term (its row entry at the consumed offset)
             uint32_t m = kDocEnd;
-            for (uint32_t t = lane; t < nt; t += 32) m = min(m, sdoc[sidx(t, 0)]);
+            for (uint32_t t = lane; t < nt; t += 32) m = min(m, sdoc[2u * sidx(t, pos[t] - anc[t])]);
             m = __reduce_min_sync(0xFFFFFFFFu, m);
             if (m >= hi) break;
             const uint32_t ws = m;
@@ -303,57 +303,56 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
             // ---- terms in clause order
             for (uint32_t g = 0; g < n_groups; ++g) {
                 const uint32_t t = (g << 5) + lane;
-                uint32_t d_first = kDocEnd, d_last = kDocEnd;
+                uint32_t d_first = kDocEnd, d_last = kDocEnd, off_t = 0, anc_t = 0;
                 if (t < nt) {
-                    d_first = sdoc[sidx(t, 0)];
-                    d_last = sdoc[sidx(t, CH - 1u)];
+                    anc_t = anc[t];
+                    off_t = pos[t] - anc_t;                      // consumed part of the row, < CH
+                    d_first = sdoc[2u * sidx(t, off_t)];
+                    d_last = sdoc[2u * sidx(t, CH - 1u)];
                 }
                 uint32_t rem = __ballot_sync(0xFFFFFFFFu, d_first < we);
-                const uint32_t dense = __ballot_sync(0xFFFFFFFFu, d_last < we);
+                const uint32_t dense = __ballot_sync(0xFFFFFFFFu, d_last < we);   // the row runs out inside the window
                 while (rem) {
                     const int b = __ffs(rem) - 1;
                     rem &= rem - 1;
                     const uint32_t tt = (g << 5) + b;
                     const uint32_t rl = NEED_CNT ? role[tt] : 0u;
-                    uint32_t d = kDocEnd;
-                    float s = 0.f;
-                    if (static_cast<uint32_t>(lane) < CH) {
-                        d = sdoc[sidx(tt, lane)];
-                        s = ssc[sidx(tt, lane)];
-                    }
-                    uint32_t p = pos[tt];
+                    const uint32_t off = __shfl_sync(0xFFFFFFFFu, off_t, b);
+                    const uint32_t a0 = __shfl_sync(0xFFFFFFFFu, anc_t, b);
+                    uint32_t n_in;
                     {
-                        const bool in = d < we;
+                        const uint32_t e = off + lane;
+                        uint2 en = make_uint2(kDocEnd, 0u);
+                        if (e < CH) en = srow[sidx(tt, e)];
+                        const bool in = en.x < we;
                         const uint32_t im = __ballot_sync(0xFFFFFFFFu, in);
-                        apply(in, d - ws, s, rl);
-                        p += __popc(im);
+                        apply(in, en.x - ws, __uint_as_float(en.y), rl);
+                        n_in = __popc(im);
                     }
-                    if ((dense >> b) & 1u) {
+                    uint32_t p = a0 + off + n_in;
+                    const bool is_dense = (dense >> b) & 1u;
+                    if (is_dense) {
                         // every staged entry was inside the window: go on with the run in global memory
-                        d = __ldg(P.run_docs + p + lane);
-                        s = __ldg(P.run_scores + p + lane);
+                        const uint2* gp = P.runs + p + lane;
+                        uint2 en = __ldg(gp);
                         for (;;) {
-                            const bool in = d < we;
+                            const bool in = en.x < we;
                             const uint32_t im = __ballot_sync(0xFFFFFFFFu, in);
-                            uint32_t d_next = 0;
-                            float s_next = 0.f;
-                            if (im == 0xFFFFFFFFu) {   // the run continues inside the window: prefetch the next chunk
-                                d_next = __ldg(P.run_docs + p + 32u + lane);
-                                s_next = __ldg(P.run_scores + p + 32u + lane);
-                            }
-                            apply(in, d - ws, s, rl);
+                            uint2 nx = make_uint2(0u, 0u);
+                            if (im == 0xFFFFFFFFu) nx = __ldg(gp + 32);   // the run continues inside the window: prefetch
+                            apply(in, en.x - ws, __uint_as_float(en.y), rl);
                             p += __popc(im);
                             if (im != 0xFFFFFFFFu) break;
-                            d = d_next;
-                            s = s_next;
+                            gp += 32;
+                            en = nx;
                         }
                     }
-                    // restage the term at its new cursor; the copy lands while the rest of the window is processed
+                    // new cursor; the row is restaged once at least half of it is consumed (always for a dense term)
                     __syncwarp();
                     if (lane == 0) pos[tt] = p;
-                    if (static_cast<uint32_t>(lane) < CH) {
-                        cp_async4(sdoc + sidx(tt, lane), P.run_docs + p + lane);
-                        cp_async4(ssc + sidx(tt, lane), P.run_scores + p + lane);
+                    if (is_dense || p - a0 >= (CH >> 1)) {
+                        if (lane == 0) anc[tt] = p;
+                        stage_row(tt, p);
                     }
                 }
             }

@@ -106,8 +106,7 @@ struct dgpu_engine {
     DevBuf<DTerm> d_dterms;
     DevBuf<DItem> d_items;
     DevBuf<QTermRun> d_qruns;
-    DevBuf<uint32_t> d_run_docs;
-    DevBuf<float> d_run_scores;
+    DevBuf<uint2> d_runs;
     DevBuf<uint64_t> d_part_keys;
     DevBuf<int32_t> d_part_counts;
     DevBuf<int64_t> d_part_hits;
@@ -224,7 +223,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     for (void* p : e->owned) cudaFree(p);
     e->d_queries.release(); e->d_terms.release(); e->d_filters.release(); e->d_order.release();
     e->d_counter.release(); e->d_keys.release(); e->d_counts.release(); e->d_hits.release();
-    e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_run_docs.release(); e->d_run_scores.release();
+    e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_runs.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
     e->d_witems.release(); e->d_part_off.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -515,14 +514,14 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     CU(e->d_witems.ensure(witems.size()));
     if (e->kernel == 3) {
         const size_t want = static_cast<size_t>(run_entries) + 16384;  // tail slack for ring look-ahead loads
-        if (want > e->d_run_docs.cap) {
+        if (want > e->d_runs.cap) {
             // grow with headroom: the scratch is reused by every batch
             const size_t cap = want + want / 4;
-            if (e->d_run_docs.ensure(cap) != cudaSuccess || e->d_run_scores.ensure(cap) != cudaSuccess)
+            if (e->d_runs.ensure(cap) != cudaSuccess)
                 return fail("cannot allocate %zu MB of decode scratch (%s); split the batch", cap * 8 >> 20,
                             cudaGetErrorString(cudaGetLastError()));
         }
-        CU(cudaMemsetAsync(e->d_run_docs.p, 0xFF, sizeof(uint32_t) * kRunPad, e->stream));
+        CU(cudaMemsetAsync(e->d_runs.p, 0xFF, sizeof(uint2) * kRunPad, e->stream));
     }
     if (b->n_queries) {
         CU(cudaMemcpyAsync(e->d_queries.p, b->queries, sizeof(dgpu_query) * b->n_queries, cudaMemcpyHostToDevice, e->stream));
@@ -599,8 +598,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.order = e->d_order.p;
     P.n_items = e->n_witems;
     P.work_counter = e->d_counter.p;
-    P.run_docs = e->d_run_docs.p;
-    P.run_scores = e->d_run_scores.p;
+    P.runs = e->d_runs.p;
     P.k = e->k;
     P.max_terms = (e->max_terms + 3u) & ~3u;
     P.cand_cap = e->plan_cap;
@@ -619,7 +617,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     if (e->n_ditems) {
         const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * 8));
         decode_score_kernel<<<grid, kDecodeThreads, 0, stream>>>(e->ix, e->d_dterms.p, e->d_items.p, e->n_ditems,
-                                                                 e->d_run_docs.p, e->d_run_scores.p);
+                                                                 e->d_runs.p);
         e->launches++;
         CU(cudaGetLastError());
     }
