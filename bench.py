@@ -331,7 +331,7 @@ def main():
         ph = (C.c_float * 3)()
         lib.dgpu_engine_last_phase_ms(eng, C.byref(ph))
         phase_ms.append([float(x) for x in ph])
-    bstats = (C.c_uint64 * 6)()
+    bstats = (C.c_uint64 * 8)()
     lib.dgpu_engine_batch_stats(eng, C.byref(bstats))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -383,11 +383,13 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel": "accumulate_topk_kernel" if batched else "search_kernel",
+                "kernel": ("intersect_topk_kernel" if int(bstats[7]) > int(bstats[6]) else "accumulate_topk_kernel") if batched else "search_kernel",
                 "kernel_ms": float(kt[0]), "algorithmic_bytes_per_launch": stats["algorithmic_bytes"],
                 "postings_per_launch": stats["postings"],
                 "postings_per_s": stats["postings"] / (float(kt[0]) / 1e3),
-                "step_ms_by_kernel": {"decode_score_kernel": med[0], "accumulate_topk_kernel": med[1], "merge_parts_kernel": med[2]}}
+                "step_ms_by_kernel": {"decode_score_kernel": med[0], "accumulate_topk_kernel+intersect_topk_kernel": med[1],
+                                      "merge_items_kernel": med[2]},
+                "work_items": {"accumulate_topk_kernel": int(bstats[6]), "intersect_topk_kernel": int(bstats[7])}}
     if batched and med[0] > 0:
         # K1 alone: reads the compressed blocks of the distinct terms once, writes 8 B per decoded posting slot
         rd, wr = int(bstats[4]), int(bstats[2]) * 8

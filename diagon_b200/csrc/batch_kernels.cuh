@@ -37,7 +37,7 @@ struct QTermRun {       // one query term, resolved to its run in the scratch
     uint32_t base;      // first scratch entry
     uint32_t len;       // entries that may hold postings (padding after them is readable)
     uint32_t meta;      // DGPU_ROLE_*
-    uint32_t pad;
+    uint32_t pad;       // first row of the term's skip index (block first docs): used by intersect_topk_kernel
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -406,6 +406,158 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
         }
 
         // ---- final select
+        __syncwarp();
+        const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
+        for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;
+        warp_bitonic_sort_desc(cand, nsort, lane);
+        const uint32_t n_out = min(n_cand, static_cast<uint32_t>(P.k));
+        for (uint32_t i = lane; i < static_cast<uint32_t>(P.k); i += 32)
+            P.out_keys[static_cast<size_t>(item) * P.k + i] = i < n_out ? cand[i] : 0ull;
+        if (lane == 0) {
+            P.out_counts[item] = static_cast<int32_t>(n_out);
+            P.out_hits[item] = static_cast<int64_t>(hits);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: AND-k by intersection. One warp per work item (a pure-MUST query of 2..32 terms, or a doc range of one).
+// The warp walks the SHORTEST list 32 postings at a time (lane = one candidate doc) and looks every candidate up
+// in the other lists: a galloping / binary search over the list's skip index (first doc of each 128-posting block,
+// from a cursor that only moves forward), then a binary search inside that block of the decoded run. Terms are
+// visited in clause order and the scores are added in that order starting from 0.0f, exactly as
+// ConjunctionScorer::score does (BooleanQuery.cpp:119-126); a chunk none of whose candidates survives a term skips
+// the remaining terms. Hits are candidates found in every list (and passing the range filters); they go straight
+// into the top-k pool: no accumulator window, no harvest.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+intersect_topk_kernel(DeviceIndex ix, AccumParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(warp) * P.warp_smem);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (;;) {
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(P.work_counter, 1u);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (slot >= P.n_items) break;
+        const uint32_t item = P.order[slot];
+        const WorkItem wi = P.items[item];
+        const dgpu_query qd = P.queries[wi.query];
+        const QTermRun* qt = P.terms + qd.term_begin;
+        const uint32_t nt = qd.term_end - qd.term_begin;   // 2..32, all MUST
+        const uint32_t nf = qd.filter_end - qd.filter_begin;
+        const dgpu_qfilter* qf = P.filters + qd.filter_begin;
+        const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
+
+        // lane t holds term t: run base, number of blocks, first row of its skip index, block cursor
+        uint32_t base_t = 0, nb_t = 0xFFFFFFFFu, tb_t = 0, cb_t = 0;
+        if (static_cast<uint32_t>(lane) < nt) {
+            const QTermRun r = qt[lane];
+            base_t = r.base;
+            nb_t = r.len / DGPU_BLOCK_POSTINGS;
+            tb_t = r.pad;
+        }
+        // lead = the shortest list (lowest clause on ties)
+        const uint32_t min_nb = __reduce_min_sync(0xFFFFFFFFu, nb_t);
+        const int lead = __ffs(__ballot_sync(0xFFFFFFFFu, nb_t == min_nb)) - 1;
+        uint32_t p = __shfl_sync(0xFFFFFFFFu, base_t, lead);
+        if (lo > ix.doc_lo && min_nb) {   // first lead entry with doc >= lo
+            uint32_t a = 0, b = min_nb * DGPU_BLOCK_POSTINGS;
+            while (a < b) {
+                const uint32_t mid = (a + b) >> 1;
+                if (__ldg(&P.runs[p + mid].x) < lo) a = mid + 1; else b = mid;
+            }
+            p += a;
+        }
+
+        uint32_t n_cand = 0, hits = 0;
+        uint64_t thresh = 0;
+        auto prune = [&]() {
+            const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
+            for (uint32_t i = n_cand + lane; i < n; i += 32) cand[i] = 0;
+            warp_bitonic_sort_desc(cand, n, lane);
+            if (n_cand >= static_cast<uint32_t>(P.k)) {
+                thresh = cand[P.k - 1];
+                n_cand = P.k;
+            }
+        };
+
+        for (; min_nb;) {
+            const uint2 en = __ldg(P.runs + p + lane);
+            const uint32_t d = en.x;
+            bool alive = d < hi;                       // padding entries are 0xFFFFFFFF
+            const uint32_t vm = __ballot_sync(0xFFFFFFFFu, alive);
+            if (!vm) break;
+            float score = 0.0f;
+            for (uint32_t t = 0; t < nt; ++t) {
+                float sc = __uint_as_float(en.y);
+                if (static_cast<int>(t) != lead) {
+                    const uint32_t base = __shfl_sync(0xFFFFFFFFu, base_t, t);
+                    const uint32_t nb = __shfl_sync(0xFFFFFFFFu, nb_t, t);
+                    const uint32_t cb = __shfl_sync(0xFFFFFFFFu, cb_t, t);
+                    const uint32_t* first = ix.first + __shfl_sync(0xFFFFFFFFu, tb_t, t);
+                    uint32_t blk = cb;
+                    bool found = false;
+                    if (alive && nb) {
+                        // last block in [cb, nb) whose first doc is <= d: gallop from the cursor, then bisect
+                        uint32_t a = cb, step = 1;
+                        while (a + step < nb && __ldg(first + a + step) <= d) {
+                            a += step;
+                            step <<= 1;
+                        }
+                        uint32_t b = min(nb, a + step);      // first[a] <= d (or a == cb), first[b] > d (or b == nb)
+                        while (b - a > 1) {
+                            const uint32_t mid = (a + b) >> 1;
+                            if (__ldg(first + mid) <= d) a = mid; else b = mid;
+                        }
+                        blk = a;
+                        // d inside block blk of the run? (entries past the postings of the last block are 0xFFFFFFFF)
+                        const uint2* row = P.runs + base + static_cast<size_t>(blk) * DGPU_BLOCK_POSTINGS;
+                        uint32_t x = 0, y = DGPU_BLOCK_POSTINGS;
+                        while (x < y) {
+                            const uint32_t mid = (x + y) >> 1;
+                            if (__ldg(&row[mid].x) < d) x = mid + 1; else y = mid;
+                        }
+                        if (x < DGPU_BLOCK_POSTINGS) {
+                            const uint2 hit = __ldg(row + x);
+                            found = hit.x == d;
+                            sc = __uint_as_float(hit.y);
+                        }
+                    }
+                    alive = alive && found;
+                    // the cursor follows the first candidate of the chunk (candidates ascend, so do their blocks)
+                    const uint32_t blk0 = __shfl_sync(0xFFFFFFFFu, blk, __ffs(vm) - 1);
+                    if (lane == static_cast<int>(t)) cb_t = blk0;
+                }
+                score = __fadd_rn(score, sc);
+                if (!__ballot_sync(0xFFFFFFFFu, alive)) break;   // nobody left in this chunk
+            }
+            bool match = alive;
+            if (nf) {
+                for (uint32_t f = 0; f < nf && match; ++f) {
+                    const int64_t val = ix.dv[qf[f].column][d - ix.doc_lo];
+                    match = (val >= qf[f].lo) && (val <= qf[f].hi);
+                    score = __fadd_rn(score, 1.0f);  // constant score of the range clause (NumericRangeQuery.cpp:117-120)
+                }
+            }
+            if (n_cand + 32u > P.cand_cap) prune();
+            const uint32_t sb = __float_as_uint(score);
+            const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+            const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - d);
+            const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+            hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
+            if (pm) {
+                if (push) cand[n_cand + __popc(pm & lt_mask)] = key;
+                n_cand += __popc(pm);
+            }
+            if (vm != 0xFFFFFFFFu) break;   // the lead list (or the doc range) ended inside this chunk
+            p += 32;
+        }
+
         __syncwarp();
         const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
         for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;

@@ -134,6 +134,8 @@ struct dgpu_engine {
     int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
     int warps_per_sm = 16;   // independent scoring warps per SM (each owns 1/n of the shared memory)
     int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
+    int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
+    uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
     // stats
     uint64_t launches = 0;
     float last_ms = 0.f;
@@ -280,6 +282,10 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->force_splits = static_cast<int>(value);
         return 0;
     }
+    if (!std::strcmp(name, "intersect")) {
+        e->intersect = value ? 1 : 0;
+        return 0;
+    }
     if (!std::strcmp(name, "max_parts")) {
         if (value < 0 || value > 64) return fail("max_parts must be in [0, 64]");
         e->max_parts = static_cast<int>(value);
@@ -376,6 +382,8 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->k = k;
     // ---- validation, per-query cost (posting blocks), distinct terms of the batch
     std::vector<uint64_t> cost(b->n_queries, 0);
+    std::vector<uint64_t> lead_cost(b->n_queries, ~0ull);   // blocks of the shortest list (what an intersection walks)
+    std::vector<uint8_t> is_and(b->n_queries, 0);
     uint32_t max_terms = 1;
     bool need_cnt = false;
     if (e->h_slot_epoch.size() != e->n_terms) {
@@ -396,19 +404,29 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         const dgpu_query& qd = b->queries[q];
         if (qd.term_end < qd.term_begin || qd.term_end > b->n_terms) return fail("query %u: bad term slice", q);
         if (qd.filter_end < qd.filter_begin || qd.filter_end > b->n_filters) return fail("query %u: bad filter slice", q);
-        max_terms = std::max(max_terms, qd.term_end - qd.term_begin);
-        if (qd.term_end - qd.term_begin > 1024) return fail("query %u: more than 1024 terms", q);
-        if (qd.n_must > 1 || qd.min_should_match > 1) need_cnt = true;
+        const uint32_t nt_q = qd.term_end - qd.term_begin;
+        if (nt_q > 1024) return fail("query %u: more than 1024 terms", q);
         if (qd.min_should_match > 254 || qd.n_must > 254) return fail("query %u: more than 254 required matches", q);
+        // a pure conjunction (every term MUST) of 2..32 terms is intersected, everything else is accumulated
+        bool all_must = e->kernel == 3 && e->intersect && nt_q >= 2 && nt_q <= 32 && qd.n_must == nt_q;
+        for (uint32_t t = qd.term_begin; all_must && t < qd.term_end; ++t) all_must = b->terms[t].role == DGPU_ROLE_MUST;
+        is_and[q] = all_must ? 1 : 0;
+        if (!all_must) {
+            max_terms = std::max(max_terms, nt_q);
+            if (qd.n_must > 1 || qd.min_should_match > 1) need_cnt = true;
+        }
         for (uint32_t t = qd.term_begin; t < qd.term_end; ++t) {
             const dgpu_qterm& qt = b->terms[t];
             if (qt.role == DGPU_ROLE_MUST_NOT) need_cnt = true;
             QTermRun run{0u, 0u, qt.role, 0u};
+            uint64_t& lead = lead_cost[q];
             if (qt.term_id != kNoTerm) {
                 if (qt.term_id >= e->n_terms) return fail("query %u: term id out of range", q);
                 if (qt.field >= e->n_fields) return fail("query %u: bad field", q);
                 const uint32_t nb = e->h_term_block_start[qt.term_id + 1] - e->h_term_block_start[qt.term_id];
                 cost[q] += nb;
+                lead = std::min<uint64_t>(lead, nb);
+                run.pad = e->h_term_block_start[qt.term_id];
                 // distinct (term, idf, field): the first use of a term id in this batch claims its slot; a later use
                 // with another idf / field (a boosted clause) gets a slot of its own
                 uint32_t slot = 0xFFFFFFFFu;
@@ -437,6 +455,8 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
                     run.base = dterms[slot].out_base;
                     run.len = nb * DGPU_BLOCK_POSTINGS;
                 }
+            } else {
+                lead = 0;   // a term that is absent here: a conjunction has no hits on this GPU
             }
             qruns[t] = run;
         }
@@ -459,6 +479,8 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     std::vector<uint64_t> item_cost;
     bool split_any = false;
     if (e->kernel == 3) {
+        for (uint32_t q = 0; q < b->n_queries; ++q)
+            if (is_and[q]) cost[q] = 1 + 8 * std::min<uint64_t>(lead_cost[q], cost[q]);   // ~8 probes per lead posting and term
         uint64_t total_cost = 0;
         for (uint32_t q = 0; q < b->n_queries; ++q) total_cost += cost[q];
         const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) * e->plan_ctas * e->plan_wpc;
@@ -485,20 +507,27 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->split_any = split_any;
     e->n_splits = b->n_queries ? static_cast<uint32_t>((witems.size() + b->n_queries - 1) / b->n_queries) : 1;
 
-    // ---- work order: decreasing cost so the long items start first
+    // ---- work order: decreasing cost so the long items start first; accumulate items first, then intersect items
     const uint32_t n_items = e->kernel == 3 ? e->n_witems : b->n_queries;
     std::vector<uint32_t> order(n_items);
     std::iota(order.begin(), order.end(), 0u);
-    if (e->kernel == 3)
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return item_cost[a] > item_cost[c]; });
-    else
+    e->n_acc_items = n_items;
+    e->n_and_items = 0;
+    if (e->kernel == 3) {
+        auto mid = std::stable_partition(order.begin(), order.end(), [&](uint32_t a) { return !is_and[witems[a].query]; });
+        e->n_acc_items = static_cast<uint32_t>(mid - order.begin());
+        e->n_and_items = n_items - e->n_acc_items;
+        std::stable_sort(order.begin(), mid, [&](uint32_t a, uint32_t c) { return item_cost[a] > item_cost[c]; });
+        std::stable_sort(mid, order.end(), [&](uint32_t a, uint32_t c) { return item_cost[a] > item_cost[c]; });
+    } else {
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+    }
 
     CU(e->d_queries.ensure(b->n_queries));
     CU(e->d_terms.ensure(b->n_terms));
     CU(e->d_filters.ensure(b->n_filters));
     CU(e->d_order.ensure(n_items));
-    CU(e->d_counter.ensure(1));
+    CU(e->d_counter.ensure(2));
     CU(e->d_keys.ensure(static_cast<size_t>(b->n_queries) * k));
     CU(e->d_counts.ensure(b->n_queries));
     CU(e->d_hits.ensure(b->n_queries));
@@ -596,7 +625,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.filters = e->d_filters.p;
     P.items = e->d_witems.p;
     P.order = e->d_order.p;
-    P.n_items = e->n_witems;
+    P.n_items = e->n_acc_items;
     P.work_counter = e->d_counter.p;
     P.runs = e->d_runs.p;
     P.k = e->k;
@@ -612,7 +641,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.out_counts = split ? e->d_part_counts.p : e->d_counts.p;
     P.out_hits = split ? e->d_part_hits.p : e->d_hits.p;
 
-    CU(cudaMemsetAsync(e->d_counter.p, 0, 4, stream));
+    CU(cudaMemsetAsync(e->d_counter.p, 0, 8, stream));
     CU(cudaEventRecord(e->ev0, stream));
     if (e->n_ditems) {
         const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * 8));
@@ -625,11 +654,25 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     auto kern = e->need_cnt ? accumulate_topk_kernel<true> : accumulate_topk_kernel<false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    const uint64_t want_ctas = (static_cast<uint64_t>(P.n_items) + e->plan_wpc - 1) / e->plan_wpc;
-    const int grid = static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * e->plan_ctas, want_ctas)));
-    kern<<<grid, e->plan_wpc * 32, smem, stream>>>(e->ix, P);
-    CU(cudaGetLastError());
-    e->launches++;
+    if (P.n_items) {
+        const uint64_t want_ctas = (static_cast<uint64_t>(P.n_items) + e->plan_wpc - 1) / e->plan_wpc;
+        const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * e->plan_ctas, want_ctas));
+        kern<<<grid, e->plan_wpc * 32, smem, stream>>>(e->ix, P);
+        CU(cudaGetLastError());
+        e->launches++;
+    }
+    if (e->n_and_items) {
+        AccumParams Q = P;
+        Q.order = e->d_order.p + e->n_acc_items;
+        Q.n_items = e->n_and_items;
+        Q.work_counter = e->d_counter.p + 1;
+        CU(cudaFuncSetAttribute(intersect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const uint64_t want_ctas = (static_cast<uint64_t>(Q.n_items) + e->plan_wpc - 1) / e->plan_wpc;
+        const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * e->plan_ctas, want_ctas));
+        intersect_topk_kernel<<<grid, e->plan_wpc * 32, smem, stream>>>(e->ix, Q);
+        CU(cudaGetLastError());
+        e->launches++;
+    }
     CU(cudaEventRecord(e->ev_b, stream));
     if (split) {
         merge_items_kernel<<<e->n_queries, 128, 0, stream>>>(e->d_part_keys.p, e->d_part_counts.p, e->d_part_hits.p,
@@ -695,13 +738,15 @@ int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]) {
     return 0;
 }
 
-int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[6]) {
+int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[8]) {
     out[0] = e->n_dterms;
     out[1] = e->n_ditems;
     out[2] = e->run_entries;
     out[3] = e->n_splits;
     out[4] = e->distinct_bytes;
     out[5] = e->last_window;
+    out[6] = e->n_acc_items;
+    out[7] = e->n_and_items;
     return 0;
 }
 

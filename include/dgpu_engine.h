@@ -150,12 +150,14 @@ int dgpu_engine_merge_parts(dgpu_engine* e, const uint64_t* part_keys, const int
 uint64_t dgpu_engine_launch_count(const dgpu_engine* e);
 float dgpu_engine_last_search_ms(const dgpu_engine* e);
 /* Device time (ms) of the phases of the last search: [0] decode_score_kernel (every distinct term of the batch
- * decoded and scored once), [1] accumulate_topk_kernel, [2] merge of doc-range splits (0 when not split). */
+ * decoded and scored once), [1] accumulate_topk_kernel + intersect_topk_kernel (whichever the batch needs),
+ * [2] merge of doc-range parts (0 when no query was split). */
 int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]);
 /* Shape of the staged batch: [0] distinct terms, [1] decode work items, [2] (doc, score) entries of the decode
- * scratch, [3] doc-range splits per query, [4] compressed bytes of the distinct terms (what decode_score_kernel
- * reads), [5] docs per window of the last accumulate_topk_kernel launch. */
-int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[6]);
+ * scratch, [3] mean doc-range parts per query, [4] compressed bytes of the distinct terms (what decode_score_kernel
+ * reads), [5] docs per window of accumulate_topk_kernel, [6] work items of accumulate_topk_kernel, [7] work items
+ * of intersect_topk_kernel (pure conjunctions). */
+int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[8]);
 
 /* Tunables. Returns 0 or -1 for an unknown name / bad value. */
 int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value);

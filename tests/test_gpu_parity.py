@@ -68,20 +68,22 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
             assert np.isnan(td.maxScore)
 
 
-# (window_docs, stage_log2, splits, warps per CTA, warps per SM): small windows walk many windows per query, stage_log2 = 1
-# pushes almost every term through the global-memory continuation, splits exercises doc-range parts + the device merge
-_TUNINGS = [(0, 0, 0, 4, 16), (1024, 0, 1, 4, 16), (256, 1, 1, 8, 32), (4096, 2, 3, 2, 8), (64, 3, 7, 1, 4), (2048, 0, 16, 4, 12)]
+# (window_docs, stage_log2, splits, warps per CTA, warps per SM, intersect): small windows walk many windows per query,
+# stage_log2 = 1 pushes almost every term through the global-memory continuation, splits exercises doc-range parts + the
+# device merge, intersect = 0 sends the conjunctions through the counting windows instead of intersect_topk_kernel
+_TUNINGS = [(0, 0, 0, 4, 16, 1), (1024, 0, 1, 4, 16, 0), (256, 1, 1, 8, 32, 1), (4096, 2, 3, 2, 8, 0), (64, 3, 7, 1, 4, 1),
+            (2048, 0, 16, 4, 12, 1)]
 
 
 @pytest.mark.parametrize("name", ["g1", "g2"])
-@pytest.mark.parametrize("window_docs,stage_log2,splits,warps,warps_per_sm", _TUNINGS)
+@pytest.mark.parametrize("window_docs,stage_log2,splits,warps,warps_per_sm,intersect", _TUNINGS)
 def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, name, window_docs, stage_log2, splits, warps,
-                                                        warps_per_sm):
+                                                        warps_per_sm, intersect):
     """dgpu_search_batch_text: the whole query file in one launch; window size, staging depth, doc-range parts and
     the warp layout must not change any result."""
     r = readers[name]
     for opt, v in (("window_docs", window_docs), ("stage_log2", stage_log2), ("splits", splits), ("warps", warps),
-                   ("warps_per_sm", warps_per_sm)):
+                   ("warps_per_sm", warps_per_sm), ("intersect", intersect)):
         r.set_option(opt, v)
     try:
         searcher = dg.IndexSearcher(r)
@@ -101,7 +103,7 @@ def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, nam
                     got = [(int(res.docs[q, j]), res.scores[q, j]) for j in range(res.counts[q])]
                     assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {i}")
     finally:
-        for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4), ("warps_per_sm", 16)):
+        for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4), ("warps_per_sm", 16), ("intersect", 1)):
             r.set_option(opt, v)
 
 
