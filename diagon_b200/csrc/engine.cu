@@ -20,9 +20,15 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <string>
 #include <vector>
+
+namespace dgpu {
+// host/host_index.cpp: runs body(begin, end, thread) over [0, n) on the persistent host worker pool (threads = 0: all)
+void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& body);
+}  // namespace dgpu
 
 namespace {
 
@@ -113,7 +119,6 @@ struct dgpu_engine {
     uint32_t n_dterms = 0, n_ditems = 0;
     uint64_t run_entries = 0;
     uint32_t n_splits = 1;              // average doc-range parts per query of the staged batch (reporting only)
-    uint64_t distinct_bytes = 0;        // compressed bytes (payload + 16 B skip row per block) of the distinct terms
     uint32_t last_window = 0;
     // launch plan of the batched path (made by stage_batch: the host sizes the per-term rings with it)
     uint32_t plan_cap = 0, plan_list = 0, plan_chlog = 5, plan_W = 0, plan_wpc = 4, plan_ctas = 1, plan_warp_smem = 0;
@@ -121,9 +126,14 @@ struct dgpu_engine {
     DevBuf<uint32_t> d_part_off;
     uint32_t n_witems = 0;
     bool split_any = false;
-    std::vector<uint32_t> h_slot;       // term id -> distinct slot of the batch being staged (epoch stamped)
-    std::vector<uint32_t> h_slot_epoch;
-    uint32_t epoch = 0;
+    struct TableEntry {
+        uint64_t key;   // term id << 32 | idf bits
+        uint32_t slot;
+        uint16_t field, epoch;
+    };
+    std::vector<TableEntry> h_table;    // distinct terms of the batch being staged (open addressing, epoch stamped)
+    std::vector<uint32_t> h_dterm_ids;  // term ids of the distinct terms (for the byte accounting of batch_stats)
+    uint16_t epoch = 0;
     // options
     int logw = 15;
     int ctas_per_sm = 3;
@@ -132,7 +142,7 @@ struct dgpu_engine {
     int force_splits = 0;    // 0 = automatic
     int window_docs = 0;     // 0 = the largest window that fits; else an upper bound (tests)
     int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
-    int warps_per_sm = 16;   // independent scoring warps per SM (each owns 1/n of the shared memory)
+    int warps_per_sm = 20;   // independent scoring warps per SM (each owns 1/n of the shared memory)
     int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
@@ -380,95 +390,133 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     if (k > DGPU_MAX_K) return fail("numHits %d exceeds DGPU_MAX_K", k);
     e->n_queries = b->n_queries;
     e->k = k;
-    // ---- validation, per-query cost (posting blocks), distinct terms of the batch
+    static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
+    auto tr0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dgpu trace]   stage/%s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tr0).count());
+        tr0 = now;
+    };
+    // ---- pass 1 (all host threads): validation, per-term block ranges, per-query cost (posting blocks)
     std::vector<uint64_t> cost(b->n_queries, 0);
     std::vector<uint64_t> lead_cost(b->n_queries, ~0ull);   // blocks of the shortest list (what an intersection walks)
     std::vector<uint8_t> is_and(b->n_queries, 0);
+    std::vector<QTermRun> qruns(b->n_terms);
+    const int n_threads = b->n_queries < 1024 ? 1 : 0;      // 0 = every host thread
+    struct Partial {
+        uint32_t max_terms = 1;
+        bool need_cnt = false;
+        std::string error;
+    };
+    std::vector<Partial> partial(256);
+    dgpu::parallel_for(b->n_queries, n_threads, [&](size_t q_lo, size_t q_hi, int th) {
+        Partial& pt = partial[static_cast<size_t>(th) & 255];
+        auto bad = [&](uint32_t q, const char* what) {
+            if (pt.error.empty()) pt.error = "query " + std::to_string(q) + ": " + what;
+        };
+        for (uint32_t q = static_cast<uint32_t>(q_lo); q < q_hi; ++q) {
+            const dgpu_query& qd = b->queries[q];
+            if (qd.term_end < qd.term_begin || qd.term_end > b->n_terms) { bad(q, "bad term slice"); continue; }
+            if (qd.filter_end < qd.filter_begin || qd.filter_end > b->n_filters) { bad(q, "bad filter slice"); continue; }
+            const uint32_t nt_q = qd.term_end - qd.term_begin;
+            if (nt_q > 1024) { bad(q, "more than 1024 terms"); continue; }
+            if (qd.min_should_match > 254 || qd.n_must > 254) { bad(q, "more than 254 required matches"); continue; }
+            // a pure conjunction (every term MUST) of 2..32 terms is intersected, everything else is accumulated
+            bool all_must = e->kernel == 3 && e->intersect && nt_q >= 2 && nt_q <= 32 && qd.n_must == nt_q;
+            for (uint32_t t = qd.term_begin; all_must && t < qd.term_end; ++t) all_must = b->terms[t].role == DGPU_ROLE_MUST;
+            is_and[q] = all_must ? 1 : 0;
+            if (!all_must) {
+                pt.max_terms = std::max(pt.max_terms, nt_q);
+                if (qd.n_must > 1 || qd.min_should_match > 1) pt.need_cnt = true;
+            }
+            uint64_t c = 0, lead = ~0ull;
+            for (uint32_t t = qd.term_begin; t < qd.term_end; ++t) {
+                const dgpu_qterm& qt = b->terms[t];
+                if (qt.role == DGPU_ROLE_MUST_NOT) pt.need_cnt = true;
+                QTermRun run{0u, 0u, qt.role, 0u};
+                if (qt.term_id != kNoTerm) {
+                    if (qt.term_id >= e->n_terms) { bad(q, "term id out of range"); continue; }
+                    if (qt.field >= e->n_fields) { bad(q, "bad field"); continue; }
+                    const uint32_t tb = e->h_term_block_start[qt.term_id];
+                    const uint32_t nb = e->h_term_block_start[qt.term_id + 1] - tb;
+                    c += nb;
+                    lead = std::min<uint64_t>(lead, nb);
+                    run.pad = tb;
+                    run.len = nb * DGPU_BLOCK_POSTINGS;
+                } else {
+                    lead = 0;   // a term that is absent here: a conjunction has no hits on this GPU
+                }
+                qruns[t] = run;
+            }
+            cost[q] = c;
+            lead_cost[q] = lead;
+            for (uint32_t f = qd.filter_begin; f < qd.filter_end; ++f)
+                if (b->filters[f].column < 0) bad(q, "bad filter column");
+        }
+    });
     uint32_t max_terms = 1;
     bool need_cnt = false;
-    if (e->h_slot_epoch.size() != e->n_terms) {
-        e->h_slot.assign(e->n_terms, 0);
-        e->h_slot_epoch.assign(e->n_terms, 0);
+    for (const Partial& pt : partial) {
+        if (!pt.error.empty()) return fail("%s", pt.error.c_str());
+        max_terms = std::max(max_terms, pt.max_terms);
+        need_cnt = need_cnt || pt.need_cnt;
+    }
+    lap("validate");
+
+    // ---- pass 2: the distinct (term, idf, field) of the batch -> runs in the scratch. The first use of a key claims a
+    // slot; the same term with another idf / field (a boosted clause) gets a slot of its own. Open addressing over a
+    // table that stays in the host's L2, stamped with an epoch instead of being cleared.
+    size_t tcap = 1024;
+    while (tcap < 2 * static_cast<size_t>(b->n_terms)) tcap <<= 1;
+    if (e->h_table.size() != tcap) {
+        e->h_table.assign(tcap, dgpu_engine::TableEntry{0, 0, 0, 0});
         e->epoch = 0;
     }
     if (++e->epoch == 0) {  // wrapped: stamps are ambiguous again
-        std::fill(e->h_slot_epoch.begin(), e->h_slot_epoch.end(), 0u);
+        std::fill(e->h_table.begin(), e->h_table.end(), dgpu_engine::TableEntry{0, 0, 0, 0});
         e->epoch = 1;
     }
     std::vector<DTerm> dterms;
     std::vector<DItem> items;
-    std::vector<QTermRun> qruns(b->n_terms);
+    dterms.reserve(b->n_terms / 2 + 16);
     uint64_t run_entries = kRunPad;  // [0, kRunPad) is the empty run (terms absent on this GPU)
-    uint64_t distinct_bytes = 0;
-    for (uint32_t q = 0; q < b->n_queries; ++q) {
-        const dgpu_query& qd = b->queries[q];
-        if (qd.term_end < qd.term_begin || qd.term_end > b->n_terms) return fail("query %u: bad term slice", q);
-        if (qd.filter_end < qd.filter_begin || qd.filter_end > b->n_filters) return fail("query %u: bad filter slice", q);
-        const uint32_t nt_q = qd.term_end - qd.term_begin;
-        if (nt_q > 1024) return fail("query %u: more than 1024 terms", q);
-        if (qd.min_should_match > 254 || qd.n_must > 254) return fail("query %u: more than 254 required matches", q);
-        // a pure conjunction (every term MUST) of 2..32 terms is intersected, everything else is accumulated
-        bool all_must = e->kernel == 3 && e->intersect && nt_q >= 2 && nt_q <= 32 && qd.n_must == nt_q;
-        for (uint32_t t = qd.term_begin; all_must && t < qd.term_end; ++t) all_must = b->terms[t].role == DGPU_ROLE_MUST;
-        is_and[q] = all_must ? 1 : 0;
-        if (!all_must) {
-            max_terms = std::max(max_terms, nt_q);
-            if (qd.n_must > 1 || qd.min_should_match > 1) need_cnt = true;
-        }
-        for (uint32_t t = qd.term_begin; t < qd.term_end; ++t) {
-            const dgpu_qterm& qt = b->terms[t];
-            if (qt.role == DGPU_ROLE_MUST_NOT) need_cnt = true;
-            QTermRun run{0u, 0u, qt.role, 0u};
-            uint64_t& lead = lead_cost[q];
-            if (qt.term_id != kNoTerm) {
-                if (qt.term_id >= e->n_terms) return fail("query %u: term id out of range", q);
-                if (qt.field >= e->n_fields) return fail("query %u: bad field", q);
-                const uint32_t nb = e->h_term_block_start[qt.term_id + 1] - e->h_term_block_start[qt.term_id];
-                cost[q] += nb;
-                lead = std::min<uint64_t>(lead, nb);
-                run.pad = e->h_term_block_start[qt.term_id];
-                // distinct (term, idf, field): the first use of a term id in this batch claims its slot; a later use
-                // with another idf / field (a boosted clause) gets a slot of its own
-                uint32_t slot = 0xFFFFFFFFu;
-                if (e->h_slot_epoch[qt.term_id] == e->epoch) {
-                    const DTerm& d = dterms[e->h_slot[qt.term_id]];
-                    uint32_t a, c;
-                    std::memcpy(&a, &d.idf, 4);
-                    std::memcpy(&c, &qt.idf, 4);
-                    if (a == c && d.field == qt.field) slot = e->h_slot[qt.term_id];
-                }
-                if (slot == 0xFFFFFFFFu && nb > 0) {
-                    slot = static_cast<uint32_t>(dterms.size());
-                    if (e->h_slot_epoch[qt.term_id] != e->epoch) {
-                        e->h_slot_epoch[qt.term_id] = e->epoch;
-                        e->h_slot[qt.term_id] = slot;
-                    }
-                    dterms.push_back(DTerm{qt.term_id, qt.idf, qt.field, static_cast<uint32_t>(run_entries)});
-                    const uint32_t b0 = e->h_term_block_start[qt.term_id];
-                    distinct_bytes += 16ull * (e->h_block_off[b0 + nb] - e->h_block_off[b0]) + 16ull * nb;
-                    for (uint32_t rel = 0; rel < nb; rel += kItemBlocks) items.push_back(DItem{slot, rel});
-                    run_entries += (static_cast<uint64_t>(nb) + kPadBlocks) * DGPU_BLOCK_POSTINGS;
-                    if (run_entries > 0xFFFFFFFFull - 4096)
-                        return fail("batch decodes to more than 2^32 postings; split the batch");
-                }
-                if (slot != 0xFFFFFFFFu) {
-                    run.base = dterms[slot].out_base;
-                    run.len = nb * DGPU_BLOCK_POSTINGS;
-                }
-            } else {
-                lead = 0;   // a term that is absent here: a conjunction has no hits on this GPU
+    for (uint32_t t = 0; t < b->n_terms; ++t) {
+        QTermRun& run = qruns[t];
+        if (run.len == 0) continue;   // absent here, or no postings
+        const dgpu_qterm& qt = b->terms[t];
+        uint32_t idf_bits;
+        std::memcpy(&idf_bits, &qt.idf, 4);
+        const uint64_t key = (static_cast<uint64_t>(qt.term_id) << 32) | idf_bits;
+        size_t h = static_cast<size_t>((key * 0x9E3779B97F4A7C15ull) >> 20) & (tcap - 1);
+        uint32_t slot = 0xFFFFFFFFu;
+        for (;; h = (h + 1) & (tcap - 1)) {
+            dgpu_engine::TableEntry& te = e->h_table[h];
+            if (te.epoch != e->epoch) {   // free: claim
+                slot = static_cast<uint32_t>(dterms.size());
+                te = dgpu_engine::TableEntry{key, slot, qt.field, e->epoch};
+                const uint32_t nb = run.len / DGPU_BLOCK_POSTINGS;
+                dterms.push_back(DTerm{qt.term_id, qt.idf, qt.field, static_cast<uint32_t>(run_entries)});
+                for (uint32_t rel = 0; rel < nb; rel += kItemBlocks) items.push_back(DItem{slot, rel});
+                run_entries += (static_cast<uint64_t>(nb) + kPadBlocks) * DGPU_BLOCK_POSTINGS;
+                break;
             }
-            qruns[t] = run;
+            if (te.key == key && te.field == qt.field) {
+                slot = te.slot;
+                break;
+            }
         }
-        for (uint32_t f = qd.filter_begin; f < qd.filter_end; ++f)
-            if (b->filters[f].column < 0) return fail("query %u: bad filter column", q);
+        if (run_entries > 0xFFFFFFFFull - 4096) return fail("batch decodes to more than 2^32 postings; split the batch");
+        run.base = dterms[slot].out_base;
     }
+    lap("terms");
     e->max_terms = max_terms;
     e->need_cnt = need_cnt;
     e->n_dterms = static_cast<uint32_t>(dterms.size());
     e->n_ditems = static_cast<uint32_t>(items.size());
     e->run_entries = run_entries;
-    e->distinct_bytes = distinct_bytes;
+    e->h_dterm_ids.resize(dterms.size());
+    for (size_t i = 0; i < dterms.size(); ++i) e->h_dterm_ids[i] = dterms[i].term_id;
     if (plan_batched(e)) return -1;
 
     // ---- work items: one warp scores one (query, doc range). A long query is cut into doc-range parts so that no
@@ -507,6 +555,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->split_any = split_any;
     e->n_splits = b->n_queries ? static_cast<uint32_t>((witems.size() + b->n_queries - 1) / b->n_queries) : 1;
 
+    lap("items");
     // ---- work order: decreasing cost so the long items start first; accumulate items first, then intersect items
     const uint32_t n_items = e->kernel == 3 ? e->n_witems : b->n_queries;
     std::vector<uint32_t> order(n_items);
@@ -523,6 +572,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
     }
 
+    lap("order");
     CU(e->d_queries.ensure(b->n_queries));
     CU(e->d_terms.ensure(b->n_terms));
     CU(e->d_filters.ensure(b->n_filters));
@@ -570,6 +620,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         }
     }
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+    lap("h2d");
     return 0;
 }
 
@@ -743,7 +794,12 @@ int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[8]) {
     out[1] = e->n_ditems;
     out[2] = e->run_entries;
     out[3] = e->n_splits;
-    out[4] = e->distinct_bytes;
+    uint64_t bytes = 0;   // compressed bytes (payload + 16 B skip row per block) of the distinct terms
+    for (uint32_t id : e->h_dterm_ids) {
+        const uint32_t b0 = e->h_term_block_start[id], b1 = e->h_term_block_start[id + 1];
+        bytes += 16ull * (e->h_block_off[b1] - e->h_block_off[b0]) + 16ull * (b1 - b0);
+    }
+    out[4] = bytes;
     out[5] = e->last_window;
     out[6] = e->n_acc_items;
     out[7] = e->n_and_items;

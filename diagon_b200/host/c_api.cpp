@@ -496,7 +496,12 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
         std::vector<const Query*> qs;
         qs.reserve(parsed.size());
         for (auto& q : parsed) qs.push_back(q.get());
-        return run_batch(*as_searcher(searcher), qs, k, out_docs, out_scores, out_counts, out_total_hits);
+        const int rc = run_batch(*as_searcher(searcher), qs, k, out_docs, out_scores, out_counts, out_total_hits);
+        // a 10K-query batch is ~500K small heap objects: release them on all threads, not serially in the destructor
+        parallel_for(parsed.size(), parsed.size() < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
+            for (size_t i = b; i < e; ++i) parsed[i].reset();
+        });
+        return rc;
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
 

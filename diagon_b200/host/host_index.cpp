@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -19,27 +21,102 @@ static int default_threads(int threads) {
     return static_cast<int>(std::max(1u, std::min(hc, 64u)));
 }
 
+// A persistent pool: query batches call parallel_for several times per batch and thread creation would cost more
+// than the work. One job at a time (callers serialise on `gate`); a parallel_for issued from inside a worker runs
+// inline.
+namespace {
+
+class WorkerPool {
+public:
+    explicit WorkerPool(size_t n) {
+        for (size_t i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+            ++generation_;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    size_t size() const { return workers_.size(); }
+
+    // Runs job(i) for i in [0, parts) on the workers (parts <= size()) and waits.
+    void run(size_t parts, const std::function<void(size_t)>& job) {
+        std::lock_guard<std::mutex> gate(gate_);
+        {
+            std::lock_guard<std::mutex> l(m_);
+            job_ = &job;
+            parts_ = parts;
+            pending_ = parts;
+            ++generation_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+    static thread_local bool in_worker;
+
+private:
+    void loop(size_t id) {
+        in_worker = true;
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(size_t)>* job = nullptr;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) return;
+                if (id < parts_) job = job_;
+            }
+            if (job) {
+                (*job)(id);
+                std::lock_guard<std::mutex> l(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+
+    std::vector<std::thread> workers_;
+    std::mutex m_, gate_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)>* job_ = nullptr;
+    size_t parts_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
+thread_local bool WorkerPool::in_worker = false;
+
+WorkerPool& pool() {
+    static WorkerPool p(static_cast<size_t>(default_threads(0)));
+    return p;
+}
+
+}  // namespace
+
 void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& body) {
     threads = default_threads(threads);
     if (n == 0) return;
-    if (threads == 1 || n < 2) {
+    if (threads == 1 || n < 2 || WorkerPool::in_worker) {
         body(0, n, 0);
         return;
     }
-    size_t t = std::min<size_t>(static_cast<size_t>(threads), n);
-    std::vector<std::thread> pool;
+    WorkerPool& wp = pool();
+    const size_t t = std::min<size_t>(std::min<size_t>(static_cast<size_t>(threads), wp.size()), n);
     std::vector<std::exception_ptr> errs(t);
-    for (size_t i = 0; i < t; ++i) {
-        size_t b = n * i / t, e = n * (i + 1) / t;
-        pool.emplace_back([&, b, e, i] {
-            try {
-                body(b, e, static_cast<int>(i));
-            } catch (...) {
-                errs[i] = std::current_exception();
-            }
-        });
-    }
-    for (auto& th : pool) th.join();
+    wp.run(t, [&](size_t i) {
+        const size_t b = n * i / t, e = n * (i + 1) / t;
+        try {
+            body(b, e, static_cast<int>(i));
+        } catch (...) {
+            errs[i] = std::current_exception();
+        }
+    });
     for (auto& e : errs)
         if (e) std::rethrow_exception(e);
 }

@@ -103,7 +103,7 @@ def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, nam
                     got = [(int(res.docs[q, j]), res.scores[q, j]) for j in range(res.counts[q])]
                     assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {i}")
     finally:
-        for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4), ("warps_per_sm", 16), ("intersect", 1)):
+        for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4), ("warps_per_sm", 20), ("intersect", 1)):
             r.set_option(opt, v)
 
 
