@@ -378,6 +378,13 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                         }
                     }
                     bool match = bits != kSentinel;  // untouched, or touched only by an excluded term
+                    const uint32_t ord0 = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+                    if (!NEED_CNT && nf == 0) {
+                        // plain disjunction / term query: every touched doc is a hit; once the pool has a threshold almost
+                        // no doc beats it, so the common batch ends here
+                        hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
+                        if (!__ballot_sync(0xFFFFFFFFu, match && ord0 >= static_cast<uint32_t>(thresh >> 32))) continue;
+                    }
                     if (NEED_CNT && match) match = (c != 255) && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
                     const uint32_t doc = ws + rr;
                     float score = __uint_as_float(bits);
@@ -393,7 +400,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                     const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
                     // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
                     const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
-                    hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
+                    if (NEED_CNT || nf) hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
                     const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
                     if (pm) {
                         if (push) cand[n_cand + __popc(pm & lt_mask)] = key;
