@@ -32,6 +32,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line. Libraries write there too (NCCL prints its version banner with printf), so
+# file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the real stdout.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 WORKLOADS = {
     # name: (corpus, query log, line prefix, k, default batch)
@@ -195,20 +204,26 @@ def main():
     if args.queries:
         batch = args.queries
 
+    def workload_text(spec):
+        return (f"{args.workload}: {batch} x {kind.split()[0]}-{log_name} top-{k} on the {corpus_name} synthetic corpus "
+                f"({spec.num_docs} docs, vocab {spec.vocab}, {spec.num_segments} segments, scale {args.scale})")
+
     if args.impl == "reference":
         if rank != 0:
             return 0
+        import diagon_b200 as dg_ref
+
         base = reference_arm(args, corpus_name, log_name, kind, k, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "bm25_topk_queries_per_sec", "unit": "queries/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {corpus_name} corpus scale {args.scale}, {kind.split()[0]}-{log_name} top-{k}"}}
+                "config": {"workload": workload_text(dg_ref.named_corpus(corpus_name, args.scale))}}
         if base is None:
             line["unavailable"] = "oracle/_ref/ref_driver missing (run make -C oracle ref in the build container)"
         else:
-            line.update({"value": base["value"], "ms_per_step": None, "cpu_baseline": base,
+            line.update({"value": base["value"], "ms_per_step": 1e3 * args.cpu_sample_queries / base["value"], "cpu_baseline": base,
                          "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import ctypes as C
@@ -340,19 +355,24 @@ def main():
     ms_per_step = total_ms / args.steps
     value = nq / (ms_per_step / 1e3)
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers: query text in host memory -> results in host memory.
+    # N == 1: one call, dgpu_search_batch_text. N > 1: every rank compiles + stages the batch (host work + H2D), runs its
+    # kernels, the all-gather and the device merge, and copies the merged top-k back to the host.
     out = searcher._alloc(nq, k)
     e2e_times = []
-    for i in range(max(2, min(args.warmup, 3)) + args.steps):
+    n_warm = max(2, min(args.warmup, 3))
+    for i in range(n_warm + args.steps):
         barrier()
         t1 = time.perf_counter()
-        res = searcher.search_batch_text(text, k, nq, out)
-        if world > 1:
-            device_step()          # sharded: all-gather + merge of the local top-k
-            torch.cuda.synchronize()
-            _ = m_hits.cpu()
+        if world == 1:
+            res = searcher.search_batch_text(text, k, nq, out)
+        else:
+            searcher.stage_batch_text(text, k, want_stats=False)
+            lib.dgpu_engine_device_results(eng, C.byref(dres))
+            device_step()
+            _ = (m_keys.cpu(), m_counts.cpu(), m_hits.cpu())   # D2H on the bench stream, synchronising
         t2 = time.perf_counter()
-        if i >= max(2, min(args.warmup, 3)):
+        if i >= n_warm:
             e2e_times.append(t2 - t1)
     e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -407,8 +427,7 @@ def main():
             "metric": "bm25_topk_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {batch} x {kind.split()[0]}-{spec.vocab and log_name} top-{k} on the {corpus_name} "
-                                   f"synthetic corpus ({spec.num_docs} docs, vocab {spec.vocab}, {nseg} segments, scale {args.scale})",
+            "config": {"workload": workload_text(spec),
                        "sharding": f"{nseg} segments over {world} GPU(s), {'NCCL all-gather + device merge' if world > 1 else 'single GPU'}",
                        "l2": "inputs larger than L2 (device image %.0f MB per GPU)" % (reader.image_bytes() / 1e6),
                        "index_build_s": build_s, "postings_on_gpu": reader.num_postings(), "image_bytes": reader.image_bytes(),
@@ -425,7 +444,7 @@ def main():
                     line["cpu_baseline"] = base
             except Exception as e:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"error": str(e)[:300]}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -429,12 +429,14 @@ class IndexSearcher:
             raise DiagonError(_lib.last_error())
         return BatchResult(docs[:r], scores[:r], counts[:r], hits[:r])
 
-    def stage_batch_text(self, text: bytes, k: int):
+    def stage_batch_text(self, text: bytes, k: int, want_stats: bool = True):
+        """Compiles the batch and leaves it staged on the device. The statistics walk every posting block of the batch on
+        the host; pass want_stats=False on a timed path."""
         stats = np.zeros(3, dtype=np.int64)
-        r = _lib.load().dgpu_stage_batch_text(self._ptr, text, len(text), k, stats.ctypes.data)
+        r = _lib.load().dgpu_stage_batch_text(self._ptr, text, len(text), k, stats.ctypes.data if want_stats else None)
         if r < 0:
             raise DiagonError(_lib.last_error())
-        return {"queries": int(stats[0]), "algorithmic_bytes": int(stats[1]), "postings": int(stats[2])}
+        return {"queries": int(stats[0]), "algorithmic_bytes": int(stats[1]), "postings": int(stats[2])} if want_stats else {"queries": r}
 
     def close(self):
         if self._ptr:
