@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--warps-per-sm", type=int, default=0)
     ap.add_argument("--window-docs", type=int, default=0)
+    ap.add_argument("--stage-log2", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="3 = batched decode_score + accumulate_topk (default), 2 = fused windows")
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
@@ -322,6 +323,8 @@ def main():
         reader.set_option("warps_per_sm", args.warps_per_sm)
     if args.window_docs:
         reader.set_option("window_docs", args.window_docs)
+    if args.stage_log2:
+        reader.set_option("stage_log2", args.stage_log2)
     if args.kernel:
         reader.set_option("kernel", args.kernel)
     if world > 1:

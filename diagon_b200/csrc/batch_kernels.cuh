@@ -42,14 +42,97 @@ struct QTermRun {       // one query term, resolved to its run in the scratch
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K3a: StreamVByte block decode fused with BM25 scoring, one warp per 128-posting block.
-// Reads the compressed block (128-bit aligned payload, 2.2-3.5 B/posting), writes 4 postings per lane as two
-// 128-bit stores of (doc, score) entries. kPadBlocks blocks after the last one of a term are filled with kDocEnd so
-// that readers never need an end-of-run check.
+//
+// The compressed payload of a block (16-byte aligned, <= 1088 bytes) is brought into shared memory by ONE bulk
+// asynchronous copy (cp.async.bulk, the 1-D TMA path) issued by one lane and signalled on an mbarrier; every warp
+// keeps two buffers in flight, so the copy of block j + 2 overlaps the decode of block j and no lane ever waits on a
+// dependent chain of global loads (skip row -> control bytes -> data bytes). Decode works on the shared-memory copy:
+// 2-bit controls -> lengths -> warp scan -> unaligned 32-bit loads, warp scan of the doc deltas. Each lane owns 4
+// postings and writes them as two 128-bit stores of (doc, score) entries. kPadBlocks blocks after the last one of a
+// term are filled with kDocEnd so that readers never need an end-of-run check.
 // ------------------------------------------------------------------------------------------------
+constexpr int kDecodeWarps = kDecodeThreads / 32;
+constexpr int kPayloadBuf = 1152;   // >= the largest payload (64 control + 2 * 512 data bytes) + slack for 8-byte reads
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+
+// Decode of one block whose payload lies at `p` (shared memory). Same lane mapping as warp_decode_block.
+__device__ __forceinline__ uint32_t warp_decode_payload(const uint8_t* p, uint32_t meta, uint32_t first_doc, int lane,
+                                                        uint32_t (&doc)[4], uint32_t (&code)[4]) {
+    const uint32_t n = (meta & 0xFFu) + 1u;
+    const uint32_t dl = (meta >> 8) & 0xFFFFu;
+    const uint32_t cb = ((n + 3u) / 4u + 3u) & ~3u;
+    uint32_t cd = 0, cf = 0;
+    if (static_cast<uint32_t>(lane) < cb) {
+        cd = p[lane];
+        cf = p[cb + lane];
+    }
+    uint32_t ld[4], lf[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ld[j] = ((cd >> (2 * j)) & 3u) + 1u;
+        lf[j] = ((cf >> (2 * j)) & 3u) + 1u;
+    }
+    const uint32_t tot = (ld[0] + ld[1] + ld[2] + ld[3]) | ((lf[0] + lf[1] + lf[2] + lf[3]) << 16);
+    const uint32_t exc = warp_inclusive_scan(tot, lane) - tot;
+    uint32_t od = 2u * cb + (exc & 0xFFFFu);
+    uint32_t of = 2u * cb + dl + (exc >> 16);
+    uint32_t run = 0;
+    uint32_t delta[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t* wd = reinterpret_cast<const uint32_t*>(p + (od & ~3u));
+        const uint32_t v = __funnelshift_r(wd[0], wd[1], (od & 3u) * 8u) & (0xFFFFFFFFu >> (32u - 8u * ld[j]));
+        od += ld[j];
+        run += v;
+        delta[j] = run;
+        const uint32_t* wf = reinterpret_cast<const uint32_t*>(p + (of & ~3u));
+        code[j] = __funnelshift_r(wf[0], wf[1], (of & 3u) * 8u) & (0xFFFFFFFFu >> (32u - 8u * lf[j]));
+        of += lf[j];
+    }
+    const uint32_t base = first_doc + warp_inclusive_scan(run, lane) - run;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) doc[j] = base + delta[j];
+    return n;
+}
+
 __global__ void __launch_bounds__(kDecodeThreads)
 decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DItem* __restrict__ items, uint32_t n_items,
                     uint2* __restrict__ runs) {
+    __shared__ __align__(128) uint8_t s_buf[kDecodeWarps][2][kPayloadBuf];
+    __shared__ __align__(8) uint64_t s_mbar[kDecodeWarps][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(&s_mbar[warp][0]));
+    const uint32_t buf0 = static_cast<uint32_t>(__cvta_generic_to_shared(&s_buf[warp][0][0]));
+    if (lane == 0) {
+        mbar_init(mbar0, 1);
+        mbar_init(mbar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase = 0;   // bit s = parity the next wait on buffer s expects
+
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const DItem it = items[item];
         const DTerm dt = dterms[it.dterm];
@@ -57,16 +140,48 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
         const uint32_t nb = __ldg(ix.term_block_start + dt.term_id + 1) - tb;
         const uint32_t rel_end = min(it.first_rel + static_cast<uint32_t>(kItemBlocks), nb);
         const float* ktab = ix.ktab + static_cast<size_t>(dt.field) * DGPU_KTAB_SIZE;
-        for (uint32_t rel = it.first_rel + warp; rel < rel_end; rel += kDecodeThreads / 32) {
+        // this warp's blocks: rel = first_rel + warp + kDecodeWarps * j; lane j holds the skip row of block j
+        const uint32_t rel0 = it.first_rel + warp;
+        const uint32_t cnt = rel0 < rel_end ? (rel_end - rel0 + kDecodeWarps - 1) / kDecodeWarps : 0u;
+        uint32_t m_off = 0, m_len = 0, m_meta = 0, m_first = 0;
+        if (static_cast<uint32_t>(lane) < cnt) {
+            const uint32_t b = tb + rel0 + kDecodeWarps * lane;
+            m_off = __ldg(ix.off + b);
+            m_len = (__ldg(ix.off + b + 1) - m_off) * 16u;
+            m_meta = __ldg(ix.meta + b);
+            m_first = __ldg(ix.first + b);
+        }
+        auto issue = [&](uint32_t j) {   // bulk copy of block j's payload into buffer j & 1 (lane j has its skip row)
+            if (static_cast<uint32_t>(lane) == j) {
+                const uint32_t s = j & 1u;
+                mbar_expect_tx(mbar0 + 8u * s, m_len);
+                bulk_copy_g2s(buf0 + s * kPayloadBuf, ix.data + static_cast<size_t>(m_off) * 16u, m_len, mbar0 + 8u * s);
+            }
+        };
+        if (cnt > 0) issue(0);
+        if (cnt > 1) issue(1);
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t s = j & 1u;
+            const uint32_t meta = __shfl_sync(0xFFFFFFFFu, m_meta, j);
+            const uint32_t first_doc = __shfl_sync(0xFFFFFFFFu, m_first, j);
+            mbar_wait(mbar0 + 8u * s, (phase >> s) & 1u);
+            phase ^= 1u << s;
             uint32_t doc[4], code[4];
-            const uint32_t n = warp_decode_block(ix, tb + rel, lane, doc, code);
+            const uint32_t n = warp_decode_payload(&s_buf[warp][s][0], meta, first_doc, lane, doc, code);
+            __syncwarp();
+            if (j + 2 < cnt) {
+                // the buffer is free again: order this warp's reads before the async-proxy write that reuses it
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                issue(j + 2);
+            }
             uint32_t ev[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool valid = 4u * lane + j < n;
-                ev[2 * j] = valid ? doc[j] : kDocEnd;
-                ev[2 * j + 1] = valid ? __float_as_uint(bm25_score(dt.idf, ktab, code[j])) : 0u;
+            for (int q = 0; q < 4; ++q) {
+                const bool valid = 4u * lane + q < n;
+                ev[2 * q] = valid ? doc[q] : kDocEnd;
+                ev[2 * q + 1] = valid ? __float_as_uint(bm25_score(dt.idf, ktab, code[q])) : 0u;
             }
+            const uint32_t rel = rel0 + kDecodeWarps * j;
             uint4* o = reinterpret_cast<uint4*>(runs + static_cast<size_t>(dt.out_base) +
                                                 static_cast<size_t>(rel) * DGPU_BLOCK_POSTINGS + 4u * lane);
             o[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
