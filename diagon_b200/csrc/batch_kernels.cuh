@@ -26,6 +26,7 @@ struct DTerm {          // one distinct (term, idf, field) of the batch
     float idf;
     uint32_t field;
     uint32_t out_base;  // first scratch entry of its run (multiple of DGPU_BLOCK_POSTINGS)
+    uint32_t first_block, n_blocks;   // its rows in the skip index
 };
 
 struct DItem {          // up to kItemBlocks consecutive blocks of one distinct term
@@ -94,22 +95,46 @@ __device__ __forceinline__ uint32_t warp_decode_payload(const uint8_t* p, uint32
         ld[j] = ((cd >> (2 * j)) & 3u) + 1u;
         lf[j] = ((cf >> (2 * j)) & 3u) + 1u;
     }
+    const uint32_t flags = meta >> 24;
     const uint32_t tot = (ld[0] + ld[1] + ld[2] + ld[3]) | ((lf[0] + lf[1] + lf[2] + lf[3]) << 16);
-    const uint32_t exc = warp_inclusive_scan(tot, lane) - tot;
+    // blocks whose values are all one byte (dense terms: every doc gap < 256; all freq == 1) skip the offset scan
+    const bool need_scan = (flags & (DGPU_BLK_DOC_U8 | DGPU_BLK_FN_U8)) != (DGPU_BLK_DOC_U8 | DGPU_BLK_FN_U8);
+    const uint32_t exc = need_scan ? warp_inclusive_scan(tot, lane) - tot : 0u;
     uint32_t od = 2u * cb + (exc & 0xFFFFu);
     uint32_t of = 2u * cb + dl + (exc >> 16);
     uint32_t run = 0;
     uint32_t delta[4];
+    if (flags & DGPU_BLK_DOC_U8) {
+        // the lane's four deltas are the four bytes of one aligned word
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(p + 2u * cb + 4u * lane);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t* wd = reinterpret_cast<const uint32_t*>(p + (od & ~3u));
-        const uint32_t v = __funnelshift_r(wd[0], wd[1], (od & 3u) * 8u) & (0xFFFFFFFFu >> (32u - 8u * ld[j]));
-        od += ld[j];
-        run += v;
-        delta[j] = run;
-        const uint32_t* wf = reinterpret_cast<const uint32_t*>(p + (of & ~3u));
-        code[j] = __funnelshift_r(wf[0], wf[1], (of & 3u) * 8u) & (0xFFFFFFFFu >> (32u - 8u * lf[j]));
-        of += lf[j];
+        for (int j = 0; j < 4; ++j) {
+            run += (w >> (8 * j)) & 0xFFu;
+            delta[j] = run;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t* wd = reinterpret_cast<const uint32_t*>(p + (od & ~3u));
+            const uint32_t v = __funnelshift_r(wd[0], wd[1], (od & 3u) * 8u) & (0xFFFFFFFFu >> (32u - 8u * ld[j]));
+            od += ld[j];
+            run += v;
+            delta[j] = run;
+        }
+    }
+    if (flags & DGPU_BLK_FN_U8) {
+        const uint32_t o = 2u * cb + dl + 4u * lane;   // not word aligned in general (dl is a byte count)
+        const uint32_t* wf = reinterpret_cast<const uint32_t*>(p + (o & ~3u));
+        const uint32_t w = __funnelshift_r(wf[0], wf[1], (o & 3u) * 8u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) code[j] = (w >> (8 * j)) & 0xFFu;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t* wf = reinterpret_cast<const uint32_t*>(p + (of & ~3u));
+            code[j] = __funnelshift_r(wf[0], wf[1], (of & 3u) * 8u) & (0xFFFFFFFFu >> (32u - 8u * lf[j]));
+            of += lf[j];
+        }
     }
     const uint32_t base = first_doc + warp_inclusive_scan(run, lane) - run;
 #pragma unroll
@@ -117,7 +142,7 @@ __device__ __forceinline__ uint32_t warp_decode_payload(const uint8_t* p, uint32
     return n;
 }
 
-__global__ void __launch_bounds__(kDecodeThreads)
+__global__ void __launch_bounds__(kDecodeThreads, 4)
 decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DItem* __restrict__ items, uint32_t n_items,
                     uint2* __restrict__ runs) {
     __shared__ __align__(128) uint8_t s_buf[kDecodeWarps][2][kPayloadBuf];
@@ -133,11 +158,17 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
     __syncthreads();
     uint32_t phase = 0;   // bit s = parity the next wait on buffer s expects
 
+    // the header of the next work item is fetched while the current one is decoded
+    DItem it_next = blockIdx.x < n_items ? items[blockIdx.x] : DItem{0u, 0u};
+    DTerm dt_next = blockIdx.x < n_items ? dterms[it_next.dterm] : DTerm{0u, 0.f, 0u, 0u, 0u, 0u};
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const DItem it = items[item];
-        const DTerm dt = dterms[it.dterm];
-        const uint32_t tb = __ldg(ix.term_block_start + dt.term_id);
-        const uint32_t nb = __ldg(ix.term_block_start + dt.term_id + 1) - tb;
+        const DItem it = it_next;
+        const DTerm dt = dt_next;
+        if (item + gridDim.x < n_items) {
+            it_next = items[item + gridDim.x];
+            dt_next = dterms[it_next.dterm];
+        }
+        const uint32_t tb = dt.first_block, nb = dt.n_blocks;
         const uint32_t rel_end = min(it.first_rel + static_cast<uint32_t>(kItemBlocks), nb);
         const float* ktab = ix.ktab + static_cast<size_t>(dt.field) * DGPU_KTAB_SIZE;
         // this warp's blocks: rel = first_rel + warp + kDecodeWarps * j; lane j holds the skip row of block j

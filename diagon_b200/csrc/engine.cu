@@ -144,6 +144,7 @@ struct dgpu_engine {
     int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
     int warps_per_sm = 20;   // independent scoring warps per SM (each owns 1/n of the shared memory)
     int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
+    int decode_ctas_per_sm = 64; // grid of decode_score_kernel (grid-stride over the decode work items)
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
     // stats
@@ -290,6 +291,11 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
     if (!std::strcmp(name, "splits")) {
         if (value < 0 || value > 64) return fail("splits must be in [0, 64]");
         e->force_splits = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "decode_ctas_per_sm")) {
+        if (value < 1 || value > 4096) return fail("decode_ctas_per_sm must be in [1, 4096]");
+        e->decode_ctas_per_sm = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "intersect")) {
@@ -496,7 +502,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
                 slot = static_cast<uint32_t>(dterms.size());
                 te = dgpu_engine::TableEntry{key, slot, qt.field, e->epoch};
                 const uint32_t nb = run.len / DGPU_BLOCK_POSTINGS;
-                dterms.push_back(DTerm{qt.term_id, qt.idf, qt.field, static_cast<uint32_t>(run_entries)});
+                dterms.push_back(DTerm{qt.term_id, qt.idf, qt.field, static_cast<uint32_t>(run_entries), run.pad, nb});
                 for (uint32_t rel = 0; rel < nb; rel += kItemBlocks) items.push_back(DItem{slot, rel});
                 run_entries += (static_cast<uint64_t>(nb) + kPadBlocks) * DGPU_BLOCK_POSTINGS;
                 break;
@@ -695,7 +701,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     CU(cudaMemsetAsync(e->d_counter.p, 0, 8, stream));
     CU(cudaEventRecord(e->ev0, stream));
     if (e->n_ditems) {
-        const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * 8));
+        const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * e->decode_ctas_per_sm));
         decode_score_kernel<<<grid, kDecodeThreads, 0, stream>>>(e->ix, e->d_dterms.p, e->d_items.p, e->n_ditems,
                                                                  e->d_runs.p);
         e->launches++;
