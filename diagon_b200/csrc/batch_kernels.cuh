@@ -253,6 +253,7 @@ struct AccumParams {
     uint32_t cand_cap;          // power of two, >= 2k and >= k + 32
     uint32_t list_cap;          // touched-list capacity (entries)
     uint32_t warp_smem;         // bytes of shared memory owned by one warp (multiple of 16)
+    uint64_t* pool;             // candidate pools in global memory (large k: cand_cap keys per warp), or null: in shared memory
     uint64_t* out_keys;         // [item][k]
     int32_t* out_counts;        // [item]
     int64_t* out_hits;          // [item]
@@ -329,7 +330,12 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
     uint8_t *role, *cnt;
     {
         uint8_t* sp = smem_raw + static_cast<size_t>(warp) * P.warp_smem;
-        cand = reinterpret_cast<uint64_t*>(sp);  sp += sizeof(uint64_t) * P.cand_cap;
+        if (P.pool) {   // a large pool (top-1000) would cost the SM most of its warps: it lives in global memory / L2
+            cand = P.pool + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * P.cand_cap;
+        } else {
+            cand = reinterpret_cast<uint64_t*>(sp);
+            sp += sizeof(uint64_t) * P.cand_cap;
+        }
         srow = reinterpret_cast<uint2*>(sp);     sp += sizeof(uint2) * (static_cast<size_t>(P.max_terms) << chlog);
         acc = reinterpret_cast<float*>(sp);      sp += sizeof(float) * W;
         pos = reinterpret_cast<uint32_t*>(sp);   sp += sizeof(uint32_t) * P.max_terms;
@@ -588,7 +594,8 @@ __global__ void __launch_bounds__(256, 1)
 intersect_topk_kernel(DeviceIndex ix, AccumParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(warp) * P.warp_smem);
+    uint64_t* cand = P.pool ? P.pool + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * P.cand_cap
+                            : reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(warp) * P.warp_smem);
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (;;) {

@@ -126,6 +126,8 @@ struct dgpu_engine {
     DevBuf<uint32_t> d_part_off;
     uint32_t n_witems = 0;
     bool split_any = false;
+    bool plan_pool_global = false;
+    DevBuf<uint64_t> d_pool;
     struct TableEntry {
         uint64_t key;   // term id << 32 | idf bits
         uint32_t slot;
@@ -175,7 +177,9 @@ static int plan_batched(dgpu_engine* e) {
     if (e->stage_log2) chlog = std::min<uint32_t>(chlog, static_cast<uint32_t>(e->stage_log2));
     const uint32_t list_cap = 512;
     const size_t per_doc = e->need_cnt ? 5 : 4;
-    const size_t fixed = accum_warp_smem_bytes(0, cap, max_terms, chlog, list_cap, e->need_cnt);
+    const bool pool_global = cap > 256;   // top-k beyond 128: the pool goes to global memory (pushes are rare once warm)
+    const uint32_t cap_smem = pool_global ? 0u : cap;
+    const size_t fixed = accum_warp_smem_bytes(0, cap_smem, max_terms, chlog, list_cap, e->need_cnt);
     const size_t per_sm = 227 * 1024;
     const size_t optin = static_cast<size_t>(e->max_smem_optin) - 256;
     // warps per SM: the requested number, fewer when a warp's fixed part (large k, many terms) needs the room
@@ -193,7 +197,8 @@ static int plan_batched(dgpu_engine* e) {
             e->plan_W = W;
             e->plan_wpc = wpc;
             e->plan_ctas = ctas;
-            e->plan_warp_smem = static_cast<uint32_t>(accum_warp_smem_bytes(W, cap, max_terms, chlog, list_cap, e->need_cnt));
+            e->plan_pool_global = pool_global;
+            e->plan_warp_smem = static_cast<uint32_t>(accum_warp_smem_bytes(W, cap_smem, max_terms, chlog, list_cap, e->need_cnt));
             e->last_window = W;
             return 0;
         }
@@ -238,7 +243,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     e->d_counter.release(); e->d_keys.release(); e->d_counts.release(); e->d_hits.release();
     e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_runs.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
-    e->d_witems.release(); e->d_part_off.release();
+    e->d_witems.release(); e->d_part_off.release(); e->d_pool.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_a) cudaEventDestroy(e->ev_a);
@@ -539,7 +544,9 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         for (uint32_t q = 0; q < b->n_queries; ++q) total_cost += cost[q];
         const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) * e->plan_ctas * e->plan_wpc;
         const uint64_t target = std::max<uint64_t>(64, total_cost / (n_warps * 4) + 1);   // posting blocks per item
-        const uint32_t cap_parts = e->max_parts ? static_cast<uint32_t>(e->max_parts) : 64u;
+        // every part keeps its own top-k and the merge compares all pairs of parts: large k gets fewer parts
+        const uint32_t cap_parts = e->max_parts ? static_cast<uint32_t>(e->max_parts)
+                                                : std::max(2u, std::min(64u, 4096u / static_cast<uint32_t>(k)));
         witems.reserve(b->n_queries);
         for (uint32_t q = 0; q < b->n_queries; ++q) {
             uint32_t parts = e->force_splits ? static_cast<uint32_t>(e->force_splits)
@@ -692,7 +699,12 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.chlog = e->plan_chlog;
     P.W = e->plan_W;
     P.warp_smem = e->plan_warp_smem;
-    const size_t smem = static_cast<size_t>(e->plan_warp_smem) * e->plan_wpc;
+    P.pool = nullptr;
+    if (e->plan_pool_global) {
+        CU(e->d_pool.ensure(static_cast<size_t>(e->sm_count) * e->plan_ctas * e->plan_wpc * e->plan_cap));
+        P.pool = e->d_pool.p;
+    }
+    const size_t smem = std::max<size_t>(static_cast<size_t>(e->plan_warp_smem) * e->plan_wpc, 16);
     const bool split = e->split_any;
     P.out_keys = split ? e->d_part_keys.p : e->d_keys.p;
     P.out_counts = split ? e->d_part_counts.p : e->d_counts.p;
