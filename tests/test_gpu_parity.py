@@ -261,3 +261,52 @@ def test_sharded_search_and_device_merge_equal_whole(synth):
     finally:
         for p in parts:
             p.close()
+
+
+@pytest.fixture(scope="module")
+def c2_full():
+    """The C2 corpus at BASELINE.json's full size (8,841,823 docs, 392 M postings, 8 segments)."""
+    spec = dg.named_corpus("C2", 1.0)
+    reader = dg.IndexReader.synthetic(spec, 0)
+    yield spec, reader
+    reader.close()
+
+
+def test_full_size_properties(c2_full):
+    """At full C2 size the oracle is too slow to be the checker; size-independent properties are:
+    (1) two independent device implementations (batched kernels vs the per-query fused kernel) agree bit for bit on
+        doc ids, scores and hit counts for OR-10 top-10;
+    (2) inclusion-exclusion: hits(a AND b) + hits(a OR b) == hits(a) + hits(b), which ties the intersection kernel,
+        the accumulate kernel and the decoder together, and hits(TERM t) == the decoded posting count of t;
+    (3) a doc-range split of every query into 7 parts + device merge changes nothing."""
+    spec, reader = c2_full
+    s = dg.IndexSearcher(reader)
+    text = dg.query_log_text("C2", spec.vocab, 300, "OR body 0")
+    a = s.search_batch_text(text, 10)
+    reader.set_option("kernel", 2)
+    try:
+        b = s.search_batch_text(text, 10)
+    finally:
+        reader.set_option("kernel", 3)
+    assert np.array_equal(a.docs, b.docs) and np.array_equal(a.scores, b.scores)
+    assert np.array_equal(a.total_hits, b.total_hits) and np.array_equal(a.counts, b.counts)
+    assert int(a.total_hits.min()) > 0 and int(a.counts.min()) == 10
+
+    reader.set_option("splits", 7)
+    try:
+        c = s.search_batch_text(text, 10)
+    finally:
+        reader.set_option("splits", 0)
+    assert np.array_equal(a.docs, c.docs) and np.array_equal(a.scores, c.scores) and np.array_equal(a.total_hits, c.total_hits)
+
+    pairs = [l.split()[2:] for l in dg.query_log_text("C3-AND2", spec.vocab, 100, "AND body").decode().strip().split("\n")]
+    lines = []
+    for x, y in pairs:
+        lines += [f"AND body {x} {y}", f"OR body 0 {x} {y}", f"TERM body {x}", f"TERM body {y}"]
+    r = s.search_batch_text(("\n".join(lines) + "\n").encode(), 10)
+    h = r.total_hits.reshape(-1, 4)
+    assert np.array_equal(h[:, 0] + h[:, 1], h[:, 2] + h[:, 3])
+    assert int(h[:, 0].sum()) > 0
+    for (x, _), row in list(zip(pairs, h))[:10]:
+        docs, _ = reader.decode_term("body", x.encode())
+        assert len(docs) == row[2]
