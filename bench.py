@@ -69,6 +69,7 @@ def parse_args():
     ap.add_argument("--window-docs", type=int, default=0)
     ap.add_argument("--stage-log2", type=int, default=0)
     ap.add_argument("--decode-ctas-per-sm", type=int, default=0)
+    ap.add_argument("--part-factor", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="3 = batched decode_score + accumulate_topk (default), 2 = fused windows")
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
@@ -328,6 +329,8 @@ def main():
         reader.set_option("stage_log2", args.stage_log2)
     if args.decode_ctas_per_sm:
         reader.set_option("decode_ctas_per_sm", args.decode_ctas_per_sm)
+    if args.part_factor:
+        reader.set_option("part_factor", args.part_factor)
     if args.kernel:
         reader.set_option("kernel", args.kernel)
     if world > 1:

@@ -13,6 +13,16 @@
 
 #include "kernels.cuh"
 
+#include <cassert>
+
+// Bounds checks of our own (compute-sanitizer is not available on the pool): build with EXTRA_NVFLAGS=-DDGPU_CHECK and
+// run the GPU tests; a violated check traps the kernel and surfaces as a launch failure.
+#ifdef DGPU_CHECK
+#define DGPU_ASSERT(cond) assert(cond)
+#else
+#define DGPU_ASSERT(cond) ((void)0)
+#endif
+
 namespace {
 
 constexpr uint32_t kDocEnd = 0xFFFFFFFFu;   // doc id of the padding entries after a run (doc ids are < 2^31)
@@ -185,6 +195,7 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
         auto issue = [&](uint32_t j) {   // bulk copy of block j's payload into buffer j & 1 (lane j has its skip row)
             if (static_cast<uint32_t>(lane) == j) {
                 const uint32_t s = j & 1u;
+                DGPU_ASSERT(m_len > 0 && m_len <= 1088 && (m_len & 15u) == 0);
                 mbar_expect_tx(mbar0 + 8u * s, m_len);
                 bulk_copy_g2s(buf0 + s * kPayloadBuf, ix.data + static_cast<size_t>(m_off) * 16u, m_len, mbar0 + 8u * s);
             }
@@ -213,6 +224,7 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
                 ev[2 * q + 1] = valid ? __float_as_uint(bm25_score(dt.idf, ktab, code[q])) : 0u;
             }
             const uint32_t rel = rel0 + kDecodeWarps * j;
+            DGPU_ASSERT(rel < nb && n <= DGPU_BLOCK_POSTINGS);
             uint4* o = reinterpret_cast<uint4*>(runs + static_cast<size_t>(dt.out_base) +
                                                 static_cast<size_t>(rel) * DGPU_BLOCK_POSTINGS + 4u * lane);
             o[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
@@ -246,6 +258,7 @@ struct AccumParams {
     uint32_t n_items;
     uint32_t* work_counter;
     const uint2* runs;          // (doc, score bits) entries of every distinct term of the batch
+    uint64_t run_total;         // entries allocated in `runs` (bounds checks)
     int k;
     uint32_t W;                 // docs per window (multiple of 32, <= 65536)
     uint32_t chlog;             // log2 of the staged entries per term (1..5)
@@ -363,6 +376,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
     auto apply = [&](bool in, uint32_t r, float s, uint32_t rl) {
         bool first = false;
         if (in) {
+            DGPU_ASSERT(r < W);
             const uint32_t old = acc_bits[r];
             if (NEED_CNT) {
                 const uint8_t c = cnt[r];
@@ -388,6 +402,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
 
     // copy entries [p, p + CH) of a run into term t's row
     auto stage_row = [&](uint32_t t, uint32_t p) {
+        DGPU_ASSERT(t < P.max_terms && static_cast<uint64_t>(p) + CH <= P.run_total);
         if (static_cast<uint32_t>(lane) < CH) cp_async8(srow_s + 8u * sidx(t, lane), P.runs + p + lane);
     };
 
@@ -486,11 +501,13 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                     if (is_dense) {
                         // every staged entry was inside the window: go on with the run in global memory
                         const uint2* gp = P.runs + p + lane;
+                        DGPU_ASSERT(static_cast<uint64_t>(p) + 32 <= P.run_total);
                         uint2 en = __ldg(gp);
                         for (;;) {
                             const bool in = en.x < we;
                             const uint32_t im = __ballot_sync(0xFFFFFFFFu, in);
                             uint2 nx = make_uint2(0u, 0u);
+                            DGPU_ASSERT(static_cast<uint64_t>(gp - P.runs) + 64 <= P.run_total + 32);
                             if (im == 0xFFFFFFFFu) nx = __ldg(gp + 32);   // the run continues inside the window: prefetch
                             apply(in, en.x - ws, __uint_as_float(en.y), rl);
                             p += __popc(im);
@@ -522,6 +539,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                     uint8_t c = 0;
                     if (i < total) {
                         rr = dense_scan ? i : tlist[i];
+                        DGPU_ASSERT(rr < W);
                         bits = acc_bits[rr];
                         acc_bits[rr] = kSentinel;
                         if (NEED_CNT) {
@@ -555,6 +573,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                     if (NEED_CNT || nf) hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
                     const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
                     if (pm) {
+                        DGPU_ASSERT(n_cand + __popc(pm) <= P.cand_cap);
                         if (push) cand[n_cand + __popc(pm & lt_mask)] = key;
                         n_cand += __popc(pm);
                     }
@@ -681,6 +700,7 @@ intersect_topk_kernel(DeviceIndex ix, AccumParams P) {
                             const uint32_t mid = (x + y) >> 1;
                             if (__ldg(&row[mid].x) < d) x = mid + 1; else y = mid;
                         }
+                        DGPU_ASSERT(static_cast<uint64_t>(row - P.runs) + DGPU_BLOCK_POSTINGS <= P.run_total);
                         if (x < DGPU_BLOCK_POSTINGS) {
                             const uint2 hit = __ldg(row + x);
                             found = hit.x == d;

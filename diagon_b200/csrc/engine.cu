@@ -146,6 +146,7 @@ struct dgpu_engine {
     int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
     int warps_per_sm = 20;   // independent scoring warps per SM (each owns 1/n of the shared memory)
     int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
+    int part_factor = 2;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
     int decode_ctas_per_sm = 64; // grid of decode_score_kernel (grid-stride over the decode work items)
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
@@ -296,6 +297,11 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
     if (!std::strcmp(name, "splits")) {
         if (value < 0 || value > 64) return fail("splits must be in [0, 64]");
         e->force_splits = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "part_factor")) {
+        if (value < 1 || value > 64) return fail("part_factor must be in [1, 64]");
+        e->part_factor = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "decode_ctas_per_sm")) {
@@ -543,7 +549,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         uint64_t total_cost = 0;
         for (uint32_t q = 0; q < b->n_queries; ++q) total_cost += cost[q];
         const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) * e->plan_ctas * e->plan_wpc;
-        const uint64_t target = std::max<uint64_t>(64, total_cost / (n_warps * 4) + 1);   // posting blocks per item
+        const uint64_t target = std::max<uint64_t>(64, total_cost / (n_warps * static_cast<uint64_t>(e->part_factor)) + 1);   // posting blocks per item
         // every part keeps its own top-k and the merge compares all pairs of parts: large k gets fewer parts
         const uint32_t cap_parts = e->max_parts ? static_cast<uint32_t>(e->max_parts)
                                                 : std::max(2u, std::min(64u, 4096u / static_cast<uint32_t>(k)));
@@ -692,6 +698,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.n_items = e->n_acc_items;
     P.work_counter = e->d_counter.p;
     P.runs = e->d_runs.p;
+    P.run_total = e->d_runs.cap;
     P.k = e->k;
     P.max_terms = (e->max_terms + 3u) & ~3u;
     P.cand_cap = e->plan_cap;
