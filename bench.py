@@ -183,6 +183,8 @@ def reference_arm(args, corpus_name, log_name, kind, k, steps, warmup, full):
             probe_docs = min(spec.num_docs, 50000)
             rate = probe_docs / max(build(os.path.join(tmp, "probe"), probe_docs, 1), 1e-3)
             docs = min(spec.num_docs, max(probe_docs, int(rate * budget) // 1000 * 1000))
+            if docs >= 0.85 * spec.num_docs:   # close enough: index the whole corpus, so the two arms run the same config
+                docs = spec.num_docs
             segments = spec.num_segments if docs == spec.num_docs else 1
             root = os.path.join(tempfile.gettempdir(), "dgpu_ref_cache")
             prefix = f"{corpus_name}_{args.scale}_"
