@@ -292,6 +292,8 @@ def main():
         emit(line)
         return 0
 
+    # one process per GPU: the host worker pools of the ranks share the box's cores instead of oversubscribing them
+    os.environ.setdefault("DGPU_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
     import ctypes as C
 
     import numpy as np

@@ -582,15 +582,22 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->n_acc_items = n_items;
     e->n_and_items = 0;
     if (e->kernel == 3) {
-        auto mid = std::stable_partition(order.begin(), order.end(), [&](uint32_t a) { return !is_and[witems[a].query]; });
-        e->n_acc_items = static_cast<uint32_t>(mid - order.begin());
-        e->n_and_items = n_items - e->n_acc_items;
-        std::stable_sort(order.begin(), mid, [&](uint32_t a, uint32_t c) { return item_cost[a] > item_cost[c]; });
-        std::stable_sort(mid, order.end(), [&](uint32_t a, uint32_t c) { return item_cost[a] > item_cost[c]; });
+        // one sort of packed keys: class (accumulate first), cost descending, item id ascending
+        std::vector<uint64_t> keys(n_items);
+        uint32_t n_and = 0;
+        for (uint32_t i = 0; i < n_items; ++i) {
+            const uint64_t cls = is_and[witems[i].query];
+            n_and += static_cast<uint32_t>(cls);
+            const uint64_t c = std::min<uint64_t>(item_cost[i], 0x7FFFFFFFull);
+            keys[i] = (cls << 63) | ((0x7FFFFFFFull - c) << 32) | i;
+        }
+        std::sort(keys.begin(), keys.end());
+        for (uint32_t i = 0; i < n_items; ++i) order[i] = static_cast<uint32_t>(keys[i]);
+        e->n_and_items = n_and;
+        e->n_acc_items = n_items - n_and;
     } else {
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
     }
-
     lap("order");
     CU(e->d_queries.ensure(b->n_queries));
     CU(e->d_terms.ensure(b->n_terms));

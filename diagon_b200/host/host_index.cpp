@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <condition_variable>
@@ -15,10 +16,18 @@
 namespace dgpu {
 
 // ------------------------------------------------------------------ helpers
+// Host threads of the worker pool: DGPU_HOST_THREADS when set (one process per GPU should divide the cores between
+// the ranks), else every hardware thread up to 64.
 static int default_threads(int threads) {
     if (threads > 0) return threads;
-    unsigned hc = std::thread::hardware_concurrency();
-    return static_cast<int>(std::max(1u, std::min(hc, 64u)));
+    static const int configured = [] {
+        const char* env = std::getenv("DGPU_HOST_THREADS");
+        const int n = env ? std::atoi(env) : 0;
+        if (n > 0) return std::min(n, 64);
+        const unsigned hc = std::thread::hardware_concurrency();
+        return static_cast<int>(std::max(1u, std::min(hc, 64u)));
+    }();
+    return configured;
 }
 
 // A persistent pool: query batches call parallel_for several times per batch and thread creation would cost more
