@@ -11,7 +11,7 @@ CXXFLAGS := -std=c++20 -O2 -fPIC -Wall -Wextra -ffp-contract=off -fno-fast-math 
 OUT      := diagon_b200/libdiagon_b200.so
 BUILD    := build
 
-HOST_SRCS := diagon_b200/host/host_index.cpp diagon_b200/host/search.cpp diagon_b200/host/c_api.cpp
+HOST_SRCS := diagon_b200/host/host_index.cpp diagon_b200/host/segment_reader.cpp diagon_b200/host/search.cpp diagon_b200/host/c_api.cpp
 HOST_OBJS := $(patsubst diagon_b200/host/%.cpp,$(BUILD)/%.o,$(HOST_SRCS))
 HOST_HDRS := $(wildcard diagon_b200/host/*.h) $(wildcard include/*.h)
 

@@ -231,6 +231,14 @@ class IndexReader:
         return cls(_lib.load().dgpu_open_dump(str(path).encode(), device, seg_lo, seg_hi))
 
     @classmethod
+    def open(cls, path: str, device: int = 0, seg_lo: int = 0, seg_hi: int = -1):
+        """An index directory written by the reference (segments_N + Diagon104 files), read natively."""
+        return cls(_lib.load().dgpu_open_index(str(path).encode(), device, seg_lo, seg_hi))
+
+    def image_hash(self) -> int:
+        return int(_lib.load().dgpu_reader_image_hash(self._ptr))
+
+    @classmethod
     def synthetic(cls, spec: "_lib.CorpusSpec", device: int = 0, seg_lo: int = 0, seg_hi: int = -1):
         return cls(_lib.load().dgpu_open_synthetic(C.byref(spec), device, seg_lo, seg_hi))
 

@@ -117,6 +117,10 @@ private:
 // DirectoryReader). Segments [seg_lo, seg_hi) are local, the others contribute statistics only.
 std::shared_ptr<HostIndex> load_dump(const std::string& path, int seg_lo = 0, int seg_hi = -1, int threads = 0);
 
+// Opens an index directory written by the reference (segments_N + Diagon104 codec files, compound or not) natively:
+// host/segment_reader.cpp. Segments [seg_lo, seg_hi) are local, the others contribute statistics only.
+std::shared_ptr<HostIndex> load_index_directory(const std::string& dir, int seg_lo = 0, int seg_hi = -1, int threads = 0);
+
 // Builds the postings of a synthetic corpus directly (no text, no reference indexer). Documents of
 // segments [seg_lo, seg_hi) are generated and encoded; df/ttf of the local range are returned in the
 // HostIndex and must be completed with set_global_stats / add_remote_doc_freq when other ranks hold

@@ -91,6 +91,18 @@ DiagonIndexReader dgpu_builder_finish(DgpuIndexBuilder b, int device);
  * [seg_lo, seg_hi) are uploaded, the rest contribute statistics (seg_hi < 0: all). */
 DiagonIndexReader dgpu_open_dump(const char* path, int device, int seg_lo, int seg_hi);
 
+/* Opens an index directory written by the reference's IndexWriter natively (segments_N, Diagon104 codec files,
+ * compound or plain): what DirectoryReader::open(MMapDirectory) + the upload walk of INTEGRATION.md §2 would
+ * produce, without linking the reference (replaces src/index/SegmentInfo.cpp:281-438,
+ * src/store/CompoundDirectory.cpp:168-214, src/codecs/blocktree/BlockTreeTermsReader.cpp:198-560,
+ * src/codecs/lucene104/Lucene104PostingsReader.cpp:27-77,:391-420, src/util/BitPacking.cpp:171-202,
+ * src/codecs/lucene104/Lucene104NormsReader.cpp:88-161, src/codecs/NumericDocValuesReader.cpp:25-118 on the open
+ * path). Segments [seg_lo, seg_hi) are uploaded, the rest contribute statistics (seg_hi < 0: all). */
+DiagonIndexReader dgpu_open_index(const char* path, int device, int seg_lo, int seg_hi);
+/* FNV-1a of everything dgpu_engine_upload receives plus the per-term statistics: two readers with the same hash
+ * answer every query identically. */
+uint64_t dgpu_reader_image_hash(DiagonIndexReader reader);
+
 /* Synthetic corpora of BASELINE.json, built without text or indexer. */
 typedef struct {
     uint64_t seed;
