@@ -35,6 +35,10 @@ PROTOTYPES = {
     # ---- include/diagon_b200_c_api.h, part 1 (mirrors diagon_c_api.h)
     "diagon_last_error": (C.c_char_p, []),
     "diagon_clear_error": (None, []),
+    "diagon_open_fs_directory": (C.c_void_p, [C.c_char_p]),
+    "diagon_open_mmap_directory": (C.c_void_p, [C.c_char_p]),
+    "diagon_close_directory": (None, [C.c_void_p]),
+    "diagon_open_index_reader": (C.c_void_p, [C.c_void_p]),
     "diagon_reader_num_docs": (C.c_int64, [C.c_void_p]),
     "diagon_reader_max_doc": (C.c_int64, [C.c_void_p]),
     "diagon_reader_get_segment_count": (C.c_int, [C.c_void_p]),

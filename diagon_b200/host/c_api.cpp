@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <limits>
 #include <sstream>
 #include <string>
@@ -140,6 +141,29 @@ extern "C" {
 // ------------------------------------------------------------------ Part 1
 const char* diagon_last_error(void) { return g_last_error.c_str(); }
 void diagon_clear_error(void) { g_last_error.clear(); }
+
+// Directory handles: the path is all the GPU engine needs (the files are memory-mapped while the index is read).
+DiagonDirectory diagon_open_fs_directory(const char* path) {
+    if (!path) { set_error("Invalid path"); return nullptr; }
+    try {
+        if (!std::filesystem::is_directory(path)) { set_error(std::string("Not a directory: ") + path); return nullptr; }
+        return new std::string(path);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+DiagonDirectory diagon_open_mmap_directory(const char* path) { return diagon_open_fs_directory(path); }
+void diagon_close_directory(DiagonDirectory dir) { delete static_cast<std::string*>(dir); }
+
+// The reader is device-resident: the whole directory is parsed (host/segment_reader.cpp) and uploaded to the GPU named
+// by the DGPU_DEVICE environment variable (default 0). Like the reference's reader it does not need the directory
+// handle afterwards.
+DiagonIndexReader diagon_open_index_reader(DiagonDirectory dir) {
+    if (!dir) { set_error("Invalid directory"); return nullptr; }
+    try {
+        const char* env = std::getenv("DGPU_DEVICE");
+        const int device = env ? std::atoi(env) : 0;
+        return new IndexReader(load_index_directory(*static_cast<std::string*>(dir)), device);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
 
 int64_t diagon_reader_num_docs(DiagonIndexReader reader) {
     if (!reader) { set_error("Invalid reader"); return -1; }

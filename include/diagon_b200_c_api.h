@@ -22,6 +22,7 @@
 extern "C" {
 #endif
 
+typedef void* DiagonDirectory;
 typedef void* DiagonIndexReader;
 typedef void* DiagonIndexSearcher;
 typedef void* DiagonQuery;
@@ -32,6 +33,15 @@ typedef void* DiagonTerm;
 /* ------------------------------------------------------------------ Part 1: mirrored entry points */
 const char* diagon_last_error(void);                                   /* diagon_c_api.h:48 */
 void diagon_clear_error(void);                                         /* :53 */
+
+/* Opening an index the way a caller of the reference does. The directory handle only carries the path; the reader
+ * is DEVICE-RESIDENT: diagon_open_index_reader parses the whole directory natively (segments_N, Diagon104 files) and
+ * uploads it to the GPU named by the DGPU_DEVICE environment variable (default 0). Fails (NULL + diagon_last_error)
+ * without a CUDA device: there is no CPU fallback. */
+DiagonDirectory diagon_open_fs_directory(const char* path);            /* diagon_c_api.h:62 */
+DiagonDirectory diagon_open_mmap_directory(const char* path);          /* :69 */
+void diagon_close_directory(DiagonDirectory dir);                      /* :74 */
+DiagonIndexReader diagon_open_index_reader(DiagonDirectory dir);       /* :321 */
 
 int64_t diagon_reader_num_docs(DiagonIndexReader reader);              /* :328 */
 int64_t diagon_reader_max_doc(DiagonIndexReader reader);               /* :335 */

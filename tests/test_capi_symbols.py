@@ -40,7 +40,8 @@ def test_reference_bridge_names_are_mirrored():
     diagon_bool_query_set_minimum_should_match diagon_bool_query_build diagon_free_query
     diagon_free_bool_query_builder diagon_top_docs_total_hits diagon_top_docs_max_score
     diagon_top_docs_score_docs_length diagon_top_docs_score_doc_at diagon_score_doc_get_doc
-    diagon_score_doc_get_score diagon_free_top_docs diagon_reader_max_doc diagon_close_index_reader""".split()
+    diagon_score_doc_get_score diagon_free_top_docs diagon_reader_max_doc diagon_close_index_reader
+    diagon_open_fs_directory diagon_open_mmap_directory diagon_close_directory diagon_open_index_reader""".split()
     have = declared("diagon_b200_c_api.h")
     assert not [w for w in want if w not in have]
 

@@ -112,3 +112,35 @@ def test_search_over_a_natively_opened_index_matches_the_reference(golden_dir):
         assert td.totalHits.value > 0
     finally:
         reader.close()
+
+
+@pytest.mark.gpu
+def test_reference_bridge_open_sequence(golden_dir):
+    """The unchanged call sequence of a CGO caller: diagon_open_mmap_directory -> diagon_open_index_reader ->
+    diagon_create_index_searcher -> diagon_search (diagon_c_api.h:69, :321, :349, :358)."""
+    from diagon_b200 import _lib
+
+    lib = _lib.load()
+    d = lib.diagon_open_mmap_directory(os.path.join(golden_dir, "idx_g1").encode())
+    assert d
+    r = lib.diagon_open_index_reader(d)
+    assert r, _lib.last_error()
+    lib.diagon_close_directory(d)                      # the reader does not need the handle any more
+    try:
+        assert lib.diagon_reader_max_doc(r) == 4421 and lib.diagon_reader_get_segment_count(r) == 3
+        s = lib.diagon_create_index_searcher(r)
+        term = lib.diagon_create_term(b"body", b"t0000001")
+        q = lib.diagon_create_term_query(term)
+        td = lib.diagon_search(s, q, 10)
+        assert td and lib.diagon_top_docs_total_hits(td) == 4410
+        assert lib.diagon_top_docs_score_docs_length(td) == 10
+        sd = lib.diagon_top_docs_score_doc_at(td, 0)
+        assert lib.diagon_score_doc_get_doc(sd) == 1869
+        lib.diagon_free_top_docs(td)
+        lib.diagon_free_query(q)
+        lib.diagon_free_term(term)
+        lib.diagon_free_index_searcher(s)
+    finally:
+        lib.diagon_close_index_reader(r)
+    assert not lib.diagon_open_index_reader(None)
+    assert not lib.diagon_open_fs_directory(os.path.join(golden_dir, "no-such-dir").encode())
