@@ -310,3 +310,40 @@ def test_full_size_properties(c2_full):
     for (x, _), row in list(zip(pairs, h))[:10]:
         docs, _ = reader.decode_term("body", x.encode())
         assert len(docs) == row[2]
+
+
+def test_wide_queries_and_empty_inputs(readers, g1_dump):
+    """Shapes at the edges of the kernels: disjunctions of 100 / 400 terms (the staged rows shrink from 32 to 16 and 4
+    entries per term), a conjunction of 40 terms (more than the 32 the intersection kernel takes: counted in the
+    windows), minimumNumberShouldMatch over 60 terms, a query whose terms are all absent next to normal ones, an
+    empty batch."""
+    import random
+
+    ox = orc.OracleIndex(g1_dump)
+    searcher = dg.IndexSearcher(readers["g1"])
+    rnd = random.Random(7)
+    terms = ["t%07d" % r for r in range(1, 1001)]
+    lines = [
+        "OR body 0 " + " ".join(rnd.sample(terms, 100)),
+        "OR body 0 " + " ".join(rnd.sample(terms, 400)),
+        "AND body " + " ".join(terms[:40]),
+        "AND body " + " ".join(terms[:6] + terms[10:40]),
+        "OR body 5 " + " ".join(rnd.sample(terms[:200], 60)),
+        "OR body 0 t9999990 t9999991",
+        "TERM body t0000003",
+        "ANDNOT body 2 t0000001 t0000002 " + " ".join(rnd.sample(terms[100:], 45)),
+    ]
+    for k in (10, 1000):
+        res = searcher.search_batch_text(("\n".join(lines) + "\n").encode(), k)
+        for q, line in enumerate(lines):
+            h, sd, _ = ox.search(api.parse_line(line), k)
+            got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
+            assert_same_topdocs(int(res.total_hits[q]), got, h, sd, line[:60])
+    # one at a time too: each query plans its own staging depth
+    for line in lines[:5]:
+        td = searcher.search(api.parse_line(line), 10)
+        h, sd, _ = ox.search(api.parse_line(line), 10)
+        assert_same_topdocs(td.totalHits.value, [(s.doc, s.score) for s in td.scoreDocs], h, sd, line[:60])
+    empty = searcher.search_batch_text(b"", 10)
+    assert len(empty.counts) == 0
+    assert len(searcher.search_batch([], 10).counts) == 0
