@@ -419,6 +419,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     std::vector<uint64_t> cost(b->n_queries, 0);
     std::vector<uint64_t> lead_cost(b->n_queries, ~0ull);   // blocks of the shortest list (what an intersection walks)
     std::vector<uint8_t> is_and(b->n_queries, 0);
+    std::vector<uint32_t> heavy_term(b->n_queries, 0);      // the query's longest list: what it streams most of
     std::vector<QTermRun> qruns(b->n_terms);
     const int n_threads = b->n_queries < 1024 ? 1 : 0;      // 0 = every host thread
     struct Partial {
@@ -448,6 +449,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
                 if (qd.n_must > 1 || qd.min_should_match > 1) pt.need_cnt = true;
             }
             uint64_t c = 0, lead = ~0ull;
+            uint32_t heavy_nb = 0;
             for (uint32_t t = qd.term_begin; t < qd.term_end; ++t) {
                 const dgpu_qterm& qt = b->terms[t];
                 if (qt.role == DGPU_ROLE_MUST_NOT) pt.need_cnt = true;
@@ -459,6 +461,10 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
                     const uint32_t nb = e->h_term_block_start[qt.term_id + 1] - tb;
                     c += nb;
                     lead = std::min<uint64_t>(lead, nb);
+                    if (nb > heavy_nb) {
+                        heavy_nb = nb;
+                        heavy_term[q] = qt.term_id;
+                    }
                     run.pad = tb;
                     run.len = nb * DGPU_BLOCK_POSTINGS;
                 } else {
@@ -582,17 +588,27 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->n_acc_items = n_items;
     e->n_and_items = 0;
     if (e->kernel == 3) {
-        // one sort of packed keys: class (accumulate first), cost descending, item id ascending
-        std::vector<uint64_t> keys(n_items);
+        // one sort of packed keys: class (accumulate first); cost class descending (powers of two: long items
+        // start first); inside a cost class the items that stream the same long list are neighbours, so the warps
+        // working on them at the same time share its run in L2; doc range; item id
+        struct Key {
+            uint64_t hi, lo;
+            bool operator<(const Key& o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
+        };
+        std::vector<Key> keys(n_items);
         uint32_t n_and = 0;
         for (uint32_t i = 0; i < n_items; ++i) {
-            const uint64_t cls = is_and[witems[i].query];
+            const uint32_t q = witems[i].query;
+            const uint64_t cls = is_and[q];
             n_and += static_cast<uint32_t>(cls);
-            const uint64_t c = std::min<uint64_t>(item_cost[i], 0x7FFFFFFFull);
-            keys[i] = (cls << 63) | ((0x7FFFFFFFull - c) << 32) | i;
+            const uint64_t c = std::max<uint64_t>(1, item_cost[i]);
+            const uint64_t lg = 63 - static_cast<uint64_t>(__builtin_clzll(c));
+            const uint64_t cost_class = lg;      // 0..63
+            keys[i].hi = (cls << 63) | ((127 - cost_class) << 40) | (static_cast<uint64_t>(heavy_term[q]) << 8);
+            keys[i].lo = (static_cast<uint64_t>(witems[i].doc_lo) << 32) | i;
         }
         std::sort(keys.begin(), keys.end());
-        for (uint32_t i = 0; i < n_items; ++i) order[i] = static_cast<uint32_t>(keys[i]);
+        for (uint32_t i = 0; i < n_items; ++i) order[i] = static_cast<uint32_t>(keys[i].lo);
         e->n_and_items = n_and;
         e->n_acc_items = n_items - n_and;
     } else {
