@@ -56,13 +56,14 @@ struct QTermRun {       // one query term, resolved to its run in the scratch
 //
 // The compressed payload of a block (16-byte aligned, <= 1088 bytes) is brought into shared memory by ONE bulk
 // asynchronous copy (cp.async.bulk, the 1-D TMA path) issued by one lane and signalled on an mbarrier; every warp
-// keeps two buffers in flight, so the copy of block j + 2 overlaps the decode of block j and no lane ever waits on a
+// keeps kDecodeStages buffers in flight, so the copies of the next blocks overlap the decode of block j and no lane ever waits on a
 // dependent chain of global loads (skip row -> control bytes -> data bytes). Decode works on the shared-memory copy:
 // 2-bit controls -> lengths -> warp scan -> unaligned 32-bit loads, warp scan of the doc deltas. Each lane owns 4
 // postings and writes them as two 128-bit stores of (doc, score) entries. kPadBlocks blocks after the last one of a
 // term are filled with kDocEnd so that readers never need an end-of-run check.
 // ------------------------------------------------------------------------------------------------
 constexpr int kDecodeWarps = kDecodeThreads / 32;
+constexpr int kDecodeStages = 2;    // payload buffers per warp: copies of blocks j+1 .. j+kDecodeStages-1 fly while j decodes
 constexpr int kPayloadBuf = 1152;   // >= the largest payload (64 control + 2 * 512 data bytes) + slack for 8-byte reads
 
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
@@ -155,14 +156,13 @@ __device__ __forceinline__ uint32_t warp_decode_payload(const uint8_t* p, uint32
 __global__ void __launch_bounds__(kDecodeThreads, 4)
 decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DItem* __restrict__ items, uint32_t n_items,
                     uint2* __restrict__ runs) {
-    __shared__ __align__(128) uint8_t s_buf[kDecodeWarps][2][kPayloadBuf];
-    __shared__ __align__(8) uint64_t s_mbar[kDecodeWarps][2];
+    __shared__ __align__(128) uint8_t s_buf[kDecodeWarps][kDecodeStages][kPayloadBuf];
+    __shared__ __align__(8) uint64_t s_mbar[kDecodeWarps][kDecodeStages];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(&s_mbar[warp][0]));
     const uint32_t buf0 = static_cast<uint32_t>(__cvta_generic_to_shared(&s_buf[warp][0][0]));
     if (lane == 0) {
-        mbar_init(mbar0, 1);
-        mbar_init(mbar0 + 8, 1);
+        for (int st = 0; st < kDecodeStages; ++st) mbar_init(mbar0 + 8u * st, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -192,18 +192,17 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
             m_meta = __ldg(ix.meta + b);
             m_first = __ldg(ix.first + b);
         }
-        auto issue = [&](uint32_t j) {   // bulk copy of block j's payload into buffer j & 1 (lane j has its skip row)
+        auto issue = [&](uint32_t j) {   // bulk copy of block j's payload into buffer j % stages (lane j has its skip row)
             if (static_cast<uint32_t>(lane) == j) {
-                const uint32_t s = j & 1u;
+                const uint32_t s = j % kDecodeStages;
                 DGPU_ASSERT(m_len > 0 && m_len <= 1088 && (m_len & 15u) == 0);
                 mbar_expect_tx(mbar0 + 8u * s, m_len);
                 bulk_copy_g2s(buf0 + s * kPayloadBuf, ix.data + static_cast<size_t>(m_off) * 16u, m_len, mbar0 + 8u * s);
             }
         };
-        if (cnt > 0) issue(0);
-        if (cnt > 1) issue(1);
+        for (uint32_t j = 0; j < cnt && j < static_cast<uint32_t>(kDecodeStages); ++j) issue(j);
         for (uint32_t j = 0; j < cnt; ++j) {
-            const uint32_t s = j & 1u;
+            const uint32_t s = j % kDecodeStages;
             const uint32_t meta = __shfl_sync(0xFFFFFFFFu, m_meta, j);
             const uint32_t first_doc = __shfl_sync(0xFFFFFFFFu, m_first, j);
             mbar_wait(mbar0 + 8u * s, (phase >> s) & 1u);
@@ -211,10 +210,10 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
             uint32_t doc[4], code[4];
             const uint32_t n = warp_decode_payload(&s_buf[warp][s][0], meta, first_doc, lane, doc, code);
             __syncwarp();
-            if (j + 2 < cnt) {
+            if (j + kDecodeStages < cnt) {
                 // the buffer is free again: order this warp's reads before the async-proxy write that reuses it
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                issue(j + 2);
+                issue(j + kDecodeStages);
             }
             uint32_t ev[8];
 #pragma unroll
