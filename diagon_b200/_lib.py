@@ -95,6 +95,8 @@ PROTOTYPES = {
     "dgpu_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dgpu_search_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "dgpu_stage_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "dgpu_compile_batch_text": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "dgpu_stage_compiled": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     "dgpu_create_long_range_query": (C.c_void_p, [C.c_char_p, C.c_int64, C.c_int64, C.c_bool, C.c_bool]),
     "dgpu_parse_query": (C.c_void_p, [C.c_char_p]),
     # ---- include/dgpu_engine.h

@@ -446,6 +446,27 @@ class IndexSearcher:
             raise DiagonError(_lib.last_error())
         return {"queries": int(stats[0]), "algorithmic_bytes": int(stats[1]), "postings": int(stats[2])} if want_stats else {"queries": r}
 
+    def compile_batch_text(self, text: bytes) -> np.ndarray:
+        """Host-only: parse + compile a (slice of a) batch into a relocatable blob (uint8 array)."""
+        lib = _lib.load()
+        need = lib.dgpu_compile_batch_text(self._ptr, text, len(text), None, 0)
+        if need < 0:
+            raise DiagonError(_lib.last_error())
+        out = np.zeros(need, dtype=np.uint8)
+        if lib.dgpu_compile_batch_text(self._ptr, text, len(text), out.ctypes.data, need) != need:
+            raise DiagonError(_lib.last_error())
+        return out
+
+    def stage_compiled(self, blobs: Sequence[np.ndarray], k: int) -> int:
+        """Stages the concatenation of compiled blobs (e.g. one per rank, in rank order) on this reader's device."""
+        n = len(blobs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in blobs])
+        sizes = (C.c_int64 * n)(*[b.size for b in blobs])
+        r = _lib.load().dgpu_stage_compiled(self._ptr, ptrs, sizes, n, k)
+        if r < 0:
+            raise DiagonError(_lib.last_error())
+        return r
+
     def close(self):
         if self._ptr:
             _lib.load().diagon_free_index_searcher(self._ptr)

@@ -587,6 +587,76 @@ int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
 
+// A compiled batch as a relocatable blob: header {magic, n_queries, n_terms, n_filters} + the three descriptor arrays
+// with offsets local to the blob. Ranks of a sharded index compile disjoint slices of a batch and exchange the blobs;
+// every descriptor only depends on GLOBAL statistics, so it is the same whichever rank compiles it.
+int64_t dgpu_compile_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, uint8_t* out,
+                                int64_t capacity) {
+    if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
+    try {
+        auto parsed = parse_batch(text, text_len);
+        std::vector<const Query*> qs;
+        qs.reserve(parsed.size());
+        for (auto& q : parsed) qs.push_back(q.get());
+        CompiledBatch batch;
+        compile_all(*as_searcher(searcher), qs, batch);
+        const uint32_t hdr[4] = {0x42504744u /* "DGPB" */, static_cast<uint32_t>(batch.queries.size()),
+                                 static_cast<uint32_t>(batch.terms.size()), static_cast<uint32_t>(batch.filters.size())};
+        const size_t nq = batch.queries.size() * sizeof(dgpu_query), nt = batch.terms.size() * sizeof(dgpu_qterm),
+                     nf = batch.filters.size() * sizeof(dgpu_qfilter);
+        const int64_t need = static_cast<int64_t>(sizeof hdr + nq + nt + nf);
+        if (out && capacity >= need) {
+            uint8_t* p = out;
+            std::memcpy(p, hdr, sizeof hdr); p += sizeof hdr;
+            std::memcpy(p, batch.queries.data(), nq); p += nq;
+            std::memcpy(p, batch.terms.data(), nt); p += nt;
+            std::memcpy(p, batch.filters.data(), nf);
+        }
+        return need;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+int dgpu_stage_compiled(DiagonIndexSearcher searcher, const uint8_t* const* blobs, const int64_t* sizes, int32_t n_blobs,
+                        int32_t k) {
+    if (!searcher || !blobs || !sizes) { set_error("Invalid arguments"); return -1; }
+    try {
+        CompiledBatch batch;
+        for (int32_t i = 0; i < n_blobs; ++i) {
+            uint32_t hdr[4];
+            if (sizes[i] < static_cast<int64_t>(sizeof hdr)) { set_error("compiled batch: truncated blob"); return -1; }
+            std::memcpy(hdr, blobs[i], sizeof hdr);
+            const size_t nq = hdr[1] * sizeof(dgpu_query), nt = hdr[2] * sizeof(dgpu_qterm), nf = hdr[3] * sizeof(dgpu_qfilter);
+            if (hdr[0] != 0x42504744u || sizes[i] < static_cast<int64_t>(sizeof hdr + nq + nt + nf)) {
+                set_error("compiled batch: bad blob");
+                return -1;
+            }
+            const uint8_t* p = blobs[i] + sizeof hdr;
+            const uint32_t toff = static_cast<uint32_t>(batch.terms.size()), foff = static_cast<uint32_t>(batch.filters.size());
+            const size_t q0 = batch.queries.size();
+            batch.queries.resize(q0 + hdr[1]);
+            std::memcpy(batch.queries.data() + q0, p, nq); p += nq;
+            for (size_t q = q0; q < batch.queries.size(); ++q) {
+                dgpu_query& d = batch.queries[q];
+                if (d.term_begin > d.term_end || d.term_end > hdr[2] || d.filter_begin > d.filter_end || d.filter_end > hdr[3]) {
+                    set_error("compiled batch: bad slice");
+                    return -1;
+                }
+                d.term_begin += toff; d.term_end += toff;
+                d.filter_begin += foff; d.filter_end += foff;
+            }
+            batch.terms.resize(toff + hdr[2]);
+            std::memcpy(batch.terms.data() + toff, p, nt); p += nt;
+            batch.filters.resize(foff + hdr[3]);
+            std::memcpy(batch.filters.data() + foff, p, nf);
+        }
+        dgpu_query_batch view = batch.view();
+        auto* rd = &as_searcher(searcher)->getIndexReader();
+        if (!rd->engine()) { set_error("host-only reader: no GPU engine, and there is no CPU fallback"); return -1; }
+        if (dgpu_engine_stage_batch(rd->engine(), &view, k) != 0) { set_error(dgpu_engine_last_error()); return -1; }
+        return static_cast<int>(batch.queries.size());
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
 DiagonQuery dgpu_parse_query(const char* line) {
     if (!line) { set_error("Invalid line"); return nullptr; }
     try {

@@ -161,6 +161,14 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
  * out_stats: [0] queries, [1] algorithmic posting bytes of the batch, [2] postings of the batch. */
 int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats);
 
+/* Sharded indexes: the host work of a batch can be divided between the ranks. dgpu_compile_batch_text parses and
+ * compiles a slice of a batch into a relocatable blob WITHOUT touching the device (returns the bytes needed; writes
+ * them when `capacity` suffices; every descriptor depends on global statistics only, so any rank may compile any
+ * query); after exchanging the blobs (one all-gather), dgpu_stage_compiled concatenates them in the order given and
+ * stages the whole batch on this rank's device (returns the number of queries). */
+int64_t dgpu_compile_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, uint8_t* out, int64_t capacity);
+int dgpu_stage_compiled(DiagonIndexSearcher searcher, const uint8_t* const* blobs, const int64_t* sizes, int32_t n_blobs, int32_t k);
+
 DiagonQuery dgpu_create_long_range_query(const char* field, int64_t lower, int64_t upper, bool include_lower, bool include_upper);
 DiagonQuery dgpu_parse_query(const char* line);
 

@@ -347,3 +347,31 @@ def test_wide_queries_and_empty_inputs(readers, g1_dump):
     empty = searcher.search_batch_text(b"", 10)
     assert len(empty.counts) == 0
     assert len(searcher.search_batch([], 10).counts) == 0
+
+
+def test_staging_compiled_slices_equals_one_call(readers, golden_dir):
+    """dgpu_compile_batch_text on slices + dgpu_stage_compiled (how the ranks of a sharded index divide the host work)
+    gives the same results as dgpu_search_batch_text on the whole batch."""
+    import ctypes as C
+
+    from diagon_b200 import _lib
+
+    r = readers["g1"]
+    s = dg.IndexSearcher(r)
+    lines = read_lines(os.path.join(golden_dir, "g1_queries.txt"))
+    k = 10
+    want = s.search_batch_text(("\n".join(lines) + "\n").encode(), k)
+    cuts = [0, 17, 18, 120, len(lines)]
+    blobs = [s.compile_batch_text(("\n".join(lines[a:b]) + "\n").encode()) for a, b in zip(cuts, cuts[1:])]
+    assert s.stage_compiled(blobs, k) == len(lines)
+    lib = _lib.load()
+    assert lib.dgpu_engine_search_staged(r.engine(), None) == 0
+    n = len(lines)
+    hk = np.zeros((n, k), dtype=np.uint64); hc = np.zeros(n, dtype=np.int32); hh = np.zeros(n, dtype=np.int64)
+    hr = _lib.Results(hk.ctypes.data, hc.ctypes.data, hh.ctypes.data)
+    assert lib.dgpu_engine_fetch_results(r.engine(), C.byref(hr)) == 0
+    assert np.array_equal(hc, want.counts) and np.array_equal(hh, want.total_hits)
+    docs = (0xFFFFFFFF - (hk & 0xFFFFFFFF)).astype(np.int64)
+    for q in range(n):
+        c = int(hc[q])
+        assert np.array_equal(docs[q, :c], want.docs[q, :c]), q

@@ -91,6 +91,44 @@ def _worker(rank, world, port, tmp):
             want_hits, want, _ = ox.search(q, K)
             assert sum(int(m[1]) for m in g_meta) == want_hits == hits_all, line
             assert np.array_equal(merged, _keys(want)[: len(want)]), line
+        # (3) the host work of a batch divided between the ranks: every rank compiles its slice of the query lines
+        # into a relocatable blob, one all_gather exchanges them, and the concatenation is the batch a single rank
+        # would have compiled (descriptors depend on global statistics only)
+        ls = dg.IndexSearcher(local)
+        ws = dg.IndexSearcher(whole)
+        n = len(lines)
+        mine_text = ("\n".join(lines[n * rank // world: n * (rank + 1) // world]) + "\n").encode()
+        blob = ls.compile_batch_text(mine_text)
+        size = torch.tensor([blob.size], dtype=torch.int64)
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, size)
+        cap = max(int(x[0]) for x in sizes)
+        padded = torch.zeros(cap, dtype=torch.uint8)
+        padded[: blob.size] = torch.from_numpy(blob)
+        gathered = [torch.zeros(cap, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(gathered, padded)
+        blobs = [g.numpy()[: int(sz[0])] for g, sz in zip(gathered, sizes)]
+
+        def unpack(b):
+            magic, nq, nt, nf = np.frombuffer(b[:16].tobytes(), dtype=np.uint32)
+            assert magic == 0x42504744
+            q = np.frombuffer(b[16:16 + 20 * nq].tobytes(), dtype=np.uint32).reshape(nq, 5).copy()
+            t = b[16 + 20 * nq: 16 + 20 * nq + 12 * nt].tobytes()
+            return q, t, nt, nf
+
+        want_q, want_t, _, _ = unpack(ws.compile_batch_text(("\n".join(lines) + "\n").encode()))
+        got_q, got_t, toff = [], b"", 0
+        for b in blobs:
+            q, t, nt, nf = unpack(b)
+            assert nf == 0
+            q[:, 0] += toff
+            q[:, 1] += toff
+            got_q.append(q)
+            got_t += t
+            toff += nt
+        assert np.array_equal(np.concatenate(got_q), want_q) and got_t == want_t
+        ls.close()
+        ws.close()
         local.close()
         whole.close()
     finally:
