@@ -448,7 +448,9 @@ def main():
         else:
             # every rank parses + compiles 1/N of the query lines, one gloo all_gather exchanges the compiled slices
             # (descriptors depend on global statistics only), then each rank stages the whole batch on its GPU
+            tt = [time.perf_counter()]
             blob = searcher.compile_batch_text(my_text)
+            tt.append(time.perf_counter())
             sz = torch.tensor([blob.size], dtype=torch.int64)
             sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
             dist.all_gather(sizes, sz, group=cpu_group)
@@ -457,10 +459,16 @@ def main():
             mine[: blob.size] = torch.from_numpy(blob)
             gathered = [torch.zeros(cap, dtype=torch.uint8) for _ in range(world)]
             dist.all_gather(gathered, mine, group=cpu_group)
+            tt.append(time.perf_counter())
             searcher.stage_compiled([g.numpy()[: int(n[0])] for g, n in zip(gathered, sizes)], k)
+            tt.append(time.perf_counter())
             lib.dgpu_engine_device_results(eng, C.byref(dres))
             device_step()
             _ = (m_keys.cpu(), m_counts.cpu(), m_hits.cpu())   # D2H on the bench stream, synchronising
+            tt.append(time.perf_counter())
+            if os.environ.get("DGPU_TRACE") and rank == 0:
+                sys.stderr.write("[bench trace] compile %.2f ms, exchange %.2f ms, stage %.2f ms, device+merge+d2h %.2f ms\n"
+                                 % tuple(1e3 * (b - a) for a, b in zip(tt, tt[1:])))
         t2 = time.perf_counter()
         if i >= n_warm:
             e2e_times.append(t2 - t1)

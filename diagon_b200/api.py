@@ -449,13 +449,16 @@ class IndexSearcher:
     def compile_batch_text(self, text: bytes) -> np.ndarray:
         """Host-only: parse + compile a (slice of a) batch into a relocatable blob (uint8 array)."""
         lib = _lib.load()
-        need = lib.dgpu_compile_batch_text(self._ptr, text, len(text), None, 0)
+        cap = 4 * len(text) + 1024          # 12-byte term / 20-byte query descriptors against >= 3 bytes of text each
+        out = np.empty(cap, dtype=np.uint8)
+        need = lib.dgpu_compile_batch_text(self._ptr, text, len(text), out.ctypes.data, cap)
         if need < 0:
             raise DiagonError(_lib.last_error())
-        out = np.zeros(need, dtype=np.uint8)
-        if lib.dgpu_compile_batch_text(self._ptr, text, len(text), out.ctypes.data, need) != need:
-            raise DiagonError(_lib.last_error())
-        return out
+        if need > cap:                      # cannot happen with the text form above; compile again into the right size
+            out = np.empty(need, dtype=np.uint8)
+            if lib.dgpu_compile_batch_text(self._ptr, text, len(text), out.ctypes.data, need) != need:
+                raise DiagonError(_lib.last_error())
+        return out[:need]
 
     def stage_compiled(self, blobs: Sequence[np.ndarray], k: int) -> int:
         """Stages the concatenation of compiled blobs (e.g. one per rank, in rank order) on this reader's device."""
