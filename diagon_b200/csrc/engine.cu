@@ -503,15 +503,30 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     std::vector<DTerm> dterms;
     std::vector<DItem> items;
     dterms.reserve(b->n_terms / 2 + 16);
+    items.reserve(b->n_terms + 16);
     uint64_t run_entries = kRunPad;  // [0, kRunPad) is the empty run (terms absent on this GPU)
+    // the probes are cache misses into a table of a few MB: hash every key first, then walk with the slot of the key
+    // 16 steps ahead already on its way
+    std::vector<uint32_t> slot_of(b->n_terms);
+    dgpu::parallel_for(b->n_terms, n_threads, [&](size_t lo, size_t hi, int) {
+        for (size_t t = lo; t < hi; ++t) {
+            const dgpu_qterm& qt = b->terms[t];
+            uint32_t idf_bits;
+            std::memcpy(&idf_bits, &qt.idf, 4);
+            const uint64_t key = (static_cast<uint64_t>(qt.term_id) << 32) | idf_bits;
+            slot_of[t] = static_cast<uint32_t>((key * 0x9E3779B97F4A7C15ull) >> 20) & static_cast<uint32_t>(tcap - 1);
+        }
+    });
+    constexpr uint32_t kAhead = 16;
     for (uint32_t t = 0; t < b->n_terms; ++t) {
+        if (t + kAhead < b->n_terms) __builtin_prefetch(&e->h_table[slot_of[t + kAhead]], 1, 1);
         QTermRun& run = qruns[t];
         if (run.len == 0) continue;   // absent here, or no postings
         const dgpu_qterm& qt = b->terms[t];
         uint32_t idf_bits;
         std::memcpy(&idf_bits, &qt.idf, 4);
         const uint64_t key = (static_cast<uint64_t>(qt.term_id) << 32) | idf_bits;
-        size_t h = static_cast<size_t>((key * 0x9E3779B97F4A7C15ull) >> 20) & (tcap - 1);
+        size_t h = slot_of[t];
         uint32_t slot = 0xFFFFFFFFu;
         for (;; h = (h + 1) & (tcap - 1)) {
             dgpu_engine::TableEntry& te = e->h_table[h];
