@@ -120,6 +120,7 @@ struct dgpu_engine {
     uint64_t run_entries = 0;
     uint32_t n_splits = 1;              // average doc-range parts per query of the staged batch (reporting only)
     uint32_t last_window = 0;
+    uint64_t h2d_bytes = 0;             // descriptor bytes the last stage_batch copied to the device
     // launch plan of the batched path (made by stage_batch: the host sizes the per-term rings with it)
     uint32_t plan_cap = 0, plan_list = 0, plan_chlog = 5, plan_W = 0, plan_wpc = 4, plan_ctas = 1, plan_warp_smem = 0;
     DevBuf<WorkItem> d_witems;
@@ -677,6 +678,9 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         }
     }
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+    e->h2d_bytes = sizeof(dgpu_query) * b->n_queries + (sizeof(dgpu_qterm) + sizeof(QTermRun)) * b->n_terms +
+                   sizeof(dgpu_qfilter) * b->n_filters + 4ull * order.size() + sizeof(WorkItem) * witems.size() +
+                   (split_any ? 4ull * part_off.size() : 0) + sizeof(DTerm) * dterms.size() + sizeof(DItem) * items.size();
     lap("h2d");
     return 0;
 }
@@ -852,7 +856,7 @@ int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]) {
     return 0;
 }
 
-int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[8]) {
+int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[10]) {
     out[0] = e->n_dterms;
     out[1] = e->n_ditems;
     out[2] = e->run_entries;
@@ -866,6 +870,8 @@ int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[8]) {
     out[5] = e->last_window;
     out[6] = e->n_acc_items;
     out[7] = e->n_and_items;
+    out[8] = e->h2d_bytes;
+    out[9] = static_cast<uint64_t>(e->n_queries) * (static_cast<uint64_t>(e->k) * 8 + 12);   // keys + count + hits
     return 0;
 }
 

@@ -156,8 +156,9 @@ int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]);
 /* Shape of the staged batch: [0] distinct terms, [1] decode work items, [2] (doc, score) entries of the decode
  * scratch, [3] mean doc-range parts per query, [4] compressed bytes of the distinct terms (what decode_score_kernel
  * reads), [5] docs per window of accumulate_topk_kernel, [6] work items of accumulate_topk_kernel, [7] work items
- * of intersect_topk_kernel (pure conjunctions). */
-int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[8]);
+ * of intersect_topk_kernel (pure conjunctions), [8] host-to-device bytes of the staged descriptors, [9] device-to-host
+ * bytes of one result fetch. */
+int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[10]);
 
 /* Tunables. Returns 0 or -1 for an unknown name / bad value. */
 int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value);
