@@ -78,6 +78,35 @@ struct DevBuf {
     }
 };
 
+// Page-locked host staging: descriptors are packed here before they go to the device and results land here before they
+// are handed to the caller, so every H2D / D2H copy of a search is a true asynchronous DMA.
+struct PinnedArena {
+    uint8_t* p = nullptr;
+    size_t cap = 0, used = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 2 + 4096;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    // copies n bytes into the arena (256-byte aligned slices) and returns where they are
+    const void* put(const void* src, size_t n) {
+        uint8_t* dst = p + used;
+        if (n) std::memcpy(dst, src, n);
+        used += (n + 255) & ~static_cast<size_t>(255);
+        return dst;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = used = 0;
+    }
+};
+
 }  // namespace
 
 struct dgpu_engine {
@@ -129,6 +158,7 @@ struct dgpu_engine {
     bool split_any = false;
     bool plan_pool_global = false;
     DevBuf<uint64_t> d_pool;
+    PinnedArena h_stage, h_results;
     struct TableEntry {
         uint64_t key;   // term id << 32 | idf bits
         uint32_t slot;
@@ -246,6 +276,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_runs.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
     e->d_witems.release(); e->d_part_off.release(); e->d_pool.release();
+    e->h_stage.release(); e->h_results.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_a) cudaEventDestroy(e->ev_a);
@@ -661,23 +692,25 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         CU(cudaMemsetAsync(e->d_runs.p, 0xFF, sizeof(uint2) * kRunPad, e->stream));
     }
     if (b->n_queries) {
-        CU(cudaMemcpyAsync(e->d_queries.p, b->queries, sizeof(dgpu_query) * b->n_queries, cudaMemcpyHostToDevice, e->stream));
-        if (b->n_terms) {
-            CU(cudaMemcpyAsync(e->d_terms.p, b->terms, sizeof(dgpu_qterm) * b->n_terms, cudaMemcpyHostToDevice, e->stream));
-            CU(cudaMemcpyAsync(e->d_qruns.p, qruns.data(), sizeof(QTermRun) * b->n_terms, cudaMemcpyHostToDevice, e->stream));
-        }
-        if (b->n_filters) CU(cudaMemcpyAsync(e->d_filters.p, b->filters, sizeof(dgpu_qfilter) * b->n_filters, cudaMemcpyHostToDevice, e->stream));
-        CU(cudaMemcpyAsync(e->d_order.p, order.data(), 4 * order.size(), cudaMemcpyHostToDevice, e->stream));
-        if (!witems.empty())
-            CU(cudaMemcpyAsync(e->d_witems.p, witems.data(), sizeof(WorkItem) * witems.size(), cudaMemcpyHostToDevice, e->stream));
-        if (split_any)
-            CU(cudaMemcpyAsync(e->d_part_off.p, part_off.data(), 4 * part_off.size(), cudaMemcpyHostToDevice, e->stream));
-        if (!dterms.empty()) {
-            CU(cudaMemcpyAsync(e->d_dterms.p, dterms.data(), sizeof(DTerm) * dterms.size(), cudaMemcpyHostToDevice, e->stream));
-            CU(cudaMemcpyAsync(e->d_items.p, items.data(), sizeof(DItem) * items.size(), cudaMemcpyHostToDevice, e->stream));
+        const size_t bytes[9] = {sizeof(dgpu_query) * b->n_queries, sizeof(dgpu_qterm) * b->n_terms, sizeof(QTermRun) * b->n_terms,
+                                 sizeof(dgpu_qfilter) * b->n_filters, 4 * order.size(), sizeof(WorkItem) * witems.size(),
+                                 split_any ? 4 * part_off.size() : 0, sizeof(DTerm) * dterms.size(), sizeof(DItem) * items.size()};
+        const void* src[9] = {b->queries, b->terms, qruns.data(), b->filters, order.data(), witems.data(), part_off.data(),
+                              dterms.data(), items.data()};
+        void* dst[9] = {e->d_queries.p, e->d_terms.p, e->d_qruns.p, e->d_filters.p, e->d_order.p, e->d_witems.p,
+                        e->d_part_off.p, e->d_dterms.p, e->d_items.p};
+        size_t total = 0;
+        for (size_t n : bytes) total += (n + 255) & ~static_cast<size_t>(255);
+        // the previous batch's copies out of the arena completed before its stage call returned
+        CU(e->h_stage.ensure(total));
+        e->h_stage.used = 0;
+        for (int i = 0; i < 9; ++i) {
+            if (!bytes[i]) continue;
+            const void* pinned = e->h_stage.put(src[i], bytes[i]);
+            CU(cudaMemcpyAsync(dst[i], pinned, bytes[i], cudaMemcpyHostToDevice, e->stream));
         }
     }
-    CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+    CU(cudaStreamSynchronize(e->stream));  // the arena is reused by the next stage call
     e->h2d_bytes = sizeof(dgpu_query) * b->n_queries + (sizeof(dgpu_qterm) + sizeof(QTermRun)) * b->n_terms +
                    sizeof(dgpu_qfilter) * b->n_filters + 4ull * order.size() + sizeof(WorkItem) * witems.size() +
                    (split_any ? 4ull * part_off.size() : 0) + sizeof(DTerm) * dterms.size() + sizeof(DItem) * items.size();
@@ -837,11 +870,20 @@ int dgpu_engine_device_results(dgpu_engine* e, dgpu_results* out) {
 int dgpu_engine_fetch_results(dgpu_engine* e, dgpu_results* out) {
     CU(cudaSetDevice(e->device));
     if (e->n_queries) {
-        CU(cudaMemcpyAsync(out->keys, e->d_keys.p, sizeof(uint64_t) * e->n_queries * e->k, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(out->counts, e->d_counts.p, sizeof(int32_t) * e->n_queries, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(out->total_hits, e->d_hits.p, sizeof(int64_t) * e->n_queries, cudaMemcpyDeviceToHost, e->stream));
+        const size_t nk = sizeof(uint64_t) * e->n_queries * e->k, nc = sizeof(int32_t) * e->n_queries,
+                     nh = sizeof(int64_t) * e->n_queries;
+        const size_t ok = 0, oh = (nk + 255) & ~static_cast<size_t>(255), oc = oh + ((nh + 255) & ~static_cast<size_t>(255));
+        CU(e->h_results.ensure(oc + nc));
+        CU(cudaMemcpyAsync(e->h_results.p + ok, e->d_keys.p, nk, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(e->h_results.p + oh, e->d_hits.p, nh, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(e->h_results.p + oc, e->d_counts.p, nc, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        std::memcpy(out->keys, e->h_results.p + ok, nk);
+        std::memcpy(out->total_hits, e->h_results.p + oh, nh);
+        std::memcpy(out->counts, e->h_results.p + oc, nc);
+    } else {
+        CU(cudaStreamSynchronize(e->stream));
     }
-    CU(cudaStreamSynchronize(e->stream));
     return read_timers(e);
 }
 
