@@ -30,6 +30,7 @@ constexpr int kItemBlocks = 64;             // posting blocks per decode work it
 constexpr int kPadBlocks = 1;               // kDocEnd blocks after every run: readers look at most 64 entries past a real one
 constexpr int kRunPad = kPadBlocks * DGPU_BLOCK_POSTINGS;  // scratch[0, kRunPad) is the empty run
 constexpr int kDecodeThreads = 256;
+constexpr uint32_t kLaneMergeMaxTerms = 16; // queries of up to this many terms are merged document-at-a-time by lanes
 
 struct DTerm {          // one distinct (term, idf, field) of the batch
     uint32_t term_id;
@@ -738,6 +739,195 @@ intersect_topk_kernel(DeviceIndex ix, AccumParams P) {
         }
 
         __syncwarp();
+        const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
+        for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;
+        warp_bitonic_sort_desc(cand, nsort, lane);
+        const uint32_t n_out = min(n_cand, static_cast<uint32_t>(P.k));
+        for (uint32_t i = lane; i < static_cast<uint32_t>(P.k); i += 32)
+            P.out_keys[static_cast<size_t>(item) * P.k + i] = i < n_out ? cand[i] : 0ull;
+        if (lane == 0) {
+            P.out_counts[item] = static_cast<int32_t>(n_out);
+            P.out_hits[item] = static_cast<int64_t>(hits);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b + K4, document-at-a-time: one LANE merges the runs of a query over its own doc range.
+//
+// A query of up to T terms is a T-way merge of sorted (doc, score) runs. The warp that owns a work item cuts the
+// item's doc range into 32 contiguous sub-ranges holding equal shares of the query's longest run; every lane finds
+// its start in every run (branch-free bisection, all terms in flight together) and then walks its sub-range on its
+// own: the heads of the T runs live in registers, the next doc is their minimum, the scores of the runs standing on
+// that doc are added in clause order starting from 0.0f (BooleanQuery.cpp:119-126, :232-241: bit-exact sums), and
+// exactly those runs advance (one 8-byte load each). No accumulator window, no touched list, no per-(term, window)
+// pass with a handful of useful lanes: every lane of every instruction works on a posting, which is what the window
+// kernel cannot offer to queries whose terms are sparse relative to a shared-memory window (C2: 70 postings per
+// 1664-doc window spread over 10 terms). The loop is uniform code (predicated, no divergence apart from lanes that
+// finish early); required-match counts, exclusions and doc-value filters are evaluated on the spot; candidates
+// above the warp's running threshold are appended to the warp's pool with one ballot per iteration.
+// ------------------------------------------------------------------------------------------------
+template <int T>
+struct LaneMergeBounds {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinCtas = T <= 8 ? 8 : (T <= 12 ? 6 : 4);
+};
+
+template <int T, bool NEED_CNT>
+__global__ void __launch_bounds__(LaneMergeBounds<T>::kThreads, LaneMergeBounds<T>::kMinCtas)
+lane_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* cand = P.pool ? P.pool + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * P.cand_cap
+                            : reinterpret_cast<uint64_t*>(smem_raw) + static_cast<size_t>(warp) * P.cand_cap;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint2* __restrict__ runs = P.runs;
+
+    for (;;) {
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(P.work_counter, 1u);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (slot >= P.n_items) break;
+        const uint32_t item = P.order[slot];
+        const WorkItem wi = P.items[item];
+        const dgpu_query qd = P.queries[wi.query];
+        const QTermRun* qt = P.terms + qd.term_begin;
+        const uint32_t nt = qd.term_end - qd.term_begin;   // <= T
+        const uint32_t nf = qd.filter_end - qd.filter_begin;
+        const dgpu_qfilter* qf = P.filters + qd.filter_begin;
+        const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
+        DGPU_ASSERT(nt <= static_cast<uint32_t>(T));
+
+        // the runs of the query (warp-uniform); terms past nt read the empty run at scratch[0]
+        uint32_t pos[T], len[T];
+        uint32_t not_mask = 0, heavy_len = 0, heavy_base = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            pos[t] = 0;
+            len[t] = 0;
+            if (static_cast<uint32_t>(t) < nt) {
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(qt + t));   // base, len, role, skip row
+                pos[t] = r.x;
+                len[t] = r.y;
+                if (NEED_CNT && r.z == DGPU_ROLE_MUST_NOT) not_mask |= 1u << t;
+                if (r.y > heavy_len) {
+                    heavy_len = r.y;
+                    heavy_base = r.x;
+                }
+            }
+        }
+
+        // sub-range of this lane: equal shares of the longest run inside [lo, hi)
+        auto lower = [&](uint32_t x) {   // entries of the longest run below doc x
+            uint32_t a = 0, b = heavy_len;
+            while (a < b) {
+                const uint32_t mid = (a + b) >> 1;
+                if (__ldg(&runs[heavy_base + mid].x) < x) a = mid + 1; else b = mid;
+            }
+            return a;
+        };
+        const uint32_t ha = lo > ix.doc_lo ? lower(lo) : 0u;
+        const uint32_t hb = hi < ix.doc_hi ? lower(hi) : heavy_len;
+        uint32_t my_lo = lo;
+        if (lane) {
+            const uint32_t idx = ha + static_cast<uint32_t>((static_cast<uint64_t>(hb - ha) * lane) >> 5);
+            DGPU_ASSERT(static_cast<uint64_t>(heavy_base) + idx < P.run_total);
+            my_lo = min(hi, max(lo, __ldg(&runs[heavy_base + idx].x)));
+        }
+        uint32_t my_hi = __shfl_down_sync(0xFFFFFFFFu, my_lo, 1);
+        if (lane == 31) my_hi = hi;
+
+        // first entry >= my_lo of every run: branch-free bisection, the T probes of a step are independent loads
+        if (heavy_len) {
+            uint32_t below[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) below[t] = 0;
+            for (uint32_t step = 1u << (31 - __clz(heavy_len)); step; step >>= 1) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t q = below[t] + step;
+                    if (q <= len[t] && __ldg(&runs[pos[t] + q - 1u].x) < my_lo) below[t] = q;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) pos[t] += below[t];
+        }
+        uint32_t hd[T], hs[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            DGPU_ASSERT(static_cast<uint64_t>(pos[t]) < P.run_total);
+            const uint2 e = __ldg(runs + pos[t]);
+            hd[t] = e.x;
+            hs[t] = e.y;
+        }
+
+        uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
+        uint64_t thresh = 0;        // key of the k-th best so far
+        uint32_t hits = 0;          // per lane
+        auto prune = [&]() {
+            const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
+            for (uint32_t i = n_cand + lane; i < n; i += 32) cand[i] = 0;
+            warp_bitonic_sort_desc(cand, n, lane);
+            if (n_cand >= static_cast<uint32_t>(P.k)) {
+                thresh = cand[P.k - 1];
+                n_cand = P.k;
+            }
+        };
+
+        for (;;) {
+            uint32_t m = hd[0];
+#pragma unroll
+            for (int t = 1; t < T; ++t) m = min(m, hd[t]);
+            const bool act = m < my_hi;
+            if (!__any_sync(0xFFFFFFFFu, act)) break;
+            float score = 0.0f;
+            uint32_t c = 0;
+            bool excluded = false;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                if (act && hd[t] == m) {
+                    if (NEED_CNT && (not_mask & (1u << t))) {
+                        excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
+                    } else {
+                        score = __fadd_rn(score, __uint_as_float(hs[t]));
+                        ++c;
+                    }
+                    ++pos[t];
+                    DGPU_ASSERT(static_cast<uint64_t>(pos[t]) < P.run_total);
+                    const uint2 e = __ldg(runs + pos[t]);
+                    hd[t] = e.x;
+                    hs[t] = e.y;
+                }
+            }
+            bool match = act;
+            if (NEED_CNT) match = act && !excluded && c != 0 && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
+            if (nf) {
+                for (uint32_t f = 0; f < nf && match; ++f) {
+                    const int64_t val = ix.dv[qf[f].column][m - ix.doc_lo];
+                    match = (val >= qf[f].lo) && (val <= qf[f].hi);
+                    score = __fadd_rn(score, 1.0f);  // constant score of the range clause (NumericRangeQuery.cpp:117-120)
+                }
+            }
+            hits += match ? 1u : 0u;
+            const uint32_t sb = __float_as_uint(score);
+            const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+            const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - m);
+            // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
+            const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
+            if (pm) {
+                if (n_cand + 32u > P.cand_cap) prune();
+                const bool still = push && key > thresh;   // the prune may have raised the threshold
+                const uint32_t sm = __ballot_sync(0xFFFFFFFFu, still);
+                if (still) cand[n_cand + __popc(sm & lt_mask)] = key;
+                n_cand += __popc(sm);
+            }
+        }
+
+        // ---- final select
+        __syncwarp();
+        hits = __reduce_add_sync(0xFFFFFFFFu, hits);
         const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
         for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;
         warp_bitonic_sort_desc(cand, nsort, lane);

@@ -180,6 +180,9 @@ struct dgpu_engine {
     int part_factor = 2;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
     int decode_ctas_per_sm = 64; // grid of decode_score_kernel (grid-stride over the decode work items)
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
+    int lane_merge = 1;      // queries of <= 16 terms go to lane_merge_topk_kernel (0: accumulated in windows)
+    uint32_t lane_max_terms = 0;                 // most terms of any lane-merge query of the staged batch
+    uint32_t n_lane_items = 0;
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
     // stats
     uint64_t launches = 0;
@@ -345,6 +348,10 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->intersect = value ? 1 : 0;
         return 0;
     }
+    if (!std::strcmp(name, "lane_merge")) {
+        e->lane_merge = value ? 1 : 0;
+        return 0;
+    }
     if (!std::strcmp(name, "max_parts")) {
         if (value < 0 || value > 64) return fail("max_parts must be in [0, 64]");
         e->max_parts = static_cast<int>(value);
@@ -455,7 +462,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     std::vector<QTermRun> qruns(b->n_terms);
     const int n_threads = b->n_queries < 1024 ? 1 : 0;      // 0 = every host thread
     struct Partial {
-        uint32_t max_terms = 1;
+        uint32_t max_terms = 1, lane_max_terms = 0;
         bool need_cnt = false;
         std::string error;
     };
@@ -475,9 +482,12 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             // a pure conjunction (every term MUST) of 2..32 terms is intersected, everything else is accumulated
             bool all_must = e->kernel == 3 && e->intersect && nt_q >= 2 && nt_q <= 32 && qd.n_must == nt_q;
             for (uint32_t t = qd.term_begin; all_must && t < qd.term_end; ++t) all_must = b->terms[t].role == DGPU_ROLE_MUST;
-            is_and[q] = all_must ? 1 : 0;
+            // class of the query: 2 = intersected, 1 = merged document-at-a-time by lanes, 0 = accumulated in windows
+            const bool lane = !all_must && e->kernel == 3 && e->lane_merge && nt_q <= kLaneMergeMaxTerms;
+            is_and[q] = all_must ? 2 : (lane ? 1 : 0);
             if (!all_must) {
-                pt.max_terms = std::max(pt.max_terms, nt_q);
+                if (lane) pt.lane_max_terms = std::max(pt.lane_max_terms, nt_q);
+                else pt.max_terms = std::max(pt.max_terms, nt_q);
                 if (qd.n_must > 1 || qd.min_should_match > 1) pt.need_cnt = true;
             }
             uint64_t c = 0, lead = ~0ull;
@@ -510,11 +520,12 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
                 if (b->filters[f].column < 0) bad(q, "bad filter column");
         }
     });
-    uint32_t max_terms = 1;
+    uint32_t max_terms = 1, lane_max_terms = 0;
     bool need_cnt = false;
     for (const Partial& pt : partial) {
         if (!pt.error.empty()) return fail("%s", pt.error.c_str());
         max_terms = std::max(max_terms, pt.max_terms);
+        lane_max_terms = std::max(lane_max_terms, pt.lane_max_terms);
         need_cnt = need_cnt || pt.need_cnt;
     }
     lap("validate");
@@ -581,6 +592,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     }
     lap("terms");
     e->max_terms = max_terms;
+    e->lane_max_terms = lane_max_terms;
     e->need_cnt = need_cnt;
     e->n_dterms = static_cast<uint32_t>(dterms.size());
     e->n_ditems = static_cast<uint32_t>(items.size());
@@ -598,7 +610,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     bool split_any = false;
     if (e->kernel == 3) {
         for (uint32_t q = 0; q < b->n_queries; ++q)
-            if (is_and[q]) cost[q] = 1 + 8 * std::min<uint64_t>(lead_cost[q], cost[q]);   // ~8 probes per lead posting and term
+            if (is_and[q] == 2) cost[q] = 1 + 8 * std::min<uint64_t>(lead_cost[q], cost[q]);   // ~8 probes per lead posting and term
         uint64_t total_cost = 0;
         for (uint32_t q = 0; q < b->n_queries; ++q) total_cost += cost[q];
         const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) * e->plan_ctas * e->plan_wpc;
@@ -634,6 +646,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     std::iota(order.begin(), order.end(), 0u);
     e->n_acc_items = n_items;
     e->n_and_items = 0;
+    e->n_lane_items = 0;
     if (e->kernel == 3) {
         // one sort of packed keys: class (accumulate first); cost class descending (powers of two: long items
         // start first); inside a cost class the items that stream the same long list are neighbours, so the warps
@@ -643,21 +656,23 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             bool operator<(const Key& o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
         };
         std::vector<Key> keys(n_items);
-        uint32_t n_and = 0;
+        uint32_t n_and = 0, n_lane = 0;
         for (uint32_t i = 0; i < n_items; ++i) {
             const uint32_t q = witems[i].query;
             const uint64_t cls = is_and[q];
-            n_and += static_cast<uint32_t>(cls);
+            n_and += cls == 2 ? 1u : 0u;
+            n_lane += cls == 1 ? 1u : 0u;
             const uint64_t c = std::max<uint64_t>(1, item_cost[i]);
             const uint64_t lg = 63 - static_cast<uint64_t>(__builtin_clzll(c));
             const uint64_t cost_class = lg;      // 0..63
-            keys[i].hi = (cls << 63) | ((127 - cost_class) << 40) | (static_cast<uint64_t>(heavy_term[q]) << 8);
+            keys[i].hi = (cls << 62) | ((127 - cost_class) << 40) | (static_cast<uint64_t>(heavy_term[q]) << 8);
             keys[i].lo = (static_cast<uint64_t>(witems[i].doc_lo) << 32) | i;
         }
         std::sort(keys.begin(), keys.end());
         for (uint32_t i = 0; i < n_items; ++i) order[i] = static_cast<uint32_t>(keys[i].lo);
         e->n_and_items = n_and;
-        e->n_acc_items = n_items - n_and;
+        e->n_lane_items = n_lane;
+        e->n_acc_items = n_items - n_and - n_lane;
     } else {
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
     }
@@ -666,7 +681,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     CU(e->d_terms.ensure(b->n_terms));
     CU(e->d_filters.ensure(b->n_filters));
     CU(e->d_order.ensure(n_items));
-    CU(e->d_counter.ensure(2));
+    CU(e->d_counter.ensure(4));
     CU(e->d_keys.ensure(static_cast<size_t>(b->n_queries) * k));
     CU(e->d_counts.ensure(b->n_queries));
     CU(e->d_hits.ensure(b->n_queries));
@@ -762,6 +777,37 @@ static int launch_fused(dgpu_engine* e, cudaStream_t stream) {
     return 0;
 }
 
+// lane_merge_topk_kernel for the smallest T that holds the longest query of the class
+template <int T>
+static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
+    auto kern = e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>;
+    constexpr int threads = LaneMergeBounds<T>::kThreads;
+    constexpr int wpc = threads / 32;
+    const size_t smem = e->plan_pool_global ? 0 : sizeof(uint64_t) * e->plan_cap * wpc;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) return fail("lane_merge_topk_kernel does not fit an SM (%zu bytes of shared memory)", smem);
+    const uint64_t want_ctas = (static_cast<uint64_t>(L.n_items) + wpc - 1) / wpc;
+    const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * per_sm, want_ctas));
+    // a global pool (large k) was sized for 64 warps per SM by launch_batched; the kernels run one after the other
+    kern<<<grid, threads, smem, stream>>>(e->ix, L);
+    CU(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+static int launch_lane_merge(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
+    const uint32_t nt = e->lane_max_terms;
+    if (nt <= 2) return launch_lane_merge_t<2>(e, L, stream);
+    if (nt <= 4) return launch_lane_merge_t<4>(e, L, stream);
+    if (nt <= 6) return launch_lane_merge_t<6>(e, L, stream);
+    if (nt <= 8) return launch_lane_merge_t<8>(e, L, stream);
+    if (nt <= 10) return launch_lane_merge_t<10>(e, L, stream);
+    if (nt <= 12) return launch_lane_merge_t<12>(e, L, stream);
+    return launch_lane_merge_t<16>(e, L, stream);
+}
+
 // kernel = 3: decode + score every distinct term of the batch once, then accumulate + top-k, one warp per item
 static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     AccumParams P{};
@@ -783,7 +829,8 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.warp_smem = e->plan_warp_smem;
     P.pool = nullptr;
     if (e->plan_pool_global) {
-        CU(e->d_pool.ensure(static_cast<size_t>(e->sm_count) * e->plan_ctas * e->plan_wpc * e->plan_cap));
+        const size_t warps_per_sm = std::max<size_t>(static_cast<size_t>(e->plan_ctas) * e->plan_wpc, 64);   // 64 = a full SM of lane-merge warps
+        CU(e->d_pool.ensure(static_cast<size_t>(e->sm_count) * warps_per_sm * e->plan_cap));
         P.pool = e->d_pool.p;
     }
     const size_t smem = std::max<size_t>(static_cast<size_t>(e->plan_warp_smem) * e->plan_wpc, 16);
@@ -792,7 +839,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.out_counts = split ? e->d_part_counts.p : e->d_counts.p;
     P.out_hits = split ? e->d_part_hits.p : e->d_hits.p;
 
-    CU(cudaMemsetAsync(e->d_counter.p, 0, 8, stream));
+    CU(cudaMemsetAsync(e->d_counter.p, 0, 16, stream));
     CU(cudaEventRecord(e->ev0, stream));
     if (e->n_ditems) {
         const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * e->decode_ctas_per_sm));
@@ -812,9 +859,16 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
         CU(cudaGetLastError());
         e->launches++;
     }
+    if (e->n_lane_items) {
+        AccumParams L = P;
+        L.order = e->d_order.p + e->n_acc_items;
+        L.n_items = e->n_lane_items;
+        L.work_counter = e->d_counter.p + 2;
+        if (launch_lane_merge(e, L, stream)) return -1;
+    }
     if (e->n_and_items) {
         AccumParams Q = P;
-        Q.order = e->d_order.p + e->n_acc_items;
+        Q.order = e->d_order.p + e->n_acc_items + e->n_lane_items;
         Q.n_items = e->n_and_items;
         Q.work_counter = e->d_counter.p + 1;
         CU(cudaFuncSetAttribute(intersect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
