@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--part-factor", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="3 = batched decode_score + accumulate_topk (default), 2 = fused windows")
     ap.add_argument("--lane-merge", type=int, default=-1, help="1 = queries of <= 16 terms on lane_merge_topk_kernel (default), 0 = windows")
+    ap.add_argument("--lane-ctas-per-sm", type=int, default=0)
+    ap.add_argument("--lane-ring-entries", type=int, default=0)
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -341,6 +343,10 @@ def main():
         reader.set_option("kernel", args.kernel)
     if args.lane_merge >= 0:
         reader.set_option("lane_merge", args.lane_merge)
+    if args.lane_ring_entries:
+        reader.set_option("lane_ring_entries", args.lane_ring_entries)
+    if args.lane_ctas_per_sm:
+        reader.set_option("lane_ctas_per_sm", args.lane_ctas_per_sm)
     if world > 1:
         # global statistics: idf / avgdl must be identical on every rank
         df = torch.from_numpy(reader.get_doc_freqs()).cuda()

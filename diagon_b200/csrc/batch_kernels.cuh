@@ -942,6 +942,291 @@ lane_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3b + K4, document-at-a-time with staged runs: lane_merge_topk_kernel's merge loop fed from shared memory.
+//
+// Lanes that walk private positions of T runs in global memory touch warps x 32 x T cache lines at once: neither L1
+// nor L2 can hold them at full occupancy and every 8-byte load costs a sector (measured: L1 hit 37 %, L2 hit 57 %,
+// 34 GB of DRAM reads for 30 GB of entries, IPC 0.9). Here the WARP streams every run of its query through a ring
+// in its slice of shared memory (coalesced 8-byte cp.async, issued one window ahead, capacities in proportion to
+// the run lengths) and walks the doc range window by window:
+//   * a window is [smallest next doc, smallest last staged doc): every entry of every run below the window end is
+//     in shared memory;
+//   * the window is cut into 32 equal doc spans, one per lane; every lane bisects every ring for its span
+//     (shared-memory probes) and merges its span document-at-a-time exactly as lane_merge_topk_kernel does, with
+//     ring reads instead of global loads;
+//   * the cursors of the next window are where the last lane stopped.
+// Global memory is read once, in order, 256 bytes per instruction; the random accesses stay on chip.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t staged_warp_smem_bytes(uint32_t ring_entries, uint32_t cap_smem, int T) {
+    size_t b = sizeof(uint2) * (static_cast<size_t>(ring_entries) + 1);   // rings + the shared end-of-run entry
+    b += (sizeof(uint32_t) * static_cast<size_t>(T) + 7) & ~static_cast<size_t>(7);   // cursor exchange
+    b += sizeof(uint64_t) * cap_smem;                                     // candidate pool
+    return (b + 15) & ~static_cast<size_t>(15);
+}
+
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+template <int T>
+struct StagedMergeBounds {   // register budget: 5 words of state per term and lane
+    static constexpr int kMinCtas = T <= 6 ? 8 : (T <= 10 ? 6 : (T <= 12 ? 5 : 4));
+};
+
+template <int T, bool NEED_CNT>
+__global__ void __launch_bounds__(LaneMergeBounds<T>::kThreads, StagedMergeBounds<T>::kMinCtas)
+staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t B = P.W;   // ring entries per warp (power of two)
+    uint8_t* sp = smem_raw + static_cast<size_t>(warp) * P.warp_smem;
+    const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(sp));
+    uint2* ring = reinterpret_cast<uint2*>(sp);
+    uint32_t* xch = reinterpret_cast<uint32_t*>(sp + sizeof(uint2) * (B + 1));
+    uint64_t* cand = P.pool ? P.pool + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * P.cand_cap
+                            : reinterpret_cast<uint64_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * T + 7) & ~7u));
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint2* __restrict__ runs = P.runs;
+    if (lane == 0) ring[B] = make_uint2(kDocEnd, 0u);   // what the unused term slots of a query read
+    __syncwarp();
+
+    for (;;) {
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(P.work_counter, 1u);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (slot >= P.n_items) break;
+        const uint32_t item = P.order[slot];
+        const WorkItem wi = P.items[item];
+        const dgpu_query qd = P.queries[wi.query];
+        const QTermRun* qt = P.terms + qd.term_begin;
+        const uint32_t nt = qd.term_end - qd.term_begin;   // <= T
+        const uint32_t nf = qd.filter_end - qd.filter_begin;
+        const dgpu_qfilter* qf = P.filters + qd.filter_begin;
+        const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
+        DGPU_ASSERT(nt <= static_cast<uint32_t>(T));
+        const bool mine = static_cast<uint32_t>(lane) < nt;
+
+        // ---- lane t holds the stream state of term t: [cur, fill) are the staged entries not consumed yet
+        uint32_t cur = 0, fill = 0, cap = 1, off = B, limit = 0, len = 0, role = 0;
+        if (mine) {
+            const QTermRun r = qt[lane];
+            cur = r.base;
+            len = r.len;
+            limit = r.base + r.len + kRunPad;   // the padding after a run is readable and says "end"
+            role = r.meta;
+            if (lo > ix.doc_lo) {               // first entry with doc >= lo
+                uint32_t a = 0, b = r.len;
+                while (a < b) {
+                    const uint32_t mid = (a + b) >> 1;
+                    if (__ldg(&runs[r.base + mid].x) < lo) a = mid + 1; else b = mid;
+                }
+                cur += a;
+            }
+        }
+        fill = cur;
+        const uint32_t not_mask = NEED_CNT ? __ballot_sync(0xFFFFFFFFu, mine && role == DGPU_ROLE_MUST_NOT) : 0u;
+
+        // ---- ring capacities: powers of two (>= 8 entries) in proportion to the run lengths, the rest of the
+        // budget goes to the rings that are furthest below their share
+        {
+            float flen = mine ? static_cast<float>(len) + 1.0f : 0.0f;
+            float tot = flen;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+            const float share = mine ? static_cast<float>(B - 8u * nt) * flen / tot : 0.0f;
+            uint32_t maxcap = 8;
+            while (maxcap < len + 8u && maxcap < B / 2u) maxcap <<= 1;
+            if (mine) {
+                cap = 8;
+                while (static_cast<float>(cap * 2u) <= share && cap < maxcap) cap <<= 1;
+            }
+            uint32_t used = __reduce_add_sync(0xFFFFFFFFu, mine ? cap : 0u);
+            for (;;) {
+                DGPU_ASSERT(used <= B);
+                const uint32_t left = B - used;
+                float want = 0.0f;
+                if (mine && cap <= left && cap < maxcap) want = share / static_cast<float>(cap) + 1e-6f;
+                const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(want));   // want >= 0: bits order as floats
+                if (best == 0u) break;
+                const int who = __ffs(__ballot_sync(0xFFFFFFFFu, __float_as_uint(want) == best)) - 1;
+                used += __shfl_sync(0xFFFFFFFFu, cap, who);
+                if (lane == who) cap <<= 1;
+            }
+            const uint32_t c = mine ? cap : 0u;
+            const uint32_t incl = warp_inclusive_scan(c, lane);
+            if (mine) off = incl - c;
+        }
+        uint32_t base[T], bmask[T];   // ring of term t: shared-memory byte address, byte mask (unused slots: the end entry)
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            base[t] = ring_s + 8u * __shfl_sync(0xFFFFFFFFu, off, t);
+            bmask[t] = 8u * __shfl_sync(0xFFFFFFFFu, cap, t) - 1u;
+        }
+
+        // copies the next entries of every run whose ring is at least half free (or that is about to end)
+        auto stage = [&]() {
+            uint32_t n = 0;
+            if (mine) {
+                const uint32_t room = cap - (fill - cur), rest = limit - fill;
+                n = min(room, rest);
+                if (n < (cap >> 1) && n != rest) n = 0;
+            }
+            uint32_t need = __ballot_sync(0xFFFFFFFFu, n != 0u);
+            while (need) {
+                const int tt = __ffs(need) - 1;
+                need &= need - 1u;
+                const uint32_t f = __shfl_sync(0xFFFFFFFFu, fill, tt), cnt = __shfl_sync(0xFFFFFFFFu, n, tt);
+                const uint32_t o = __shfl_sync(0xFFFFFFFFu, off, tt), msk = __shfl_sync(0xFFFFFFFFu, cap, tt) - 1u;
+                DGPU_ASSERT(static_cast<uint64_t>(f) + cnt <= P.run_total && o + msk < B);
+                for (uint32_t i = lane; i < cnt; i += 32) cp_async8(ring_s + 8u * (o + ((f + i) & msk)), runs + f + i);
+            }
+            fill += n;
+            cp_async_commit();
+        };
+
+        uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
+        uint64_t thresh = 0;        // key of the k-th best so far
+        uint32_t hits = 0;          // per lane
+        auto prune = [&]() {
+            const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
+            for (uint32_t i = n_cand + lane; i < n; i += 32) cand[i] = 0;
+            warp_bitonic_sort_desc(cand, n, lane);
+            if (n_cand >= static_cast<uint32_t>(P.k)) {
+                thresh = cand[P.k - 1];
+                n_cand = P.k;
+            }
+        };
+
+        __syncwarp();
+        stage();
+        cp_async_wait_all();
+        __syncwarp();
+        for (;;) {
+            // ---- window: from the smallest next doc to the smallest last staged doc
+            uint32_t first = kDocEnd, last = kDocEnd;
+            if (mine) {
+                DGPU_ASSERT(fill - cur >= 1u && fill - cur <= cap);
+                first = ring[off + (cur & (cap - 1u))].x;
+                last = ring[off + ((fill - 1u) & (cap - 1u))].x;
+            }
+            const uint32_t ws = __reduce_min_sync(0xFFFFFFFFu, first);
+            if (ws >= hi) break;
+            const uint32_t we = min(__reduce_min_sync(0xFFFFFFFFu, last), hi);
+            DGPU_ASSERT(we > ws);
+            const uint32_t avail = fill - cur;   // complete in shared memory; what stage() adds now is for later windows
+            stage();
+
+            const uint32_t span = we - ws;
+            const uint32_t my_lo = ws + static_cast<uint32_t>((static_cast<uint64_t>(span) * lane) >> 5);
+            const uint32_t my_hi = ws + static_cast<uint32_t>((static_cast<uint64_t>(span) * (lane + 1)) >> 5);
+
+            // ---- this lane's start in every ring: entries below my_lo among the staged ones (branch-free bisection)
+            uint32_t p8[T], hd[T], hs[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const uint32_t c = __shfl_sync(0xFFFFFFFFu, cur, t), n = __shfl_sync(0xFFFFFFFFu, avail, t);
+                uint32_t below = 0;
+                for (uint32_t step = n ? 1u << (31 - __clz(n)) : 0u; step; step >>= 1) {
+                    const uint32_t q = below + step;
+                    if (q <= n && lds32(base[t] + (((c + q - 1u) << 3) & bmask[t])) < my_lo) below = q;
+                }
+                p8[t] = (c + below) << 3;
+                const uint2 e = lds64(base[t] + (p8[t] & bmask[t]));
+                hd[t] = e.x;
+                hs[t] = e.y;
+            }
+
+            // ---- document-at-a-time merge of [my_lo, my_hi)
+            for (;;) {
+                uint32_t m = hd[0];
+#pragma unroll
+                for (int t = 1; t < T; ++t) m = min(m, hd[t]);
+                const bool act = m < my_hi;
+                if (!__any_sync(0xFFFFFFFFu, act)) break;
+                float score = 0.0f;
+                uint32_t c = 0;
+                bool excluded = false;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    if (act && hd[t] == m) {
+                        if (NEED_CNT && (not_mask & (1u << t))) {
+                            excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
+                        } else {
+                            score = __fadd_rn(score, __uint_as_float(hs[t]));
+                            ++c;
+                        }
+                        p8[t] += 8u;
+                        const uint2 e = lds64(base[t] + (p8[t] & bmask[t]));
+                        hd[t] = e.x;
+                        hs[t] = e.y;
+                    }
+                }
+                bool match = act;
+                if (NEED_CNT) match = act && !excluded && c != 0 && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
+                if (nf) {
+                    for (uint32_t f = 0; f < nf && match; ++f) {
+                        const int64_t val = ix.dv[qf[f].column][m - ix.doc_lo];
+                        match = (val >= qf[f].lo) && (val <= qf[f].hi);
+                        score = __fadd_rn(score, 1.0f);  // constant score of the range clause (NumericRangeQuery.cpp:117-120)
+                    }
+                }
+                hits += match ? 1u : 0u;
+                const uint32_t sb = __float_as_uint(score);
+                const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+                const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - m);
+                // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
+                const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
+                if (pm) {
+                    if (n_cand + 32u > P.cand_cap) prune();
+                    const bool still = push && key > thresh;   // the prune may have raised the threshold
+                    const uint32_t sm = __ballot_sync(0xFFFFFFFFu, still);
+                    if (still) cand[n_cand + __popc(sm & lt_mask)] = key;
+                    n_cand += __popc(sm);
+                }
+            }
+
+            // ---- the last lane stands on the first entry >= we of every run: the cursors of the next window
+            __syncwarp();
+            if (lane == 31) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) xch[t] = p8[t];
+            }
+            __syncwarp();
+            if (mine) {
+                const uint32_t adv = (xch[lane] - (cur << 3)) >> 3;
+                DGPU_ASSERT(adv < avail);
+                cur += adv;
+            }
+            cp_async_wait_all();
+            __syncwarp();
+        }
+
+        // ---- final select
+        __syncwarp();
+        hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+        const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
+        for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;
+        warp_bitonic_sort_desc(cand, nsort, lane);
+        const uint32_t n_out = min(n_cand, static_cast<uint32_t>(P.k));
+        for (uint32_t i = lane; i < static_cast<uint32_t>(P.k); i += 32)
+            P.out_keys[static_cast<size_t>(item) * P.k + i] = i < n_out ? cand[i] : 0ull;
+        if (lane == 0) {
+            P.out_counts[item] = static_cast<int32_t>(n_out);
+            P.out_hits[item] = static_cast<int64_t>(hits);
+        }
+        __syncwarp();
+    }
+}
+
 // Merge of the parts of every query (doc-range splits, consecutive items [part_off[q], part_off[q + 1])): every key
 // finds its rank by binary search in the other parts' sorted lists; keys are unique (distinct docs).
 __global__ void merge_items_kernel(const uint64_t* __restrict__ part_keys, const int32_t* __restrict__ part_counts,

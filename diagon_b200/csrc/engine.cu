@@ -183,6 +183,8 @@ struct dgpu_engine {
     int lane_merge = 1;      // queries of <= 16 terms go to lane_merge_topk_kernel (0: accumulated in windows)
     uint32_t lane_max_terms = 0;                 // most terms of any lane-merge query of the staged batch
     uint32_t n_lane_items = 0;
+    int lane_ring_entries = 2048;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
+    int lane_ctas_per_sm = 0; // 0 = as many as fit; else an upper bound on the 4-warp CTAs of lane_merge_topk_kernel per SM
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
     // stats
     uint64_t launches = 0;
@@ -349,7 +351,18 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         return 0;
     }
     if (!std::strcmp(name, "lane_merge")) {
-        e->lane_merge = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail("lane_merge must be 0 (windows), 1 (staged rings) or 2 (global loads)");
+        e->lane_merge = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "lane_ring_entries")) {
+        if (value < 512 || value > 8192) return fail("lane_ring_entries must be in [512, 8192]");
+        e->lane_ring_entries = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "lane_ctas_per_sm")) {
+        if (value < 0 || value > 16) return fail("lane_ctas_per_sm must be in [0, 16]");
+        e->lane_ctas_per_sm = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "max_parts")) {
@@ -777,17 +790,31 @@ static int launch_fused(dgpu_engine* e, cudaStream_t stream) {
     return 0;
 }
 
-// lane_merge_topk_kernel for the smallest T that holds the longest query of the class
+// lane_merge_topk_kernel / staged_merge_topk_kernel for the smallest T that holds the longest query of the class
 template <int T>
 static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
-    auto kern = e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>;
     constexpr int threads = LaneMergeBounds<T>::kThreads;
     constexpr int wpc = threads / 32;
-    const size_t smem = e->plan_pool_global ? 0 : sizeof(uint64_t) * e->plan_cap * wpc;
+    const bool staged = e->lane_merge == 1;
+    auto kern = staged ? (e->need_cnt ? staged_merge_topk_kernel<T, true> : staged_merge_topk_kernel<T, false>)
+                       : (e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>);
+    const uint32_t cap_smem = e->plan_pool_global ? 0u : e->plan_cap;
+    size_t smem = sizeof(uint64_t) * cap_smem * wpc;
+    if (staged) {
+        uint32_t ring = 512;
+        while (ring < static_cast<uint32_t>(e->lane_ring_entries)) ring <<= 1;
+        L.W = ring;
+        L.warp_smem = static_cast<uint32_t>(staged_warp_smem_bytes(ring, cap_smem, T));
+        smem = static_cast<size_t>(L.warp_smem) * wpc;
+        if (smem > static_cast<size_t>(e->max_smem_optin))
+            return fail("staged_merge_topk_kernel needs %zu bytes of shared memory, device allows %d", smem, e->max_smem_optin);
+    }
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    if (per_sm < 1) return fail("lane_merge_topk_kernel does not fit an SM (%zu bytes of shared memory)", smem);
+    if (per_sm < 1) return fail("lane merge kernel does not fit an SM (%zu bytes of shared memory)", smem);
+    if (e->lane_ctas_per_sm) per_sm = std::min(per_sm, e->lane_ctas_per_sm);
     const uint64_t want_ctas = (static_cast<uint64_t>(L.n_items) + wpc - 1) / wpc;
     const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * per_sm, want_ctas));
     // a global pool (large k) was sized for 64 warps per SM by launch_batched; the kernels run one after the other

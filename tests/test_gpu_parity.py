@@ -68,25 +68,28 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
             assert np.isnan(td.maxScore)
 
 
-# (window_docs, stage_log2, splits, warps per CTA, warps per SM, intersect, lane_merge): small windows walk many windows
-# per query, stage_log2 = 1 pushes almost every term through the global-memory continuation, splits exercises doc-range
-# parts + the device merge, intersect = 0 sends the conjunctions through the counting windows instead of
-# intersect_topk_kernel, lane_merge = 0 sends the queries of <= 16 terms through the windows instead of
-# lane_merge_topk_kernel (with 1 the windows still score the longer queries of the file)
-_TUNINGS = [(0, 0, 0, 4, 16, 1, 0), (1024, 0, 1, 4, 16, 0, 0), (256, 1, 1, 8, 32, 1, 0), (4096, 2, 3, 2, 8, 0, 0),
-            (64, 3, 7, 1, 4, 1, 0), (2048, 0, 16, 4, 12, 1, 0), (0, 0, 0, 4, 20, 1, 1), (0, 0, 1, 4, 20, 0, 1),
-            (512, 0, 3, 4, 20, 0, 1), (0, 0, 16, 4, 20, 1, 1)]
+# (window_docs, stage_log2, splits, warps per CTA, warps per SM, intersect, lane_merge, lane_ring_entries): small windows
+# walk many windows per query, stage_log2 = 1 pushes almost every term through the global-memory continuation, splits
+# exercises doc-range parts + the device merge, intersect = 0 sends the conjunctions through the counting windows instead
+# of intersect_topk_kernel; lane_merge picks the kernel of the queries of <= 16 terms: 0 = accumulate_topk_kernel
+# (windows), 1 = staged_merge_topk_kernel (rings of lane_ring_entries entries per warp), 2 = lane_merge_topk_kernel
+# (global loads); with 1 and 2 the windows still score the longer queries of the file
+_TUNINGS = [(0, 0, 0, 4, 16, 1, 0, 1024), (1024, 0, 1, 4, 16, 0, 0, 1024), (256, 1, 1, 8, 32, 1, 0, 1024),
+            (4096, 2, 3, 2, 8, 0, 0, 1024), (64, 3, 7, 1, 4, 1, 0, 1024), (2048, 0, 16, 4, 12, 1, 0, 1024),
+            (0, 0, 0, 4, 20, 1, 1, 1024), (0, 0, 1, 4, 20, 0, 1, 512), (512, 0, 3, 4, 20, 0, 1, 2048),
+            (0, 0, 16, 4, 20, 1, 1, 4096), (0, 0, 0, 4, 20, 0, 2, 1024), (0, 0, 5, 4, 20, 1, 2, 1024)]
 
 
 @pytest.mark.parametrize("name", ["g1", "g2"])
-@pytest.mark.parametrize("window_docs,stage_log2,splits,warps,warps_per_sm,intersect,lane_merge", _TUNINGS)
+@pytest.mark.parametrize("window_docs,stage_log2,splits,warps,warps_per_sm,intersect,lane_merge,ring", _TUNINGS)
 def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, name, window_docs, stage_log2, splits, warps,
-                                                        warps_per_sm, intersect, lane_merge):
+                                                        warps_per_sm, intersect, lane_merge, ring):
     """dgpu_search_batch_text: the whole query file in one launch; the kernel a query is routed to, window size, staging
     depth, doc-range parts and the warp layout must not change any result."""
     r = readers[name]
     for opt, v in (("window_docs", window_docs), ("stage_log2", stage_log2), ("splits", splits), ("warps", warps),
-                   ("warps_per_sm", warps_per_sm), ("intersect", intersect), ("lane_merge", lane_merge)):
+                   ("warps_per_sm", warps_per_sm), ("intersect", intersect), ("lane_merge", lane_merge),
+                   ("lane_ring_entries", ring)):
         r.set_option(opt, v)
     try:
         searcher = dg.IndexSearcher(r)
@@ -107,7 +110,7 @@ def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, nam
                     assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {i}")
     finally:
         for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4), ("warps_per_sm", 20), ("intersect", 1),
-                       ("lane_merge", 1)):
+                       ("lane_merge", 1), ("lane_ring_entries", 1024)):
             r.set_option(opt, v)
 
 
