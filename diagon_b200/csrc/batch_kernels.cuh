@@ -288,6 +288,9 @@ __host__ __device__ inline size_t accum_warp_smem_bytes(uint32_t W, uint32_t cap
 __device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
@@ -948,8 +951,8 @@ lane_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
 // Lanes that walk private positions of T runs in global memory touch warps x 32 x T cache lines at once: neither L1
 // nor L2 can hold them at full occupancy and every 8-byte load costs a sector (measured: L1 hit 37 %, L2 hit 57 %,
 // 34 GB of DRAM reads for 30 GB of entries, IPC 0.9). Here the WARP streams every run of its query through a ring
-// in its slice of shared memory (coalesced 8-byte cp.async, issued one window ahead, capacities in proportion to
-// the run lengths) and walks the doc range window by window:
+// in its slice of shared memory (coalesced 16-byte cp.async, capacities in proportion to the run lengths) and walks
+// the doc range window by window:
 //   * a window is [smallest next doc, smallest last staged doc): every entry of every run below the window end is
 //     in shared memory;
 //   * the window is cut into 32 equal doc spans, one per lane; every lane bisects every ring for its span
@@ -1077,7 +1080,7 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             if (mine) {
                 const uint32_t room = cap - (fill - cur), rest = limit - fill;
                 n = min(room, rest);
-                if (n < (cap >> 1) && n != rest) n = 0;
+                if (n < (cap >> 2) && n != rest) n = 0;   // refill once a quarter of the ring is free: long windows
             }
             uint32_t need = __ballot_sync(0xFFFFFFFFu, n != 0u);
             while (need) {
@@ -1086,7 +1089,13 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 const uint32_t f = __shfl_sync(0xFFFFFFFFu, fill, tt), cnt = __shfl_sync(0xFFFFFFFFu, n, tt);
                 const uint32_t o = __shfl_sync(0xFFFFFFFFu, off, tt), msk = __shfl_sync(0xFFFFFFFFu, cap, tt) - 1u;
                 DGPU_ASSERT(static_cast<uint64_t>(f) + cnt <= P.run_total && o + msk < B);
-                for (uint32_t i = lane; i < cnt; i += 32) cp_async8(ring_s + 8u * (o + ((f + i) & msk)), runs + f + i);
+                // one entry to reach 16-byte alignment, then pairs of entries, then the odd one at the end
+                const uint32_t head = f & 1u & (cnt ? 1u : 0u), pairs = (cnt - head) >> 1, tail = (cnt - head) & 1u;
+                if (lane == 0 && head) cp_async8(ring_s + 8u * (o + (f & msk)), runs + f);
+                const uint32_t f2 = f + head;
+                for (uint32_t i = lane; i < pairs; i += 32)
+                    cp_async16(ring_s + 8u * (o + ((f2 + 2u * i) & msk)), runs + f2 + 2u * i);
+                if (lane == 31 && tail) cp_async8(ring_s + 8u * (o + ((f + cnt - 1u) & msk)), runs + f + cnt - 1u);
             }
             fill += n;
             cp_async_commit();
@@ -1121,24 +1130,44 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             if (ws >= hi) break;
             const uint32_t we = min(__reduce_min_sync(0xFFFFFFFFu, last), hi);
             DGPU_ASSERT(we > ws);
-            const uint32_t avail = fill - cur;   // complete in shared memory; what stage() adds now is for later windows
-            stage();
+            const uint32_t avail = fill - cur;
 
-            const uint32_t span = we - ws;
-            const uint32_t my_lo = ws + static_cast<uint32_t>((static_cast<uint64_t>(span) * lane) >> 5);
-            const uint32_t my_hi = ws + static_cast<uint32_t>((static_cast<uint64_t>(span) * (lane + 1)) >> 5);
+            // ---- lane spans: equal shares of the PIVOT ring (the one with the most staged entries) inside the window;
+            // lane l starts at the pivot's entry number l * n_in / 32 and ends where lane l + 1 starts
+            const uint32_t pivot_n = __reduce_max_sync(0xFFFFFFFFu, mine ? avail : 0u);
+            const int pivot = __ffs(__ballot_sync(0xFFFFFFFFu, mine && avail == pivot_n)) - 1;
+            const uint32_t pv_c = __shfl_sync(0xFFFFFFFFu, cur, pivot);
+            const uint32_t pv_base = ring_s + 8u * __shfl_sync(0xFFFFFFFFu, off, pivot);
+            const uint32_t pv_mask = 8u * __shfl_sync(0xFFFFFFFFu, cap, pivot) - 1u;
+            // entries of a ring below doc x among its n staged ones, given that the last one is not below x:
+            // branch-free bisection in byte units; the first probe folds the non-power-of-two part of n
+            auto ring_below8 = [&](uint32_t rbase, uint32_t rmask, uint32_t c, uint32_t n, uint32_t x) -> uint32_t {
+                const uint32_t pw = 1u << (31 - __clz(n));
+                uint32_t at = (c - 1u) << 3;   // byte position of "entry c - 1": at + 8 * q is the q-th staged entry
+                const uint32_t rem8 = (n - pw) << 3;
+                if (rem8 && lds32(rbase + ((at + rem8) & rmask)) < x) at += rem8;
+                for (uint32_t step8 = pw << 2; step8 >= 8u; step8 >>= 1) {
+                    const uint32_t q = at + step8;
+                    if (lds32(rbase + (q & rmask)) < x) at = q;
+                }
+                return at + 8u;   // byte position of the first entry >= x
+            };
+            const uint32_t pv_in8 = ring_below8(pv_base, pv_mask, pv_c, pivot_n, we) - (pv_c << 3);   // bytes inside the window
+            uint32_t my_lo = ws;
+            const uint32_t pv_mine8 = (pv_c << 3) + ((((pv_in8 >> 3) * static_cast<uint32_t>(lane)) >> 5) << 3);
+            if (lane) my_lo = min(lds32(pv_base + (pv_mine8 & pv_mask)), we);   // (the pivot may have nothing in the window)
+            uint32_t my_hi = __shfl_down_sync(0xFFFFFFFFu, my_lo, 1);
+            if (lane == 31) my_hi = we;
+            DGPU_ASSERT(my_lo >= ws && my_lo <= my_hi && my_hi <= we);
 
-            // ---- this lane's start in every ring: entries below my_lo among the staged ones (branch-free bisection)
+            // ---- this lane's start in every ring: the first staged entry >= my_lo
             uint32_t p8[T], hd[T], hs[T];
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 const uint32_t c = __shfl_sync(0xFFFFFFFFu, cur, t), n = __shfl_sync(0xFFFFFFFFu, avail, t);
-                uint32_t below = 0;
-                for (uint32_t step = n ? 1u << (31 - __clz(n)) : 0u; step; step >>= 1) {
-                    const uint32_t q = below + step;
-                    if (q <= n && lds32(base[t] + (((c + q - 1u) << 3) & bmask[t])) < my_lo) below = q;
-                }
-                p8[t] = (c + below) << 3;
+                p8[t] = 0;
+                if (t == pivot) p8[t] = pv_mine8;
+                else if (n) p8[t] = ring_below8(base[t], bmask[t], c, n, my_lo);
                 const uint2 e = lds64(base[t] + (p8[t] & bmask[t]));
                 hd[t] = e.x;
                 hs[t] = e.y;
@@ -1206,6 +1235,10 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 DGPU_ASSERT(adv < avail);
                 cur += adv;
             }
+            // refill what this window freed. The copy is waited for here: a window needs at least two staged entries
+            // of every live run to make progress, which only a refill that knows this window's consumption guarantees;
+            // the other warps of the SM cover the latency
+            stage();
             cp_async_wait_all();
             __syncwarp();
         }
