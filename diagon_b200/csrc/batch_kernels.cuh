@@ -979,22 +979,20 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
-template <int T>
-struct StagedMergeBounds {   // register budget: 5 words of state per term and lane
-    static constexpr int kMinCtas = T <= 6 ? 8 : (T <= 10 ? 6 : (T <= 12 ? 5 : 4));
-};
-
+// One warp per CTA: the ring area starts at the CTA's dynamic shared memory, a link-time constant, so the address of
+// a ring entry is ONE logic op (mask the cursor, or in the ring's offset: rings are laid out by decreasing size, each
+// aligned to its size relative to the area) and the constant folds into the load.
 template <int T, bool NEED_CNT>
-__global__ void __launch_bounds__(LaneMergeBounds<T>::kThreads, StagedMergeBounds<T>::kMinCtas)
+__global__ void __launch_bounds__(32, 16)
 staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t B = P.W;   // ring entries per warp (power of two)
-    uint8_t* sp = smem_raw + static_cast<size_t>(warp) * P.warp_smem;
-    const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(sp));
+    const int lane = threadIdx.x;
+    const uint32_t B = P.W;   // ring entries (multiple of 64)
+    uint8_t* sp = smem_raw;
+    const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
     uint2* ring = reinterpret_cast<uint2*>(sp);
     uint32_t* xch = reinterpret_cast<uint32_t*>(sp + sizeof(uint2) * (B + 1));
-    uint64_t* cand = P.pool ? P.pool + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * P.cand_cap
+    uint64_t* cand = P.pool ? P.pool + static_cast<size_t>(blockIdx.x) * P.cand_cap
                             : reinterpret_cast<uint64_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * T + 7) & ~7u));
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint2* __restrict__ runs = P.runs;
@@ -1002,11 +1000,11 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
     __syncwarp();
 
     for (;;) {
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(P.work_counter, 1u);
-        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-        if (slot >= P.n_items) break;
-        const uint32_t item = P.order[slot];
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(P.work_counter, 1u);
+        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+        if (ticket >= P.n_items) break;
+        const uint32_t item = P.order[ticket];
         const WorkItem wi = P.items[item];
         const dgpu_query qd = P.queries[wi.query];
         const QTermRun* qt = P.terms + qd.term_begin;
@@ -1063,16 +1061,22 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 used += __shfl_sync(0xFFFFFFFFu, cap, who);
                 if (lane == who) cap <<= 1;
             }
-            const uint32_t c = mine ? cap : 0u;
-            const uint32_t incl = warp_inclusive_scan(c, lane);
-            if (mine) off = incl - c;
+            // rings by decreasing capacity (ties by term): every ring starts at a multiple of its own size
+            uint32_t before = 0;
+            for (uint32_t u = 0; u < nt; ++u) {
+                const uint32_t cu = __shfl_sync(0xFFFFFFFFu, cap, u);
+                if (cu > cap || (cu == cap && u < static_cast<uint32_t>(lane))) before += cu;
+            }
+            if (mine) off = before;
+            DGPU_ASSERT(!mine || ((off & (cap - 1u)) == 0u && off + cap <= B));
         }
-        uint32_t base[T], bmask[T];   // ring of term t: shared-memory byte address, byte mask (unused slots: the end entry)
+        uint32_t roff[T], bmask[T];   // ring of term t: byte offset in the ring area, byte mask (unused slots: the end entry)
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            base[t] = ring_s + 8u * __shfl_sync(0xFFFFFFFFu, off, t);
+            roff[t] = 8u * __shfl_sync(0xFFFFFFFFu, off, t);
             bmask[t] = 8u * __shfl_sync(0xFFFFFFFFu, cap, t) - 1u;
         }
+        auto slot = [&](uint32_t at8, uint32_t rmask, uint32_t ro) -> uint32_t { return ring_s + ((at8 & rmask) | ro); };
 
         // copies the next entries of every run whose ring is at least half free (or that is about to end)
         auto stage = [&]() {
@@ -1103,6 +1107,7 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
 
         uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
         uint64_t thresh = 0;        // key of the k-th best so far
+        float thresh_f = __uint_as_float(0xFF800000u);   // its score (-inf until there is one): the merge loop's quick test
         uint32_t hits = 0;          // per lane
         auto prune = [&]() {
             const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
@@ -1111,6 +1116,8 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             if (n_cand >= static_cast<uint32_t>(P.k)) {
                 thresh = cand[P.k - 1];
                 n_cand = P.k;
+                const uint32_t o = static_cast<uint32_t>(thresh >> 32);
+                thresh_f = __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
             }
         };
 
@@ -1137,25 +1144,25 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             const uint32_t pivot_n = __reduce_max_sync(0xFFFFFFFFu, mine ? avail : 0u);
             const int pivot = __ffs(__ballot_sync(0xFFFFFFFFu, mine && avail == pivot_n)) - 1;
             const uint32_t pv_c = __shfl_sync(0xFFFFFFFFu, cur, pivot);
-            const uint32_t pv_base = ring_s + 8u * __shfl_sync(0xFFFFFFFFu, off, pivot);
+            const uint32_t pv_off = 8u * __shfl_sync(0xFFFFFFFFu, off, pivot);
             const uint32_t pv_mask = 8u * __shfl_sync(0xFFFFFFFFu, cap, pivot) - 1u;
             // entries of a ring below doc x among its n staged ones, given that the last one is not below x:
             // branch-free bisection in byte units; the first probe folds the non-power-of-two part of n
-            auto ring_below8 = [&](uint32_t rbase, uint32_t rmask, uint32_t c, uint32_t n, uint32_t x) -> uint32_t {
+            auto ring_below8 = [&](uint32_t ro, uint32_t rmask, uint32_t c, uint32_t n, uint32_t x) -> uint32_t {
                 const uint32_t pw = 1u << (31 - __clz(n));
                 uint32_t at = (c - 1u) << 3;   // byte position of "entry c - 1": at + 8 * q is the q-th staged entry
                 const uint32_t rem8 = (n - pw) << 3;
-                if (rem8 && lds32(rbase + ((at + rem8) & rmask)) < x) at += rem8;
+                if (rem8 && lds32(slot(at + rem8, rmask, ro)) < x) at += rem8;
                 for (uint32_t step8 = pw << 2; step8 >= 8u; step8 >>= 1) {
                     const uint32_t q = at + step8;
-                    if (lds32(rbase + (q & rmask)) < x) at = q;
+                    if (lds32(slot(q, rmask, ro)) < x) at = q;
                 }
                 return at + 8u;   // byte position of the first entry >= x
             };
-            const uint32_t pv_in8 = ring_below8(pv_base, pv_mask, pv_c, pivot_n, we) - (pv_c << 3);   // bytes inside the window
+            const uint32_t pv_in8 = ring_below8(pv_off, pv_mask, pv_c, pivot_n, we) - (pv_c << 3);   // bytes inside the window
             uint32_t my_lo = ws;
             const uint32_t pv_mine8 = (pv_c << 3) + ((((pv_in8 >> 3) * static_cast<uint32_t>(lane)) >> 5) << 3);
-            if (lane) my_lo = min(lds32(pv_base + (pv_mine8 & pv_mask)), we);   // (the pivot may have nothing in the window)
+            if (lane) my_lo = min(lds32(slot(pv_mine8, pv_mask, pv_off)), we);   // (the pivot may have nothing in the window)
             uint32_t my_hi = __shfl_down_sync(0xFFFFFFFFu, my_lo, 1);
             if (lane == 31) my_hi = we;
             DGPU_ASSERT(my_lo >= ws && my_lo <= my_hi && my_hi <= we);
@@ -1167,8 +1174,8 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 const uint32_t c = __shfl_sync(0xFFFFFFFFu, cur, t), n = __shfl_sync(0xFFFFFFFFu, avail, t);
                 p8[t] = 0;
                 if (t == pivot) p8[t] = pv_mine8;
-                else if (n) p8[t] = ring_below8(base[t], bmask[t], c, n, my_lo);
-                const uint2 e = lds64(base[t] + (p8[t] & bmask[t]));
+                else if (n) p8[t] = ring_below8(roff[t], bmask[t], c, n, my_lo);
+                const uint2 e = lds64(slot(p8[t], bmask[t], roff[t]));
                 hd[t] = e.x;
                 hs[t] = e.y;
             }
@@ -1193,7 +1200,7 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                             ++c;
                         }
                         p8[t] += 8u;
-                        const uint2 e = lds64(base[t] + (p8[t] & bmask[t]));
+                        const uint2 e = lds64(slot(p8[t], bmask[t], roff[t]));
                         hd[t] = e.x;
                         hs[t] = e.y;
                     }
@@ -1208,13 +1215,16 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                     }
                 }
                 hits += match ? 1u : 0u;
-                const uint32_t sb = __float_as_uint(score);
-                const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
-                const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - m);
-                // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
-                const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
-                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
+                // quick test on the score alone: a superset of "key > thresh" (ties and -0.0f are settled by the key
+                // compare below; a NaN score fails it, and NaN is never collected)
+                const bool maybe = match && score >= thresh_f;
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, maybe);
                 if (pm) {
+                    const uint32_t sb = __float_as_uint(score);
+                    const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+                    const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - m);
+                    // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
+                    const bool push = maybe && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
                     if (n_cand + 32u > P.cand_cap) prune();
                     const bool still = push && key > thresh;   // the prune may have raised the threshold
                     const uint32_t sm = __ballot_sync(0xFFFFFFFFu, still);

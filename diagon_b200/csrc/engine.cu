@@ -183,8 +183,8 @@ struct dgpu_engine {
     int lane_merge = 1;      // queries of <= 16 terms go to lane_merge_topk_kernel (0: accumulated in windows)
     uint32_t lane_max_terms = 0;                 // most terms of any lane-merge query of the staged batch
     uint32_t n_lane_items = 0;
-    int lane_ring_entries = 2048;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
-    int lane_ctas_per_sm = 0; // 0 = as many as fit; else an upper bound on the 4-warp CTAs of lane_merge_topk_kernel per SM
+    int lane_ring_entries = 2304;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
+    int lane_ctas_per_sm = 0; // 0 = as many as fit; else an upper bound on the CTAs per SM of the lane merge kernels
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
     // stats
     uint64_t launches = 0;
@@ -793,16 +793,15 @@ static int launch_fused(dgpu_engine* e, cudaStream_t stream) {
 // lane_merge_topk_kernel / staged_merge_topk_kernel for the smallest T that holds the longest query of the class
 template <int T>
 static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
-    constexpr int threads = LaneMergeBounds<T>::kThreads;
-    constexpr int wpc = threads / 32;
     const bool staged = e->lane_merge == 1;
+    const int wpc = staged ? 1 : LaneMergeBounds<T>::kThreads / 32;   // warps per CTA
+    const int threads = 32 * wpc;
     auto kern = staged ? (e->need_cnt ? staged_merge_topk_kernel<T, true> : staged_merge_topk_kernel<T, false>)
                        : (e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>);
     const uint32_t cap_smem = e->plan_pool_global ? 0u : e->plan_cap;
     size_t smem = sizeof(uint64_t) * cap_smem * wpc;
     if (staged) {
-        uint32_t ring = 512;
-        while (ring < static_cast<uint32_t>(e->lane_ring_entries)) ring <<= 1;
+        const uint32_t ring = static_cast<uint32_t>(e->lane_ring_entries) & ~63u;
         L.W = ring;
         L.warp_smem = static_cast<uint32_t>(staged_warp_smem_bytes(ring, cap_smem, T));
         smem = static_cast<size_t>(L.warp_smem) * wpc;
