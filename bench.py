@@ -264,6 +264,17 @@ def reference_arm(args, corpus_name, log_name, kind, k, steps, warmup, full):
 
 
 # ------------------------------------------------------------------------------------------------ main
+def lane_kernel_name(bstats):
+    return "staged_merge_topk_kernel" if int(bstats[11]) == 1 else "lane_merge_topk_kernel"
+
+
+def dominant_kernel(bstats):
+    """The scoring kernel most work items of the batch went to (they run one after the other in phase [1])."""
+    items = {"accumulate_topk_kernel": int(bstats[6]), "intersect_topk_kernel": int(bstats[7]),
+             lane_kernel_name(bstats): int(bstats[10])}
+    return max(items, key=items.get)
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -430,7 +441,7 @@ def main():
         ph = (C.c_float * 3)()
         lib.dgpu_engine_last_phase_ms(eng, C.byref(ph))
         phase_ms.append([float(x) for x in ph])
-    bstats = (C.c_uint64 * 10)()
+    bstats = (C.c_uint64 * 16)()
     lib.dgpu_engine_batch_stats(eng, C.byref(bstats))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -504,19 +515,21 @@ def main():
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         if tj["workload"] == args.workload and args.scale == 1.0 and not args.queries and world == 1 and batched \
-                and tj["kernel"] == "accumulate_topk_kernel":
+                and tj["kernel"] == dominant_kernel(bstats):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel": ("intersect_topk_kernel" if int(bstats[7]) > int(bstats[6]) else "accumulate_topk_kernel") if batched else "search_kernel",
+                "kernel": dominant_kernel(bstats) if batched else "search_kernel",
                 "kernel_ms": float(kt[0]), "algorithmic_bytes_per_launch": stats["algorithmic_bytes"],
                 "postings_per_launch": stats["postings"],
                 "postings_per_s": stats["postings"] / (float(kt[0]) / 1e3),
-                "step_ms_by_kernel": {"decode_score_kernel": med[0], "accumulate_topk_kernel+intersect_topk_kernel": med[1],
-                                      "merge_items_kernel": med[2]},
-                "work_items": {"accumulate_topk_kernel": int(bstats[6]), "intersect_topk_kernel": int(bstats[7])}}
+                "step_ms_by_kernel": {"decode_score_kernel": med[0], "scoring_kernels": med[1], "merge_items_kernel": med[2]},
+                "work_items": {"accumulate_topk_kernel": int(bstats[6]), "intersect_topk_kernel": int(bstats[7]),
+                               lane_kernel_name(bstats): int(bstats[10])}}
+    if batched and int(bstats[10]) and int(bstats[11]) == 1:
+        roofline["ring_entries_per_warp"] = int(bstats[12])
     if batched and med[0] > 0:
         # K1 alone: reads the compressed blocks of the distinct terms once, writes 8 B per decoded posting slot
         rd, wr = int(bstats[4]), int(bstats[2]) * 8

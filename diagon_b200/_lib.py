@@ -119,7 +119,7 @@ PROTOTYPES = {
     "dgpu_engine_last_search_ms": (C.c_float, [C.c_void_p]),
     "dgpu_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "dgpu_engine_last_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3)]),
-    "dgpu_engine_batch_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 10)]),
+    "dgpu_engine_batch_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 16)]),
 }
 
 _lib = None

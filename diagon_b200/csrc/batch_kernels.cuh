@@ -982,9 +982,17 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 // One warp per CTA: the ring area starts at the CTA's dynamic shared memory, a link-time constant, so the address of
 // a ring entry is ONE logic op (mask the cursor, or in the ring's offset: rings are laid out by decreasing size, each
 // aligned to its size relative to the area) and the constant folds into the load.
-template <int T, bool NEED_CNT>
+//
+// MODE 0: plain disjunctions / term queries (every merged doc is a hit); 1: required-match counts and exclusions;
+// 2: 1 + doc-value range filters. In mode 2 the filter value of a doc is loaded when the doc is merged and tested
+// kFilterDepth iterations later, together with the collection of that doc, so the load's latency (an L2 hit at best:
+// the column is read at random) hides behind the next merge step (measured on C4: depth 1 beats 0 by 10 %, 3 is slower).
+constexpr int kFilterDepth = 1;
+template <int T, int MODE>
 __global__ void __launch_bounds__(32, 16)
 staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
+    constexpr bool NEED_CNT = MODE >= 1;
+    constexpr bool FILTER = MODE == 2;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x;
     const uint32_t B = P.W;   // ring entries (multiple of 64)
@@ -1009,8 +1017,27 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
         const dgpu_query qd = P.queries[wi.query];
         const QTermRun* qt = P.terms + qd.term_begin;
         const uint32_t nt = qd.term_end - qd.term_begin;   // <= T
-        const uint32_t nf = qd.filter_end - qd.filter_begin;
+        const uint32_t nf = FILTER ? qd.filter_end - qd.filter_begin : 0u;
         const dgpu_qfilter* qf = P.filters + qd.filter_begin;
+        const int64_t* dv0 = nullptr;   // first range filter of the query: column, bounds
+        int64_t lo0 = 0, hi0 = 0;
+        if (FILTER && nf) {
+            dv0 = ix.dv[qf[0].column] - ix.doc_lo;
+            lo0 = qf[0].lo;
+            hi0 = qf[0].hi;
+        }
+        // mode 2: the last kFilterDepth docs this lane merged, waiting for their filter values ([0] is the oldest)
+        uint32_t pend_doc[kFilterDepth];
+        float pend_score[kFilterDepth];
+        int64_t pend_val[kFilterDepth];
+        bool pend[kFilterDepth];
+#pragma unroll
+        for (int d = 0; d < kFilterDepth; ++d) {
+            pend_doc[d] = 0;
+            pend_score[d] = 0.0f;
+            pend_val[d] = 0;
+            pend[d] = false;
+        }
         const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
         DGPU_ASSERT(nt <= static_cast<uint32_t>(T));
         const bool mine = static_cast<uint32_t>(lane) < nt;
@@ -1121,6 +1148,47 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             }
         };
 
+        // warp-collective: counts the hit and offers it to the pool
+        auto collect = [&](uint32_t doc, float score, bool match) {
+            hits += match ? 1u : 0u;
+            // quick test on the score alone: a superset of "key > thresh" (ties and -0.0f are settled by the key
+            // compare below; a NaN score fails it, and NaN is never collected)
+            const bool maybe = match && score >= thresh_f;
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, maybe);
+            if (pm) {
+                const uint32_t sb = __float_as_uint(score);
+                const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+                const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
+                // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
+                const bool push = maybe && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+                if (n_cand + 32u > P.cand_cap) prune();
+                const bool still = push && key > thresh;   // the prune may have raised the threshold
+                const uint32_t sm = __ballot_sync(0xFFFFFFFFu, still);
+                if (still) cand[n_cand + __popc(sm & lt_mask)] = key;
+                n_cand += __popc(sm);
+            }
+        };
+        // mode 2: the oldest pending doc of this lane against its filters (its first value was loaded kFilterDepth
+        // iterations ago), then the queue moves up
+        auto collect_pending = [&]() {
+            bool ok = pend[0] && pend_val[0] >= lo0 && pend_val[0] <= hi0;
+            float sc = __fadd_rn(pend_score[0], 1.0f);   // constant score of the range clause (NumericRangeQuery.cpp:117-120)
+            for (uint32_t f = 1; f < nf && ok; ++f) {
+                const int64_t val = ix.dv[qf[f].column][pend_doc[0] - ix.doc_lo];
+                ok = (val >= qf[f].lo) && (val <= qf[f].hi);
+                sc = __fadd_rn(sc, 1.0f);
+            }
+            collect(pend_doc[0], sc, ok);
+#pragma unroll
+            for (int d = 0; d + 1 < kFilterDepth; ++d) {
+                pend_doc[d] = pend_doc[d + 1];
+                pend_score[d] = pend_score[d + 1];
+                pend_val[d] = pend_val[d + 1];
+                pend[d] = pend[d + 1];
+            }
+            pend[kFilterDepth - 1] = false;
+        };
+
         __syncwarp();
         stage();
         cp_async_wait_all();
@@ -1207,29 +1275,16 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 }
                 bool match = act;
                 if (NEED_CNT) match = act && !excluded && c != 0 && (qd.n_must ? c == qd.n_must : c >= qd.min_should_match);
-                if (nf) {
-                    for (uint32_t f = 0; f < nf && match; ++f) {
-                        const int64_t val = ix.dv[qf[f].column][m - ix.doc_lo];
-                        match = (val >= qf[f].lo) && (val <= qf[f].hi);
-                        score = __fadd_rn(score, 1.0f);  // constant score of the range clause (NumericRangeQuery.cpp:117-120)
-                    }
-                }
-                hits += match ? 1u : 0u;
-                // quick test on the score alone: a superset of "key > thresh" (ties and -0.0f are settled by the key
-                // compare below; a NaN score fails it, and NaN is never collected)
-                const bool maybe = match && score >= thresh_f;
-                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, maybe);
-                if (pm) {
-                    const uint32_t sb = __float_as_uint(score);
-                    const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
-                    const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - m);
-                    // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
-                    const bool push = maybe && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
-                    if (n_cand + 32u > P.cand_cap) prune();
-                    const bool still = push && key > thresh;   // the prune may have raised the threshold
-                    const uint32_t sm = __ballot_sync(0xFFFFFFFFu, still);
-                    if (still) cand[n_cand + __popc(sm & lt_mask)] = key;
-                    n_cand += __popc(sm);
+                if (FILTER && nf) {
+                    int64_t v = 0;
+                    if (match) v = dv0[m];
+                    collect_pending();
+                    pend_doc[kFilterDepth - 1] = m;
+                    pend_score[kFilterDepth - 1] = score;
+                    pend_val[kFilterDepth - 1] = v;
+                    pend[kFilterDepth - 1] = match;
+                } else {
+                    collect(m, score, match);
                 }
             }
 
@@ -1255,6 +1310,9 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
 
         // ---- final select
         __syncwarp();
+        if (FILTER && nf) {
+            for (int d = 0; d < kFilterDepth; ++d) collect_pending();
+        }
         hits = __reduce_add_sync(0xFFFFFFFFu, hits);
         const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
         for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;

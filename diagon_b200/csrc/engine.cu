@@ -183,6 +183,7 @@ struct dgpu_engine {
     int lane_merge = 1;      // queries of <= 16 terms go to lane_merge_topk_kernel (0: accumulated in windows)
     uint32_t lane_max_terms = 0;                 // most terms of any lane-merge query of the staged batch
     uint32_t n_lane_items = 0;
+    uint32_t batch_filters = 0;                  // range filters of the staged batch
     int lane_ring_entries = 2304;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
     int lane_ctas_per_sm = 0; // 0 = as many as fit; else an upper bound on the CTAs per SM of the lane merge kernels
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
@@ -459,6 +460,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     if (k > DGPU_MAX_K) return fail("numHits %d exceeds DGPU_MAX_K", k);
     e->n_queries = b->n_queries;
     e->k = k;
+    e->batch_filters = b->n_filters;
     static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
     auto tr0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -796,7 +798,8 @@ static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stre
     const bool staged = e->lane_merge == 1;
     const int wpc = staged ? 1 : LaneMergeBounds<T>::kThreads / 32;   // warps per CTA
     const int threads = 32 * wpc;
-    auto kern = staged ? (e->need_cnt ? staged_merge_topk_kernel<T, true> : staged_merge_topk_kernel<T, false>)
+    auto kern = staged ? (e->batch_filters ? staged_merge_topk_kernel<T, 2>
+                                           : (e->need_cnt ? staged_merge_topk_kernel<T, 1> : staged_merge_topk_kernel<T, 0>))
                        : (e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>);
     const uint32_t cap_smem = e->plan_pool_global ? 0u : e->plan_cap;
     size_t smem = sizeof(uint64_t) * cap_smem * wpc;
@@ -978,7 +981,7 @@ int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]) {
     return 0;
 }
 
-int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[10]) {
+int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[16]) {
     out[0] = e->n_dterms;
     out[1] = e->n_ditems;
     out[2] = e->run_entries;
@@ -994,6 +997,10 @@ int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[10]) {
     out[7] = e->n_and_items;
     out[8] = e->h2d_bytes;
     out[9] = static_cast<uint64_t>(e->n_queries) * (static_cast<uint64_t>(e->k) * 8 + 12);   // keys + count + hits
+    out[10] = e->n_lane_items;
+    out[11] = static_cast<uint64_t>(e->lane_merge);
+    out[12] = static_cast<uint64_t>(e->lane_ring_entries) & ~63ull;
+    out[13] = out[14] = out[15] = 0;
     return 0;
 }
 

@@ -151,14 +151,17 @@ uint64_t dgpu_engine_launch_count(const dgpu_engine* e);
 float dgpu_engine_last_search_ms(const dgpu_engine* e);
 /* Device time (ms) of the phases of the last search: [0] decode_score_kernel (every distinct term of the batch
  * decoded and scored once), [1] accumulate_topk_kernel + intersect_topk_kernel (whichever the batch needs),
- * [2] merge of doc-range parts (0 when no query was split). */
+ * [2] merge of doc-range parts (0 when no query was split). Phase [1] also covers staged_merge_topk_kernel /
+ * lane_merge_topk_kernel, which score the queries of up to 16 terms. */
 int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]);
 /* Shape of the staged batch: [0] distinct terms, [1] decode work items, [2] (doc, score) entries of the decode
  * scratch, [3] mean doc-range parts per query, [4] compressed bytes of the distinct terms (what decode_score_kernel
  * reads), [5] docs per window of accumulate_topk_kernel, [6] work items of accumulate_topk_kernel, [7] work items
  * of intersect_topk_kernel (pure conjunctions), [8] host-to-device bytes of the staged descriptors, [9] device-to-host
- * bytes of one result fetch. */
-int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[10]);
+ * bytes of one result fetch, [10] work items of the document-at-a-time merge kernel (queries of <= 16 terms),
+ * [11] which one that is: 1 = staged_merge_topk_kernel, 2 = lane_merge_topk_kernel, [12] ring entries per warp of
+ * staged_merge_topk_kernel, [13..15] reserved (0). */
+int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[16]);
 
 /* Tunables. Returns 0 or -1 for an unknown name / bad value. */
 int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value);
