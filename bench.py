@@ -73,6 +73,7 @@ def parse_args():
     ap.add_argument("--kernel", type=int, default=0, help="3 = batched decode_score + accumulate_topk (default), 2 = fused windows")
     ap.add_argument("--lane-merge", type=int, default=-1, help="1 = queries of <= 16 terms on lane_merge_topk_kernel (default), 0 = windows")
     ap.add_argument("--lane-ctas-per-sm", type=int, default=0)
+    ap.add_argument("--pool-smem-cap", type=int, default=0)
     ap.add_argument("--lane-ring-entries", type=int, default=0)
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
@@ -356,6 +357,8 @@ def main():
         reader.set_option("lane_merge", args.lane_merge)
     if args.lane_ring_entries:
         reader.set_option("lane_ring_entries", args.lane_ring_entries)
+    if args.pool_smem_cap:
+        reader.set_option("pool_smem_cap", args.pool_smem_cap)
     if args.lane_ctas_per_sm:
         reader.set_option("lane_ctas_per_sm", args.lane_ctas_per_sm)
     if world > 1:

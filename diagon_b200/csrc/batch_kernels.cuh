@@ -30,7 +30,8 @@ constexpr int kItemBlocks = 64;             // posting blocks per decode work it
 constexpr int kPadBlocks = 1;               // kDocEnd blocks after every run: readers look at most 64 entries past a real one
 constexpr int kRunPad = kPadBlocks * DGPU_BLOCK_POSTINGS;  // scratch[0, kRunPad) is the empty run
 constexpr int kDecodeThreads = 256;
-constexpr uint32_t kLaneMergeMaxTerms = 16; // queries of up to this many terms are merged document-at-a-time by lanes
+constexpr uint32_t kLaneMergeMaxTerms = 16;   // lane_merge_topk_kernel: queries of up to this many terms
+constexpr uint32_t kStagedMergeMaxTerms = 32; // staged_merge_topk_kernel (one lane per term holds the stream state)
 
 struct DTerm {          // one distinct (term, idf, field) of the batch
     uint32_t term_id;
@@ -989,7 +990,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 // the column is read at random) hides behind the next merge step (measured on C4: depth 1 beats 0 by 10 %, 3 is slower).
 constexpr int kFilterDepth = 1;
 template <int T, int MODE>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, T <= 16 ? 16 : 8)   // 128 registers up to 16 terms, 255 beyond (5 words per term)
 staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
     constexpr bool NEED_CNT = MODE >= 1;
     constexpr bool FILTER = MODE == 2;

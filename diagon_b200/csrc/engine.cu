@@ -185,6 +185,7 @@ struct dgpu_engine {
     uint32_t n_lane_items = 0;
     uint32_t batch_filters = 0;                  // range filters of the staged batch
     int lane_ring_entries = 2304;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
+    int pool_smem_cap = 256;        // candidate pools of up to this many keys live in shared memory, larger ones in global
     int lane_ctas_per_sm = 0; // 0 = as many as fit; else an upper bound on the CTAs per SM of the lane merge kernels
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
     // stats
@@ -215,7 +216,7 @@ static int plan_batched(dgpu_engine* e) {
     if (e->stage_log2) chlog = std::min<uint32_t>(chlog, static_cast<uint32_t>(e->stage_log2));
     const uint32_t list_cap = 512;
     const size_t per_doc = e->need_cnt ? 5 : 4;
-    const bool pool_global = cap > 256;   // top-k beyond 128: the pool goes to global memory (pushes are rare once warm)
+    const bool pool_global = cap > static_cast<uint32_t>(e->pool_smem_cap);   // large top-k: the pool goes to global memory
     const uint32_t cap_smem = pool_global ? 0u : cap;
     const size_t fixed = accum_warp_smem_bytes(0, cap_smem, max_terms, chlog, list_cap, e->need_cnt);
     const size_t per_sm = 227 * 1024;
@@ -361,6 +362,11 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->lane_ring_entries = static_cast<int>(value);
         return 0;
     }
+    if (!std::strcmp(name, "pool_smem_cap")) {
+        if (value < 64 || value > 8192) return fail("pool_smem_cap must be in [64, 8192]");
+        e->pool_smem_cap = static_cast<int>(value);
+        return 0;
+    }
     if (!std::strcmp(name, "lane_ctas_per_sm")) {
         if (value < 0 || value > 16) return fail("lane_ctas_per_sm must be in [0, 16]");
         e->lane_ctas_per_sm = static_cast<int>(value);
@@ -498,7 +504,8 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             bool all_must = e->kernel == 3 && e->intersect && nt_q >= 2 && nt_q <= 32 && qd.n_must == nt_q;
             for (uint32_t t = qd.term_begin; all_must && t < qd.term_end; ++t) all_must = b->terms[t].role == DGPU_ROLE_MUST;
             // class of the query: 2 = intersected, 1 = merged document-at-a-time by lanes, 0 = accumulated in windows
-            const bool lane = !all_must && e->kernel == 3 && e->lane_merge && nt_q <= kLaneMergeMaxTerms;
+            const bool lane = !all_must && e->kernel == 3 && e->lane_merge &&
+                              nt_q <= (e->lane_merge == 1 ? kStagedMergeMaxTerms : kLaneMergeMaxTerms);
             is_and[q] = all_must ? 2 : (lane ? 1 : 0);
             if (!all_must) {
                 if (lane) pt.lane_max_terms = std::max(pt.lane_max_terms, nt_q);
@@ -792,15 +799,10 @@ static int launch_fused(dgpu_engine* e, cudaStream_t stream) {
     return 0;
 }
 
-// lane_merge_topk_kernel / staged_merge_topk_kernel for the smallest T that holds the longest query of the class
-template <int T>
-static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
-    const bool staged = e->lane_merge == 1;
-    const int wpc = staged ? 1 : LaneMergeBounds<T>::kThreads / 32;   // warps per CTA
+// the document-at-a-time merge kernels are instantiated for the smallest T that holds the longest query of the class
+template <class Kern>
+static int launch_merge_kernel(dgpu_engine* e, AccumParams& L, cudaStream_t stream, Kern kern, int wpc, int T, bool staged) {
     const int threads = 32 * wpc;
-    auto kern = staged ? (e->batch_filters ? staged_merge_topk_kernel<T, 2>
-                                           : (e->need_cnt ? staged_merge_topk_kernel<T, 1> : staged_merge_topk_kernel<T, 0>))
-                       : (e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>);
     const uint32_t cap_smem = e->plan_pool_global ? 0u : e->plan_cap;
     size_t smem = sizeof(uint64_t) * cap_smem * wpc;
     if (staged) {
@@ -826,6 +828,20 @@ static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stre
     return 0;
 }
 
+template <int T>
+static int launch_staged_only_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
+    auto kern = e->batch_filters ? staged_merge_topk_kernel<T, 2>
+                                 : (e->need_cnt ? staged_merge_topk_kernel<T, 1> : staged_merge_topk_kernel<T, 0>);
+    return launch_merge_kernel(e, L, stream, kern, 1, T, true);
+}
+
+template <int T>
+static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
+    if (e->lane_merge == 1) return launch_staged_only_t<T>(e, L, stream);
+    auto kern = e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>;
+    return launch_merge_kernel(e, L, stream, kern, LaneMergeBounds<T>::kThreads / 32, T, false);
+}
+
 static int launch_lane_merge(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
     const uint32_t nt = e->lane_max_terms;
     if (nt <= 2) return launch_lane_merge_t<2>(e, L, stream);
@@ -834,7 +850,10 @@ static int launch_lane_merge(dgpu_engine* e, AccumParams& L, cudaStream_t stream
     if (nt <= 8) return launch_lane_merge_t<8>(e, L, stream);
     if (nt <= 10) return launch_lane_merge_t<10>(e, L, stream);
     if (nt <= 12) return launch_lane_merge_t<12>(e, L, stream);
-    return launch_lane_merge_t<16>(e, L, stream);
+    if (nt <= 16) return launch_lane_merge_t<16>(e, L, stream);
+    if (nt <= 20) return launch_staged_only_t<20>(e, L, stream);
+    if (nt <= 24) return launch_staged_only_t<24>(e, L, stream);
+    return launch_staged_only_t<32>(e, L, stream);
 }
 
 // kernel = 3: decode + score every distinct term of the batch once, then accumulate + top-k, one warp per item
