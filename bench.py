@@ -71,7 +71,7 @@ def parse_args():
     ap.add_argument("--decode-ctas-per-sm", type=int, default=0)
     ap.add_argument("--part-factor", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="3 = batched decode_score + accumulate_topk (default), 2 = fused windows")
-    ap.add_argument("--lane-merge", type=int, default=-1, help="1 = queries of <= 16 terms on lane_merge_topk_kernel (default), 0 = windows")
+    ap.add_argument("--lane-merge", type=int, default=-1, help="1 = queries of <= 32 terms on staged_merge_topk_kernel (default), 2 = <= 16 terms on lane_merge_topk_kernel, 0 = windows")
     ap.add_argument("--lane-ctas-per-sm", type=int, default=0)
     ap.add_argument("--pool-smem-cap", type=int, default=0)
     ap.add_argument("--lane-ring-entries", type=int, default=0)

@@ -71,7 +71,7 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
 # (window_docs, stage_log2, splits, warps per CTA, warps per SM, intersect, lane_merge, lane_ring_entries): small windows
 # walk many windows per query, stage_log2 = 1 pushes almost every term through the global-memory continuation, splits
 # exercises doc-range parts + the device merge, intersect = 0 sends the conjunctions through the counting windows instead
-# of intersect_topk_kernel; lane_merge picks the kernel of the queries of <= 16 terms: 0 = accumulate_topk_kernel
+# of intersect_topk_kernel; lane_merge picks the kernel of the shorter queries (<= 32 terms staged, <= 16 global): 0 = accumulate_topk_kernel
 # (windows), 1 = staged_merge_topk_kernel (rings of lane_ring_entries entries per warp), 2 = lane_merge_topk_kernel
 # (global loads); with 1 and 2 the windows still score the longer queries of the file
 _TUNINGS = [(0, 0, 0, 4, 16, 1, 0, 1024), (1024, 0, 1, 4, 16, 0, 0, 1024), (256, 1, 1, 8, 32, 1, 0, 1024),
