@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--lane-merge", type=int, default=-1, help="1 = queries of <= 32 terms on staged_merge_topk_kernel (default), 2 = <= 16 terms on lane_merge_topk_kernel, 0 = windows")
     ap.add_argument("--lane-ctas-per-sm", type=int, default=0)
     ap.add_argument("--pool-smem-cap", type=int, default=0)
+    ap.add_argument("--pipeline-chunks", type=int, default=0, help="chunks of the end-to-end text call (1 = no host/device overlap)")
     ap.add_argument("--lane-ring-entries", type=int, default=0)
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
@@ -357,6 +358,8 @@ def main():
         reader.set_option("lane_merge", args.lane_merge)
     if args.lane_ring_entries:
         reader.set_option("lane_ring_entries", args.lane_ring_entries)
+    if args.pipeline_chunks:
+        reader.set_option("pipeline_chunks", args.pipeline_chunks)
     if args.pool_smem_cap:
         reader.set_option("pool_smem_cap", args.pool_smem_cap)
     if args.lane_ctas_per_sm:
@@ -559,7 +562,8 @@ def main():
                        "kernel_path": "batched" if batched else "fused-windows"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "call": ("dgpu_search_batch_text (host text -> host results)" if world == 1 else
+                    "call": ("dgpu_search_batch_text (host text -> host results; the batch is cut into chunks, chunk i + 1 is parsed, "
+                             "compiled and staged on a second engine while the kernels of chunk i run)" if world == 1 else
                              "per rank: dgpu_compile_batch_text on 1/N of the lines, gloo all_gather of the slices, "
                              "dgpu_stage_compiled, kernels, NCCL all_gather, device merge, D2H of the merged top-k"),
                     "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},

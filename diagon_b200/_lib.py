@@ -120,6 +120,10 @@ PROTOTYPES = {
     "dgpu_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "dgpu_engine_last_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3)]),
     "dgpu_engine_batch_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 16)]),
+    "dgpu_engine_create_shadow": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dgpu_engine_sync_options": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dgpu_engine_wait": (C.c_int, [C.c_void_p]),
+    "dgpu_engine_pipeline": (None, [C.c_void_p, C.POINTER(C.c_int32 * 2)]),
 }
 
 _lib = None

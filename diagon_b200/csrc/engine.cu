@@ -185,6 +185,9 @@ struct dgpu_engine {
     uint32_t n_lane_items = 0;
     uint32_t batch_filters = 0;                  // range filters of the staged batch
     int lane_ring_entries = 2304;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
+    int pipeline_chunks = 4;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
+    int pipeline_min = 2048;        // batches of fewer queries are not cut
+    bool shadow = false;            // shares another engine's uploaded index
     int pool_smem_cap = 256;        // candidate pools of up to this many keys live in shared memory, larger ones in global
     int lane_ctas_per_sm = 0; // 0 = as many as fit; else an upper bound on the CTAs per SM of the lane merge kernels
     uint32_t n_acc_items = 0, n_and_items = 0;   // how the work items split between the two kernels
@@ -362,6 +365,16 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->lane_ring_entries = static_cast<int>(value);
         return 0;
     }
+    if (!std::strcmp(name, "pipeline_chunks")) {
+        if (value < 1 || value > 64) return fail("pipeline_chunks must be in [1, 64]");
+        e->pipeline_chunks = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "pipeline_min")) {
+        if (value < 1) return fail("pipeline_min must be >= 1");
+        e->pipeline_min = static_cast<int>(std::min<int64_t>(value, 1 << 30));
+        return 0;
+    }
     if (!std::strcmp(name, "pool_smem_cap")) {
         if (value < 64 || value > 8192) return fail("pool_smem_cap must be in [64, 8192]");
         e->pool_smem_cap = static_cast<int>(value);
@@ -407,6 +420,57 @@ int dgpu_engine_upload(dgpu_engine* e, const dgpu_index_image* im) {
     e->ix.doc_lo = im->doc_lo;
     e->ix.doc_hi = im->doc_hi;
     return 0;
+}
+
+int dgpu_engine_sync_options(dgpu_engine* dst, const dgpu_engine* src) {
+    dst->logw = src->logw;
+    dst->ctas_per_sm = src->ctas_per_sm;
+    dst->warps = src->warps;
+    dst->kernel = src->kernel;
+    dst->force_splits = src->force_splits;
+    dst->window_docs = src->window_docs;
+    dst->stage_log2 = src->stage_log2;
+    dst->warps_per_sm = src->warps_per_sm;
+    dst->max_parts = src->max_parts;
+    dst->part_factor = src->part_factor;
+    dst->decode_ctas_per_sm = src->decode_ctas_per_sm;
+    dst->intersect = src->intersect;
+    dst->lane_merge = src->lane_merge;
+    dst->lane_ring_entries = src->lane_ring_entries;
+    dst->lane_ctas_per_sm = src->lane_ctas_per_sm;
+    dst->pool_smem_cap = src->pool_smem_cap;
+    dst->pipeline_chunks = src->pipeline_chunks;
+    dst->pipeline_min = src->pipeline_min;
+    return 0;
+}
+
+int dgpu_engine_create_shadow(dgpu_engine* primary, dgpu_engine** out) {
+    *out = nullptr;
+    if (primary->owned.empty()) return fail("the primary engine holds no index");
+    dgpu_engine* e = nullptr;
+    if (dgpu_engine_create(primary->device, &e)) return -1;
+    e->shadow = true;
+    e->ix = primary->ix;                      // device arrays of the primary: shared, never freed here
+    e->n_terms = primary->n_terms;
+    e->n_blocks = primary->n_blocks;
+    e->n_fields = primary->n_fields;
+    e->h_term_block_start = primary->h_term_block_start;
+    e->h_block_meta = primary->h_block_meta;
+    e->h_block_off = primary->h_block_off;
+    dgpu_engine_sync_options(e, primary);
+    *out = e;
+    return 0;
+}
+
+int dgpu_engine_wait(dgpu_engine* e) {
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+void dgpu_engine_pipeline(const dgpu_engine* e, int32_t out[2]) {
+    out[0] = e->pipeline_chunks;
+    out[1] = e->pipeline_min;
 }
 
 int dgpu_engine_set_ktab(dgpu_engine* e, const float* ktab, uint32_t n_fields) {

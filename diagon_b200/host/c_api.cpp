@@ -45,9 +45,11 @@ void add_clause(DiagonQuery bool_query, DiagonQuery clause, Occur occur) {
     }
 }
 
-// Splits a text batch into lines and parses them on all host threads.
-std::vector<std::unique_ptr<Query>> parse_batch(const char* text, int64_t len) {
-    std::vector<std::pair<const char*, const char*>> lines;
+using LineSpan = std::pair<const char*, const char*>;
+
+// The non-empty lines of a text batch.
+std::vector<LineSpan> split_lines(const char* text, int64_t len) {
+    std::vector<LineSpan> lines;
     const char* p = text;
     const char* end = text + len;
     while (p < end) {
@@ -56,11 +58,29 @@ std::vector<std::unique_ptr<Query>> parse_batch(const char* text, int64_t len) {
         if (e > p) lines.emplace_back(p, e);
         p = nl ? nl + 1 : end;
     }
-    std::vector<std::unique_ptr<Query>> out(lines.size());
-    parallel_for(lines.size(), lines.size() < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
-        for (size_t i = b; i < e; ++i) out[i] = parse_query_line(std::string(lines[i].first, lines[i].second));
+    return lines;
+}
+
+// Parses lines [lo, hi) on all host threads.
+std::vector<std::unique_ptr<Query>> parse_lines(const std::vector<LineSpan>& lines, size_t lo, size_t hi) {
+    std::vector<std::unique_ptr<Query>> out(hi - lo);
+    parallel_for(hi - lo, hi - lo < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) out[i] = parse_query_line(std::string(lines[lo + i].first, lines[lo + i].second));
     });
     return out;
+}
+
+// Splits a text batch into lines and parses them on all host threads.
+std::vector<std::unique_ptr<Query>> parse_batch(const char* text, int64_t len) {
+    const auto lines = split_lines(text, len);
+    return parse_lines(lines, 0, lines.size());
+}
+
+// a 10K-query batch is ~500K small heap objects: release them on all threads, not serially in the destructor
+void release_parsed(std::vector<std::unique_ptr<Query>>& parsed) {
+    parallel_for(parsed.size(), parsed.size() < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) parsed[i].reset();
+    });
 }
 
 void unpack(const std::vector<uint64_t>& keys, const std::vector<int32_t>& counts, int32_t n, int32_t k,
@@ -130,6 +150,64 @@ int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, 
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         std::fprintf(stderr, "[dgpu trace] compile %.3f ms, engine search %.3f ms, unpack %.3f ms\n", ms(t0, t1), ms(t1, t2),
                      ms(t2, std::chrono::steady_clock::now()));
+    }
+    return static_cast<int>(n);
+}
+
+// A large text batch in chunks over two engines that share the device index: while the kernels of chunk i run, the host
+// parses, compiles and stages chunk i + 1 on the other engine. Results are those of the unchunked call (queries are
+// independent; only the sharing of decoded terms between queries shrinks to a chunk).
+int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int chunks, int32_t k, int32_t* out_docs,
+                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits) {
+    if (k <= 0) throw std::invalid_argument("numHits must be > 0");
+    static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    IndexReader& rd = s.getIndexReader();
+    dgpu_engine* eng[2] = {rd.engine(), rd.shadow_engine()};
+    const size_t n = lines.size();
+    std::vector<uint64_t> keys(n * static_cast<size_t>(k));
+    std::vector<int32_t> counts(n);
+    struct Inflight { size_t q0 = 0; bool active = false; } fly[2];
+    auto fetch = [&](int slot) {
+        if (!fly[slot].active) return;
+        fly[slot].active = false;
+        const size_t q0 = fly[slot].q0;
+        dgpu_results res{keys.data() + q0 * static_cast<size_t>(k), counts.data() + q0, out_total_hits + q0};
+        if (dgpu_engine_fetch_results(eng[slot], &res) != 0)
+            throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
+    };
+    try {
+        for (int c = 0; c < chunks; ++c) {
+            const size_t q0 = n * static_cast<size_t>(c) / chunks, q1 = n * static_cast<size_t>(c + 1) / chunks;
+            if (q1 == q0) continue;
+            const int slot = c & 1;
+            auto parsed = parse_lines(lines, q0, q1);
+            std::vector<const Query*> qs;
+            qs.reserve(parsed.size());
+            for (auto& q : parsed) qs.push_back(q.get());
+            CompiledBatch batch;
+            compile_all(s, qs, batch);
+            release_parsed(parsed);
+            fetch(slot);   // the chunk before last ran on this engine: its results leave before its buffers are reused
+            dgpu_query_batch view = batch.view();
+            if (dgpu_engine_stage_batch(eng[slot], &view, k) != 0 || dgpu_engine_search_staged(eng[slot], nullptr) != 0)
+                throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
+            fly[slot] = Inflight{q0, true};
+        }
+        fetch(0);
+        fetch(1);
+    } catch (...) {
+        dgpu_engine_wait(eng[0]);
+        dgpu_engine_wait(eng[1]);
+        throw;
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    unpack(keys, counts, static_cast<int32_t>(n), k, out_docs, out_scores);
+    std::memcpy(out_counts, counts.data(), n * sizeof(int32_t));
+    if (trace) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[dgpu trace] pipelined: %d chunks %.3f ms, unpack %.3f ms\n", chunks, ms(t0, t1),
+                     ms(t1, std::chrono::steady_clock::now()));
     }
     return static_cast<int>(n);
 }
@@ -544,19 +622,24 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
     if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
     try {
         auto tp = std::chrono::steady_clock::now();
-        auto parsed = parse_batch(text, text_len);
+        const auto lines = split_lines(text, text_len);
+        if (static_cast<int64_t>(lines.size()) > max_queries) { set_error("more queries than max_queries"); return -1; }
+        IndexSearcher& s = *as_searcher(searcher);
+        if (dgpu_engine* e = s.getIndexReader().engine()) {
+            int32_t pl[2];
+            dgpu_engine_pipeline(e, pl);
+            if (pl[0] > 1 && lines.size() >= static_cast<size_t>(pl[1]) && lines.size() >= static_cast<size_t>(pl[0]))
+                return run_text_pipelined(s, lines, pl[0], k, out_docs, out_scores, out_counts, out_total_hits);
+        }
+        auto parsed = parse_lines(lines, 0, lines.size());
         if (std::getenv("DGPU_TRACE"))
             std::fprintf(stderr, "[dgpu trace] parse %.3f ms\n",
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count());
-        if (static_cast<int64_t>(parsed.size()) > max_queries) { set_error("more queries than max_queries"); return -1; }
         std::vector<const Query*> qs;
         qs.reserve(parsed.size());
         for (auto& q : parsed) qs.push_back(q.get());
-        const int rc = run_batch(*as_searcher(searcher), qs, k, out_docs, out_scores, out_counts, out_total_hits);
-        // a 10K-query batch is ~500K small heap objects: release them on all threads, not serially in the destructor
-        parallel_for(parsed.size(), parsed.size() < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
-            for (size_t i = b; i < e; ++i) parsed[i].reset();
-        });
+        const int rc = run_batch(s, qs, k, out_docs, out_scores, out_counts, out_total_hits);
+        release_parsed(parsed);
         return rc;
     } catch (const std::exception& e) { set_error(e); return -1; }
 }

@@ -68,7 +68,16 @@ IndexReader::IndexReader(std::shared_ptr<HostIndex> index, int device) : index_(
 }
 
 IndexReader::~IndexReader() {
+    if (shadow_) dgpu_engine_destroy(shadow_);
     if (engine_) dgpu_engine_destroy(engine_);
+}
+
+dgpu_engine* IndexReader::shadow_engine() {
+    if (!engine_) return nullptr;
+    if (!shadow_ && dgpu_engine_create_shadow(engine_, &shadow_) != 0)
+        throw std::runtime_error(std::string("dgpu shadow engine: ") + dgpu_engine_last_error());
+    dgpu_engine_sync_options(shadow_, engine_);
+    return shadow_;
 }
 
 // ------------------------------------------------------------------ compilation

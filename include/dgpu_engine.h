@@ -114,6 +114,16 @@ int dgpu_engine_device(const dgpu_engine* e);
 int dgpu_engine_sm_count(const dgpu_engine* e);
 
 int dgpu_engine_upload(dgpu_engine* e, const dgpu_index_image* image);
+/* A second engine over the SAME uploaded index (device arrays are shared, not copied; `primary` must outlive it):
+ * its own stream, staging and result buffers, so that the host can stage the next chunk of a large batch while the
+ * kernels of the previous chunk run (dgpu_search_batch_text). The tunables of `primary` are copied at creation and by
+ * dgpu_engine_sync_options. */
+int dgpu_engine_create_shadow(dgpu_engine* primary, dgpu_engine** out);
+int dgpu_engine_sync_options(dgpu_engine* dst, const dgpu_engine* src);
+/* Blocks until the work queued on the engine's stream is done. */
+int dgpu_engine_wait(dgpu_engine* e);
+/* How dgpu_search_batch_text cuts a batch: [0] chunks (1 = no pipelining), [1] smallest batch that is cut. */
+void dgpu_engine_pipeline(const dgpu_engine* e, int32_t out[2]);
 /* Replaces the k(norm) tables (they depend on avgdl, i.e. on GLOBAL statistics of a sharded index). */
 int dgpu_engine_set_ktab(dgpu_engine* e, const float* ktab, uint32_t n_fields);
 

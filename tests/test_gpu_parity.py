@@ -115,6 +115,30 @@ def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, nam
 
 
 @pytest.mark.parametrize("name", ["g1", "g2"])
+@pytest.mark.parametrize("chunks", [2, 3, 7])
+def test_pipelined_text_batch_matches_golden(readers, golden_dir, name, chunks):
+    """dgpu_search_batch_text cuts a large batch into chunks and stages chunk i + 1 on a second engine (same device
+    index) while the kernels of chunk i run: forced here on the golden file, results must not change."""
+    r = readers[name]
+    r.set_option("pipeline_chunks", chunks)
+    r.set_option("pipeline_min", 1)
+    try:
+        searcher = dg.IndexSearcher(r)
+        text = open(os.path.join(golden_dir, f"{name}_queries.txt"), "rb").read()
+        for k in (10, 100):
+            _, ref = read_results(os.path.join(golden_dir, f"{name}_k{k}_exhaustive.res"))
+            for _ in range(2):   # the second call reuses both engines' buffers
+                res = searcher.search_batch_text(text, k)
+                assert len(res.counts) == len(ref)
+                for q, (hits, _, docs) in enumerate(ref):
+                    got = [(int(res.docs[q, j]), res.scores[q, j]) for j in range(res.counts[q])]
+                    assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
+    finally:
+        r.set_option("pipeline_chunks", 4)
+        r.set_option("pipeline_min", 2048)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
 def test_fused_window_kernel_matches_golden(readers, golden_dir, name):
     """The per-query fused kernel (option kernel=2, no decode sharing) stays bit-exact too."""
     r = readers[name]
