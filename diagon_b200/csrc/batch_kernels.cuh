@@ -1256,12 +1256,15 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 for (int t = 1; t < T; ++t) m = min(m, hd[t]);
                 const bool act = m < my_hi;
                 if (!__any_sync(0xFFFFFFFFu, act)) break;
+                // a lane that is done compares against a doc id no head can hold (docs < 2^31, padding = 2^32 - 1): one
+                // compare per term instead of a compare and a predicate combine
+                const uint32_t mm = act ? m : 0xFFFFFFFEu;
                 float score = 0.0f;
                 uint32_t c = 0;
                 bool excluded = false;
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    if (act && hd[t] == m) {
+                    if (hd[t] == mm) {
                         if (NEED_CNT && (not_mask & (1u << t))) {
                             excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
                         } else {
