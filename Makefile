@@ -21,7 +21,14 @@ $(BUILD)/%.o: diagon_b200/host/%.cpp $(HOST_HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(BUILD)/engine.o: diagon_b200/csrc/engine.cu $(wildcard diagon_b200/csrc/*.cuh) include/dgpu_engine.h Makefile
+# the flags are a dependency too: `make EXTRA_NVFLAGS=-DDGPU_CHECK` followed by a plain `make` must rebuild
+$(BUILD)/.nvflags: FORCE
+	@mkdir -p $(BUILD)
+	@echo '$(NVFLAGS)' | cmp -s - $@ || echo '$(NVFLAGS)' > $@
+
+FORCE:
+
+$(BUILD)/engine.o: diagon_b200/csrc/engine.cu $(wildcard diagon_b200/csrc/*.cuh) include/dgpu_engine.h Makefile $(BUILD)/.nvflags
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/ptxas.log || (cat $(BUILD)/ptxas.log; false)
 
@@ -35,4 +42,4 @@ oracle:
 clean:
 	rm -rf $(BUILD) $(OUT)
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean FORCE
