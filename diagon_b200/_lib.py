@@ -78,6 +78,8 @@ PROTOTYPES = {
     "dgpu_open_dump": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "dgpu_open_index": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "dgpu_reader_image_hash": (C.c_uint64, [C.c_void_p]),
+    "dgpu_reader_save_image": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "dgpu_open_image": (C.c_void_p, [C.c_char_p, C.c_int]),
     "dgpu_named_corpus": (C.c_int, [C.c_char_p, C.c_double, C.POINTER(CorpusSpec)]),
     "dgpu_write_synthetic_dump": (C.c_int, [C.POINTER(CorpusSpec), C.c_char_p]),
     "dgpu_query_log_text": (C.c_void_p, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_int64)]),

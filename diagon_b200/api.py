@@ -238,6 +238,16 @@ class IndexReader:
     def image_hash(self) -> int:
         return int(_lib.load().dgpu_reader_image_hash(self._ptr))
 
+    def save_image(self, path: str):
+        """Writes the device layout + dictionary + statistics to one file (DGPUIMG1) for from_image."""
+        if _lib.load().dgpu_reader_save_image(self._ptr, str(path).encode()) != 0:
+            raise DiagonError(_lib.last_error())
+
+    @classmethod
+    def from_image(cls, path: str, device: int = 0):
+        """Reopens what save_image wrote: a read and an upload, no parsing or encoding."""
+        return cls(_lib.load().dgpu_open_image(str(path).encode(), device))
+
     @classmethod
     def synthetic(cls, spec: "_lib.CorpusSpec", device: int = 0, seg_lo: int = 0, seg_hi: int = -1):
         return cls(_lib.load().dgpu_open_synthetic(C.byref(spec), device, seg_lo, seg_hi))

@@ -426,27 +426,22 @@ DiagonIndexReader dgpu_open_index(const char* path, int device, int seg_lo, int 
 
 uint64_t dgpu_reader_image_hash(DiagonIndexReader reader) {
     if (!reader) { set_error("Invalid reader"); return 0; }
-    const HostIndex& ix = as_reader(reader)->index();
-    const IndexImage& im = ix.image;
-    uint64_t h = 0xcbf29ce484222325ull;   // FNV-1a over everything that is uploaded, plus the statistics
-    const bool trace = std::getenv("DGPU_TRACE") != nullptr;
-    auto mix = [&](const void* p, size_t n) {
-        const uint8_t* b = static_cast<const uint8_t*>(p);
-        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
-        if (trace) std::fprintf(stderr, "[dgpu trace] image hash after %zu bytes: %016llx\n", n, static_cast<unsigned long long>(h));
-    };
-    mix(im.term_block_start.data(), im.term_block_start.size() * 4);
-    mix(im.block_first_doc.data(), im.block_first_doc.size() * 4);
-    mix(im.block_last_doc.data(), im.block_last_doc.size() * 4);
-    mix(im.block_data_off.data(), im.block_data_off.size() * 4);
-    mix(im.block_meta.data(), im.block_meta.size() * 4);
-    mix(im.data.data(), im.data.size());
-    mix(im.ktab.data(), im.ktab.size() * 4);
-    for (const auto& c : im.dv) mix(c.data(), c.size() * 8);
-    mix(ix.term_doc_freq.data(), ix.term_doc_freq.size() * sizeof(ix.term_doc_freq[0]));
-    mix(&im.doc_lo, 4);
-    mix(&im.doc_hi, 4);
-    return h;
+    return as_reader(reader)->index().image_hash();
+}
+
+int dgpu_reader_save_image(DiagonIndexReader reader, const char* path) {
+    if (!reader || !path) { set_error("Invalid reader or path"); return -1; }
+    try {
+        as_reader(reader)->index().save_image(path);
+        return 0;
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+DiagonIndexReader dgpu_open_image(const char* path, int device) {
+    if (!path) { set_error("Invalid path"); return nullptr; }
+    try {
+        return new IndexReader(HostIndex::load_image(path), device);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
 }
 
 static synth::CorpusSpec to_spec(const dgpu_corpus_spec& s) {

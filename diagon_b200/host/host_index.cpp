@@ -1,5 +1,7 @@
 #include "host_index.h"
 
+#include <ostream>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -758,6 +760,228 @@ void write_synthetic_dump(const synth::CorpusSpec& spec, const std::string& path
             for (uint32_t d = b; d < e; ++d) put<int64_t>(o, corpus.price(d));
         }
     }
+}
+
+}  // namespace dgpu
+
+// ------------------------------------------------------------------ persisted image (DGPUIMG1)
+namespace dgpu {
+namespace {
+
+constexpr char kImageMagic[8] = {'D', 'G', 'P', 'U', 'I', 'M', 'G', '1'};
+
+template <class T>
+void img_put_pod(std::ostream& out, const T& v) { out.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <class T>
+void img_put_vec(std::ostream& out, const std::vector<T>& v) {
+    img_put_pod<uint64_t>(out, v.size());
+    if (!v.empty()) out.write(reinterpret_cast<const char*>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+}
+void img_put_str(std::ostream& out, const std::string& s) {
+    img_put_pod<uint32_t>(out, static_cast<uint32_t>(s.size()));
+    out.write(s.data(), static_cast<std::streamsize>(s.size()));
+}
+
+[[noreturn]] void bad_image(const char* what) { throw std::runtime_error(std::string("corrupt index image: ") + what); }
+
+template <class T>
+T img_get_pod(const uint8_t*& p, const uint8_t* end) {
+    if (static_cast<size_t>(end - p) < sizeof(T)) bad_image("truncated");
+    T v;
+    std::memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    return v;
+}
+template <class T>
+void img_get_vec(const uint8_t*& p, const uint8_t* end, std::vector<T>& v) {
+    const uint64_t n = img_get_pod<uint64_t>(p, end);
+    if (n > static_cast<uint64_t>(end - p) / sizeof(T)) bad_image("array runs past the end of the file");
+    v.resize(n);
+    if (n) std::memcpy(v.data(), p, n * sizeof(T));
+    p += n * sizeof(T);
+}
+std::string img_get_str(const uint8_t*& p, const uint8_t* end) {
+    const uint32_t n = img_get_pod<uint32_t>(p, end);
+    if (n > static_cast<uint64_t>(end - p)) bad_image("string runs past the end of the file");
+    std::string s(reinterpret_cast<const char*>(p), n);
+    p += n;
+    return s;
+}
+
+}  // namespace
+
+void TermDictionary::write_to(std::ostream& out) const {
+    img_put_vec(out, slots_);
+    img_put_vec(out, offsets_);
+    img_put_vec(out, lengths_);
+    img_put_vec(out, fields_);
+    img_put_vec(out, pool_);
+}
+
+void TermDictionary::read_from(const uint8_t*& p, const uint8_t* end) {
+    img_get_vec(p, end, slots_);
+    img_get_vec(p, end, offsets_);
+    img_get_vec(p, end, lengths_);
+    img_get_vec(p, end, fields_);
+    img_get_vec(p, end, pool_);
+    const size_t n = offsets_.size();
+    if (lengths_.size() != n || fields_.size() != n) bad_image("dictionary arrays disagree");
+    if (!slots_.empty() && (slots_.size() & (slots_.size() - 1))) bad_image("dictionary table size");
+    for (size_t i = 0; i < n; ++i)
+        if (offsets_[i] > pool_.size() || lengths_[i] > pool_.size() - offsets_[i]) bad_image("dictionary term out of range");
+    for (uint32_t sl : slots_)
+        if (sl > n) bad_image("dictionary slot out of range");
+}
+
+uint64_t HostIndex::image_hash() const {
+    const IndexImage& im = image;
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&](const void* p, size_t n) {
+        const uint8_t* b = static_cast<const uint8_t*>(p);
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+    };
+    mix(im.term_block_start.data(), im.term_block_start.size() * 4);
+    mix(im.block_first_doc.data(), im.block_first_doc.size() * 4);
+    mix(im.block_last_doc.data(), im.block_last_doc.size() * 4);
+    mix(im.block_data_off.data(), im.block_data_off.size() * 4);
+    mix(im.block_meta.data(), im.block_meta.size() * 4);
+    mix(im.data.data(), im.data.size());
+    mix(im.ktab.data(), im.ktab.size() * 4);
+    for (const auto& c : im.dv) mix(c.data(), c.size() * 8);
+    mix(term_doc_freq.data(), term_doc_freq.size() * sizeof(term_doc_freq[0]));
+    mix(&im.doc_lo, 4);
+    mix(&im.doc_hi, 4);
+    return h;
+}
+
+void HostIndex::save_image(const std::string& path) const {
+    std::ofstream out(path, std::ios::binary | std::ios::trunc);
+    if (!out) throw std::runtime_error("cannot write " + path);
+    out.write(kImageMagic, 8);
+    img_put_pod<uint32_t>(out, 1u);   // version
+    img_put_pod<uint64_t>(out, image_hash());
+    img_put_pod<uint32_t>(out, static_cast<uint32_t>(fields.size()));
+    for (const auto& f : fields) img_put_str(out, f);
+    img_put_pod<uint32_t>(out, static_cast<uint32_t>(dv_names.size()));
+    for (const auto& f : dv_names) img_put_str(out, f);
+    img_put_pod<uint32_t>(out, static_cast<uint32_t>(segments.size()));
+    for (size_t sg = 0; sg < segments.size(); ++sg) {
+        img_put_pod<int32_t>(out, segments[sg].max_doc);
+        img_put_pod<int32_t>(out, segments[sg].doc_base);
+        img_put_pod<uint8_t>(out, segments[sg].is_local ? 1 : 0);
+        if (field_stats[sg].size() != fields.size()) throw std::runtime_error("field statistics do not cover every field");
+        for (const auto& st : field_stats[sg]) {
+            img_put_pod<uint8_t>(out, st.has_terms ? 1 : 0);
+            img_put_pod<int64_t>(out, st.sum_total_term_freq);
+            img_put_pod<int64_t>(out, st.sum_doc_freq);
+            img_put_pod<int32_t>(out, st.doc_count);
+        }
+    }
+    img_put_pod<int64_t>(out, max_doc_total);
+    img_put_vec(out, term_doc_freq);
+    img_put_vec(out, term_total_term_freq);
+    img_put_vec(out, global_sum_ttf_override_);
+    dict.write_to(out);
+    img_put_vec(out, image.term_block_start);
+    img_put_vec(out, image.block_first_doc);
+    img_put_vec(out, image.block_last_doc);
+    img_put_vec(out, image.block_data_off);
+    img_put_vec(out, image.block_meta);
+    img_put_vec(out, image.data);
+    img_put_vec(out, image.term_bytes);
+    img_put_pod<uint32_t>(out, image.doc_lo);
+    img_put_pod<uint32_t>(out, image.doc_hi);
+    img_put_pod<uint32_t>(out, image.n_fields);
+    img_put_vec(out, image.ktab);
+    img_put_pod<uint32_t>(out, static_cast<uint32_t>(image.dv.size()));
+    for (const auto& c : image.dv) img_put_vec(out, c);
+    out.flush();
+    if (!out) throw std::runtime_error("short write to " + path);
+}
+
+std::shared_ptr<HostIndex> HostIndex::load_image(const std::string& path) {
+    std::ifstream in(path, std::ios::binary | std::ios::ate);
+    if (!in) throw std::runtime_error("cannot open " + path);
+    const std::streamsize size = in.tellg();
+    if (size < 20) bad_image("too short");
+    std::vector<uint8_t> buf(static_cast<size_t>(size));
+    in.seekg(0);
+    in.read(reinterpret_cast<char*>(buf.data()), size);
+    if (!in) throw std::runtime_error("short read from " + path);
+    const uint8_t* p = buf.data();
+    const uint8_t* end = p + buf.size();
+    if (std::memcmp(p, kImageMagic, 8) != 0) bad_image("not a DGPUIMG1 file");
+    p += 8;
+    if (img_get_pod<uint32_t>(p, end) != 1u) bad_image("unsupported version");
+    const uint64_t want_hash = img_get_pod<uint64_t>(p, end);
+    auto ix = std::make_shared<HostIndex>();
+    const uint32_t nf = img_get_pod<uint32_t>(p, end);
+    if (nf > 65535) bad_image("field count");
+    for (uint32_t i = 0; i < nf; ++i) ix->fields.push_back(img_get_str(p, end));
+    const uint32_t ndv = img_get_pod<uint32_t>(p, end);
+    if (ndv > 65535) bad_image("doc-values column count");
+    for (uint32_t i = 0; i < ndv; ++i) ix->dv_names.push_back(img_get_str(p, end));
+    const uint32_t nseg = img_get_pod<uint32_t>(p, end);
+    if (nseg > (1u << 24)) bad_image("segment count");
+    for (uint32_t sg = 0; sg < nseg; ++sg) {
+        SegmentMeta m;
+        m.max_doc = img_get_pod<int32_t>(p, end);
+        m.doc_base = img_get_pod<int32_t>(p, end);
+        m.is_local = img_get_pod<uint8_t>(p, end) != 0;
+        if (m.max_doc < 0 || m.doc_base < 0) bad_image("segment bounds");
+        ix->segments.push_back(m);
+        std::vector<FieldSegmentStats> stats(nf);
+        for (auto& st : stats) {
+            st.has_terms = img_get_pod<uint8_t>(p, end) != 0;
+            st.sum_total_term_freq = img_get_pod<int64_t>(p, end);
+            st.sum_doc_freq = img_get_pod<int64_t>(p, end);
+            st.doc_count = img_get_pod<int32_t>(p, end);
+        }
+        ix->field_stats.push_back(std::move(stats));
+    }
+    ix->max_doc_total = img_get_pod<int64_t>(p, end);
+    img_get_vec(p, end, ix->term_doc_freq);
+    img_get_vec(p, end, ix->term_total_term_freq);
+    img_get_vec(p, end, ix->global_sum_ttf_override_);
+    ix->dict.read_from(p, end);
+    IndexImage& im = ix->image;
+    img_get_vec(p, end, im.term_block_start);
+    img_get_vec(p, end, im.block_first_doc);
+    img_get_vec(p, end, im.block_last_doc);
+    img_get_vec(p, end, im.block_data_off);
+    img_get_vec(p, end, im.block_meta);
+    img_get_vec(p, end, im.data);
+    img_get_vec(p, end, im.term_bytes);
+    im.doc_lo = img_get_pod<uint32_t>(p, end);
+    im.doc_hi = img_get_pod<uint32_t>(p, end);
+    im.n_fields = img_get_pod<uint32_t>(p, end);
+    img_get_vec(p, end, im.ktab);
+    const uint32_t ncol = img_get_pod<uint32_t>(p, end);
+    if (ncol != ndv) bad_image("doc-values columns disagree with their names");
+    im.dv.resize(ncol);
+    for (auto& c : im.dv) img_get_vec(p, end, c);
+    if (p != end) bad_image("trailing bytes");
+
+    // structure: what the kernels index with must be in range before anything is uploaded
+    const size_t n_terms = ix->dict.size(), n_blocks = im.block_first_doc.size();
+    if (im.term_block_start.size() != n_terms + 1 || ix->term_doc_freq.size() != n_terms ||
+        ix->term_total_term_freq.size() != n_terms)
+        bad_image("term arrays disagree with the dictionary");
+    if (im.block_last_doc.size() != n_blocks || im.block_meta.size() != n_blocks || im.block_data_off.size() != n_blocks + 1)
+        bad_image("block arrays disagree");
+    if (im.term_block_start.front() != 0 || im.term_block_start.back() != n_blocks) bad_image("term block ranges");
+    for (size_t t = 0; t < n_terms; ++t)
+        if (im.term_block_start[t] > im.term_block_start[t + 1]) bad_image("term block ranges are not monotone");
+    for (size_t b = 0; b < n_blocks; ++b)
+        if (im.block_data_off[b] > im.block_data_off[b + 1]) bad_image("block offsets are not monotone");
+    if (static_cast<uint64_t>(im.block_data_off.back()) * 16u > im.data.size()) bad_image("block payloads run past the data");
+    if (im.n_fields != nf || im.ktab.size() != static_cast<size_t>(nf) * DGPU_KTAB_SIZE) bad_image("k tables");
+    if (im.doc_hi < im.doc_lo) bad_image("doc range");
+    for (const auto& c : im.dv)
+        if (c.size() != static_cast<size_t>(im.doc_hi - im.doc_lo)) bad_image("doc-values column length");
+    if (!ix->global_sum_ttf_override_.empty() && ix->global_sum_ttf_override_.size() != nf) bad_image("statistics overrides");
+    if (ix->image_hash() != want_hash) bad_image("content hash mismatch");
+    return ix;
 }
 
 }  // namespace dgpu

@@ -15,6 +15,7 @@
 #include "synth_corpus.h"
 
 #include <cstdint>
+#include <iosfwd>
 #include <functional>
 #include <memory>
 #include <string>
@@ -46,6 +47,9 @@ public:
     void reserve(size_t n_terms);
     std::string term_bytes(uint32_t id) const;
     uint16_t term_field(uint32_t id) const { return fields_[id]; }
+    // persisted image (host_index.cpp: HostIndex::save_image / load_image)
+    void write_to(std::ostream& out) const;
+    void read_from(const uint8_t*& p, const uint8_t* end);
 
 private:
     static uint64_t hash(uint16_t field, const uint8_t* bytes, size_t len);
@@ -83,6 +87,13 @@ public:
     void set_global_stats(int field, int64_t sum_total_term_freq, int64_t max_doc_total_);
 
     void finalize_tables();  // ktab per field from avgdl
+
+    // Persisted device layout: everything this object holds — dictionary, statistics and the
+    // encoded image — in one little-endian file, so that reopening an index costs a read and an upload instead of a
+    // parse and an encode. load_image checks the structure and the image hash and throws std::runtime_error on damage.
+    void save_image(const std::string& path) const;
+    static std::shared_ptr<HostIndex> load_image(const std::string& path);
+    uint64_t image_hash() const;   // FNV-1a over everything that is uploaded, plus the document frequencies
 
     // Algorithmic bytes of one term's posting list in the device layout (roofline accounting).
     uint64_t term_encoded_bytes(uint32_t term_id) const {

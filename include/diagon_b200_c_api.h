@@ -112,6 +112,13 @@ DiagonIndexReader dgpu_open_index(const char* path, int device, int seg_lo, int 
 /* FNV-1a of everything dgpu_engine_upload receives plus the per-term statistics: two readers with the same hash
  * answer every query identically. */
 uint64_t dgpu_reader_image_hash(DiagonIndexReader reader);
+/* Persisted device layout: writes everything the reader holds — term dictionary, per-segment
+ * and global statistics, the encoded posting blocks, k tables, doc-values columns — to one little-endian file
+ * (DGPUIMG1), and opens such a file: a read and an upload instead of a parse and an encode (what reopening costs the
+ * reference is re-reading .tim/.tip/.doc through src/codecs/lucene104/Lucene104FieldsProducer.cpp:70-137 per segment).
+ * A sharded reader saves its shard. dgpu_open_image verifies structure and content hash; NULL + message on damage. */
+int dgpu_reader_save_image(DiagonIndexReader reader, const char* path);
+DiagonIndexReader dgpu_open_image(const char* path, int device);
 
 /* Synthetic corpora of BASELINE.json, built without text or indexer. */
 typedef struct {

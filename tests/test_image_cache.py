@@ -1,0 +1,119 @@
+"""Persisted device layout (DGPUIMG1): save_image / from_image round trips.
+
+CPU part: host-only readers (device -1: dictionary, statistics and the encoded image, no engine). Two readers with the
+same image hash hold the same bytes for the GPU and the same document frequencies; the compiled form of a query batch
+covers the dictionary and the remaining statistics. The GPU part searches through a reopened image."""
+import gzip
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import diagon_b200 as dg
+from diagon_b200 import api
+from tests.util import assert_same_topdocs, read_lines, read_results
+
+
+@pytest.fixture(scope="module")
+def g1_raw(golden_dir, tmp_path_factory):
+    raw = tmp_path_factory.mktemp("img") / "g1.dmp"
+    with gzip.open(os.path.join(golden_dir, "g1.dmp.gz"), "rb") as f, open(raw, "wb") as g:
+        shutil.copyfileobj(f, g)
+    return str(raw)
+
+
+def _same_host_view(a, b, text):
+    assert a.image_hash() == b.image_hash()
+    assert np.array_equal(a.get_doc_freqs(), b.get_doc_freqs())
+    assert a.get_field_totals("body") == b.get_field_totals("body")
+    assert a.maxDoc() == b.maxDoc()
+    sa, sb = dg.IndexSearcher(a), dg.IndexSearcher(b)
+    try:
+        assert np.array_equal(sa.compile_batch_text(text), sb.compile_batch_text(text))
+    finally:
+        sa.close()
+        sb.close()
+
+
+def test_image_round_trip_host_only(g1_raw, golden_dir, tmp_path):
+    text = open(os.path.join(golden_dir, "g1_queries.txt"), "rb").read()
+    src = dg.IndexReader.from_dump(g1_raw, -1)
+    path = str(tmp_path / "g1.img")
+    src.save_image(path)
+    back = dg.IndexReader.from_image(path, -1)
+    _same_host_view(src, back, text)
+    # a second generation is byte-identical: nothing is lost or reordered on the way through the file
+    path2 = str(tmp_path / "g1b.img")
+    back.save_image(path2)
+    assert open(path, "rb").read() == open(path2, "rb").read()
+    back.close()
+    src.close()
+
+
+def test_image_of_a_shard_and_of_a_synthetic_corpus(g1_raw, tmp_path):
+    text = b"OR body 0 t0000011 t0000150 t0002000\nAND body t0000020 t0000300\n"
+    # a shard: local postings of segments [1, 3), statistics of all
+    shard = dg.IndexReader.from_dump(g1_raw, -1, 1, 3)
+    p1 = str(tmp_path / "shard.img")
+    shard.save_image(p1)
+    back = dg.IndexReader.from_image(p1, -1)
+    _same_host_view(shard, back, b"OR body 0 market oil\n")
+    back.close()
+    shard.close()
+    # a synthetic corpus with a doc-values column (C4 shape)
+    spec = dg.named_corpus("C4", 0.0005)
+    syn = dg.IndexReader.synthetic(spec, -1)
+    p2 = str(tmp_path / "c4.img")
+    syn.save_image(p2)
+    back = dg.IndexReader.from_image(p2, -1)
+    _same_host_view(syn, back, text)
+    back.close()
+    syn.close()
+
+
+def test_damaged_images_are_refused(g1_raw, tmp_path):
+    src = dg.IndexReader.from_dump(g1_raw, -1)
+    path = str(tmp_path / "g1.img")
+    src.save_image(path)
+    src.close()
+    blob = open(path, "rb").read()
+
+    def refused(data, what):
+        bad = str(tmp_path / "bad.img")
+        open(bad, "wb").write(data)
+        with pytest.raises(api.DiagonError, match=what):
+            dg.IndexReader.from_image(bad, -1)
+
+    refused(b"", "cannot open|too short|corrupt")
+    refused(blob[:16], "corrupt index image")
+    refused(b"XGPUIMG1" + blob[8:], "not a DGPUIMG1 file")
+    refused(blob[: len(blob) // 2], "corrupt index image")
+    refused(blob + b"\0", "trailing bytes")
+    for pos in (len(blob) // 3, len(blob) - 9):   # payload bytes: structure still parses, the content hash does not match
+        flipped = bytearray(blob)
+        flipped[pos] ^= 0x40
+        refused(bytes(flipped), "corrupt index image")
+    with pytest.raises(api.DiagonError):
+        dg.IndexReader.from_image(str(tmp_path / "missing.img"), -1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [10, 100])
+def test_search_through_a_reopened_image(g1_raw, golden_dir, tmp_path, k):
+    src = dg.IndexReader.from_dump(g1_raw, -1)
+    path = str(tmp_path / "g1.img")
+    src.save_image(path)
+    src.close()
+    reader = dg.IndexReader.from_image(path, 0)
+    try:
+        searcher = dg.IndexSearcher(reader)
+        text = open(os.path.join(golden_dir, "g1_queries.txt"), "rb").read()
+        _, ref = read_results(os.path.join(golden_dir, f"g1_k{k}_exhaustive.res"))
+        res = searcher.search_batch_text(text, k)
+        assert len(res.counts) == len(ref)
+        for q, (hits, _, docs) in enumerate(ref):
+            got = [(int(res.docs[q, j]), res.scores[q, j]) for j in range(res.counts[q])]
+            assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
+    finally:
+        reader.close()
