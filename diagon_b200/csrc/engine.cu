@@ -184,7 +184,7 @@ struct dgpu_engine {
     uint32_t lane_max_terms = 0;                 // most terms of any lane-merge query of the staged batch
     uint32_t n_lane_items = 0;
     uint32_t batch_filters = 0;                  // range filters of the staged batch
-    int lane_ring_entries = 2304;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
+    int lane_ring_entries = 2176;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
     int pipeline_chunks = 4;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
     int pipeline_min = 2048;        // batches of fewer queries are not cut
     bool shadow = false;            // shares another engine's uploaded index
