@@ -1,12 +1,18 @@
 // Batched scoring kernels of diagon_b200 (sm_100a). Included by engine.cu only; DESIGN.md §4-§5.
 //
-//   K1+K3a  decode_score_kernel     every DISTINCT term of a query batch is decoded (StreamVByte blocks) and scored
-//                                   (norm lookup, freq -> BM25) exactly once per batch into a device scratch of
-//                                   (doc, score) runs: the score of a posting depends on the term, not on the query
-//                                   (idf comes from global statistics), so queries that share a term share this work;
-//   K3b+K4  accumulate_topk_kernel  per query: doc-window at a time, scatter-add of the runs of its terms in clause
-//                                   order into shared-memory accumulators (bit-exact float sums), touched-list
-//                                   harvest with filters / required-match counts, running-threshold top-k.
+//   K1+K3a  decode_score_kernel       every DISTINCT term of a query batch is decoded (StreamVByte blocks) and scored
+//                                     (norm lookup, freq -> BM25) exactly once per batch into a device scratch of
+//                                     (doc, score) runs: the score of a posting depends on the term, not on the query
+//                                     (idf comes from global statistics), so queries that share a term share this work;
+//   K3b+K4  staged_merge_topk_kernel  queries of up to 32 terms, document-at-a-time: one warp per (query, doc range),
+//                                     the runs of the query streamed through shared-memory rings, one lane per doc
+//                                     span merging the runs in clause order (bit-exact float sums), match counts /
+//                                     exclusions / doc-value filters on the spot, running-threshold top-k;
+//           lane_merge_topk_kernel    the same merge with every lane reading its runs from global memory (A/B);
+//           accumulate_topk_kernel    longer queries, term-at-a-time: doc-window at a time, scatter-add of the runs in
+//                                     clause order into shared-memory accumulators, touched-list harvest, top-k;
+//   K2      intersect_topk_kernel     pure conjunctions: galloping intersection led by the shortest list;
+//           merge_items_kernel        merge of the doc-range parts of a query.
 //
 // Paths cited as file:line are relative to /root/reference/src/core/.
 #pragma once
