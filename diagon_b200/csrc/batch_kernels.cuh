@@ -971,8 +971,74 @@ lane_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
 __host__ __device__ inline size_t staged_warp_smem_bytes(uint32_t ring_entries, uint32_t cap_smem, int T) {
     size_t b = sizeof(uint2) * (static_cast<size_t>(ring_entries) + 1);   // rings + the shared end-of-run entry
     b += (sizeof(uint32_t) * static_cast<size_t>(T) + 7) & ~static_cast<size_t>(7);   // cursor exchange
-    b += sizeof(uint64_t) * cap_smem;                                     // candidate pool
+    b += cap_smem ? sizeof(uint64_t) * cap_smem                           // candidate pool in shared memory, or
+                  : sizeof(uint32_t) * 256;                               // the digit histogram of warp_select_topk (pool in global memory)
     return (b + 15) & ~static_cast<size_t>(15);
+}
+
+// Large candidate pools (top-1000: 2048 keys in global memory): keeps the k largest of the n distinct keys in keys[0, k)
+// (in no particular order) and returns the k-th largest. Radix selection, most significant byte first: a 256-bin
+// histogram (shared memory) of the keys that agree with the digits chosen so far, one pass per byte, then one
+// compaction pass. 8 + 1 passes over the pool instead of the 66 compare-exchange stages of a full bitonic sort.
+__device__ __forceinline__ uint64_t warp_select_topk(uint64_t* keys, uint32_t n, uint32_t k, uint32_t* hist, int lane) {
+    DGPU_ASSERT(k >= 1 && n >= k);
+    uint64_t prefix = 0, mask = 0;
+    uint32_t want = k;   // rank (1 = largest) of the wanted key among the keys that match the prefix
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint64_t key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[static_cast<uint32_t>(key >> shift) & 0xFFu], 1u);
+        }
+        __syncwarp();
+        // lane l owns the digits 255 - 8l .. 248 - 8l, largest first
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = hist[255 - (8 * lane + j)];
+            sum += c[j];
+        }
+        const uint32_t incl = warp_inclusive_scan(sum, lane), excl = incl - sum;   // keys with a larger digit: excl
+        const bool here = excl < want && want <= incl;
+        uint32_t digit = 0, above = 0;
+        if (here) {
+            uint32_t run = excl;
+            bool found = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (!found && run + c[j] >= want) {
+                    digit = 255u - (8u * lane + j);
+                    above = run;
+                    found = true;
+                }
+                run += c[j];
+            }
+        }
+        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, here);
+        DGPU_ASSERT(hm != 0u);
+        const int src = __ffs(hm) - 1;
+        digit = __shfl_sync(0xFFFFFFFFu, digit, src);
+        above = __shfl_sync(0xFFFFFFFFu, above, src);
+        want -= above;
+        prefix |= static_cast<uint64_t>(digit) << shift;
+        mask |= 0xFFull << shift;
+        __syncwarp();
+    }
+    const uint64_t kth = prefix;   // keys are distinct: exactly k of them are >= kth
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t w = 0;
+    for (uint32_t base = 0; base < n; base += 32) {   // in-place, in order: the write cursor never passes the read cursor
+        const uint32_t i = base + lane;
+        const uint64_t key = i < n ? keys[i] : 0ull;
+        const bool keep = i < n && key >= kth;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (keep) keys[w + __popc(m & lt_mask)] = key;
+        w += __popc(m);
+        __syncwarp();
+    }
+    DGPU_ASSERT(w == k);
+    return kth;
 }
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -995,8 +1061,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 // kFilterDepth iterations later, together with the collection of that doc, so the load's latency (an L2 hit at best:
 // the column is read at random) hides behind the next merge step (measured on C4: depth 1 beats 0 by 10 %, 3 is slower).
 constexpr int kFilterDepth = 1;
-template <int T, int MODE>
-__global__ void __launch_bounds__(32, T <= 16 ? 16 : 8)   // 128 registers up to 16 terms, 255 beyond (5 words per term)
+// BIGK: the candidate pool lives in global memory (top-k beyond 128) and is pruned by selection; a separate
+// instantiation, so that the selection code does not touch the register allocation of the small-k merge loop
+// (measured: compiled into one kernel it cost the C2 loop 35 %).
+template <int T, int MODE, bool BIGK>
+__global__ void __launch_bounds__(32, T <= 12 ? 16 : (T <= 16 ? 12 : 8))   // 128 registers up to 12 terms, 168 for 16, 255 beyond
 staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
     constexpr bool NEED_CNT = MODE >= 1;
     constexpr bool FILTER = MODE == 2;
@@ -1007,8 +1076,10 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
     const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
     uint2* ring = reinterpret_cast<uint2*>(sp);
     uint32_t* xch = reinterpret_cast<uint32_t*>(sp + sizeof(uint2) * (B + 1));
-    uint64_t* cand = P.pool ? P.pool + static_cast<size_t>(blockIdx.x) * P.cand_cap
-                            : reinterpret_cast<uint64_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * T + 7) & ~7u));
+    uint64_t* cand = BIGK ? P.pool + static_cast<size_t>(blockIdx.x) * P.cand_cap
+                          : reinterpret_cast<uint64_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * T + 7) & ~7u));
+    // with the pool in global memory, its place in shared memory holds the digit histogram of warp_select_topk
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * T + 7) & ~7u));
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint2* __restrict__ runs = P.runs;
     if (lane == 0) ring[B] = make_uint2(kDocEnd, 0u);   // what the unused term slots of a query read
@@ -1144,15 +1215,20 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
         float thresh_f = __uint_as_float(0xFF800000u);   // its score (-inf until there is one): the merge loop's quick test
         uint32_t hits = 0;          // per lane
         auto prune = [&]() {
-            const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
-            for (uint32_t i = n_cand + lane; i < n; i += 32) cand[i] = 0;
-            warp_bitonic_sort_desc(cand, n, lane);
-            if (n_cand >= static_cast<uint32_t>(P.k)) {
+            if (BIGK) {   // large pool: select, do not sort
+                if (n_cand < static_cast<uint32_t>(P.k)) return;
+                __syncwarp();
+                thresh = warp_select_topk(cand, n_cand, static_cast<uint32_t>(P.k), hist, lane);
+            } else {
+                const uint32_t n = min(P.cand_cap, pow2_at_least(n_cand));
+                for (uint32_t i = n_cand + lane; i < n; i += 32) cand[i] = 0;
+                warp_bitonic_sort_desc(cand, n, lane);
+                if (n_cand < static_cast<uint32_t>(P.k)) return;
                 thresh = cand[P.k - 1];
-                n_cand = P.k;
-                const uint32_t o = static_cast<uint32_t>(thresh >> 32);
-                thresh_f = __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
             }
+            n_cand = P.k;
+            const uint32_t o = static_cast<uint32_t>(thresh >> 32);
+            thresh_f = __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
         };
 
         // warp-collective: counts the hit and offers it to the pool
@@ -1324,6 +1400,7 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             for (int d = 0; d < kFilterDepth; ++d) collect_pending();
         }
         hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+        if (BIGK && n_cand > static_cast<uint32_t>(P.k)) prune();   // sort k keys, not the whole pool
         const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
         for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;
         warp_bitonic_sort_desc(cand, nsort, lane);

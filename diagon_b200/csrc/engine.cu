@@ -894,8 +894,14 @@ static int launch_merge_kernel(dgpu_engine* e, AccumParams& L, cudaStream_t stre
 
 template <int T>
 static int launch_staged_only_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
-    auto kern = e->batch_filters ? staged_merge_topk_kernel<T, 2>
-                                 : (e->need_cnt ? staged_merge_topk_kernel<T, 1> : staged_merge_topk_kernel<T, 0>);
+    if (e->plan_pool_global) {
+        if (!L.pool) return fail("internal: global candidate pool missing");
+        auto kern = e->batch_filters ? staged_merge_topk_kernel<T, 2, true>
+                                     : (e->need_cnt ? staged_merge_topk_kernel<T, 1, true> : staged_merge_topk_kernel<T, 0, true>);
+        return launch_merge_kernel(e, L, stream, kern, 1, T, true);
+    }
+    auto kern = e->batch_filters ? staged_merge_topk_kernel<T, 2, false>
+                                 : (e->need_cnt ? staged_merge_topk_kernel<T, 1, false> : staged_merge_topk_kernel<T, 0, false>);
     return launch_merge_kernel(e, L, stream, kern, 1, T, true);
 }
 
