@@ -623,7 +623,8 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
         if (dgpu_engine* e = s.getIndexReader().engine()) {
             int32_t pl[2];
             dgpu_engine_pipeline(e, pl);
-            if (pl[0] > 1 && lines.size() >= static_cast<size_t>(pl[1]) && lines.size() >= static_cast<size_t>(pl[0]))
+            if (pl[0] > 1 && lines.size() >= static_cast<size_t>(pl[1]) && lines.size() >= static_cast<size_t>(pl[0]) &&
+                s.getIndexReader().shadow_engine())
                 return run_text_pipelined(s, lines, pl[0], k, out_docs, out_scores, out_counts, out_total_hits);
         }
         auto parsed = parse_lines(lines, 0, lines.size());

@@ -73,9 +73,12 @@ IndexReader::~IndexReader() {
 }
 
 dgpu_engine* IndexReader::shadow_engine() {
-    if (!engine_) return nullptr;
-    if (!shadow_ && dgpu_engine_create_shadow(engine_, &shadow_) != 0)
-        throw std::runtime_error(std::string("dgpu shadow engine: ") + dgpu_engine_last_error());
+    if (!engine_ || shadow_failed_) return nullptr;
+    if (!shadow_ && dgpu_engine_create_shadow(engine_, &shadow_) != 0) {
+        shadow_ = nullptr;
+        shadow_failed_ = true;   // the caller runs the batch on engine() alone; not retried on every call
+        return nullptr;
+    }
     dgpu_engine_sync_options(shadow_, engine_);
     return shadow_;
 }

@@ -174,13 +174,14 @@ public:
     const HostIndex& index() const { return *index_; }
     dgpu_engine* engine() const { return engine_; }
     // A second engine over the same device index (created on first use): the batch call stages one chunk on it while
-    // the kernels of the previous chunk run on engine(). nullptr for a host-only reader.
+    // the kernels of the previous chunk run on engine(). nullptr for a host-only reader or when it cannot be created.
     dgpu_engine* shadow_engine();
 
 private:
     std::shared_ptr<HostIndex> index_;
     dgpu_engine* engine_ = nullptr;
     dgpu_engine* shadow_ = nullptr;
+    bool shadow_failed_ = false;
 };
 
 // IndexSearcher.h:35-147. enable_block_max_wand is accepted for source compatibility and ignored:
