@@ -76,6 +76,7 @@ def parse_args():
     ap.add_argument("--pool-smem-cap", type=int, default=0)
     ap.add_argument("--pipeline-chunks", type=int, default=0, help="chunks of the end-to-end text call (1 = no host/device overlap)")
     ap.add_argument("--lane-ring-entries", type=int, default=0)
+    ap.add_argument("--union-window-docs", type=int, default=0, help="docs per window (bits of shared memory) of union_topk_kernel")
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -267,7 +268,7 @@ def reference_arm(args, corpus_name, log_name, kind, k, steps, warmup, full):
 
 # ------------------------------------------------------------------------------------------------ main
 def lane_kernel_name(bstats):
-    return "staged_merge_topk_kernel" if int(bstats[11]) == 1 else "lane_merge_topk_kernel"
+    return {1: "staged_merge_topk_kernel", 2: "lane_merge_topk_kernel", 3: "union_topk_kernel"}.get(int(bstats[11]), "accumulate_topk_kernel")
 
 
 def dominant_kernel(bstats):
@@ -356,6 +357,8 @@ def main():
         reader.set_option("kernel", args.kernel)
     if args.lane_merge >= 0:
         reader.set_option("lane_merge", args.lane_merge)
+    if args.union_window_docs:
+        reader.set_option("union_window_docs", args.union_window_docs)
     if args.lane_ring_entries:
         reader.set_option("lane_ring_entries", args.lane_ring_entries)
     if args.pipeline_chunks:

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiagon_b200.so")
+# DGPU_LIB: another build of the same library (debugging only, e.g. the -DDGPU_CHECK build with device-side bounds checks)
+LIB_PATH = os.environ.get("DGPU_LIB") or os.path.join(_HERE, "libdiagon_b200.so")
 
 
 class CorpusSpec(C.Structure):

@@ -161,9 +161,21 @@ __device__ __forceinline__ uint32_t warp_decode_payload(const uint8_t* p, uint32
     return n;
 }
 
+// Output layouts: AOS = (doc, score) entries (accumulate_topk_kernel, intersect_topk_kernel and the register-merge
+// kernels); SOA = doc ids, scores and the maximum score of every 64 entries as three arrays (union_topk_kernel streams
+// doc ids only and looks at scores where the chunk maximum says a doc may be collected).
+struct RunArrays {
+    uint2* aos;
+    uint32_t* docs;
+    float* scores;
+    float* cmax;   // [entry / 64]
+};
+
+template <bool AOS, bool SOA>
 __global__ void __launch_bounds__(kDecodeThreads, 4)
 decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DItem* __restrict__ items, uint32_t n_items,
-                    uint2* __restrict__ runs) {
+                    RunArrays out) {
+    uint2* __restrict__ runs = out.aos;
     __shared__ __align__(128) uint8_t s_buf[kDecodeWarps][kDecodeStages][kPayloadBuf];
     __shared__ __align__(8) uint64_t s_mbar[kDecodeWarps][kDecodeStages];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,15 +244,36 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
             }
             const uint32_t rel = rel0 + kDecodeWarps * j;
             DGPU_ASSERT(rel < nb && n <= DGPU_BLOCK_POSTINGS);
-            uint4* o = reinterpret_cast<uint4*>(runs + static_cast<size_t>(dt.out_base) +
-                                                static_cast<size_t>(rel) * DGPU_BLOCK_POSTINGS + 4u * lane);
-            o[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
-            o[1] = make_uint4(ev[4], ev[5], ev[6], ev[7]);
-            if (rel + 1 == nb) {
+            const size_t e0 = static_cast<size_t>(dt.out_base) + static_cast<size_t>(rel) * DGPU_BLOCK_POSTINGS + 4u * lane;
+            if (AOS) {
+                uint4* o = reinterpret_cast<uint4*>(runs + e0);
+                o[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
+                o[1] = make_uint4(ev[4], ev[5], ev[6], ev[7]);
+                if (rel + 1 == nb) {
 #pragma unroll
-                for (int pb = 1; pb <= kPadBlocks; ++pb) {
-                    o[pb * (DGPU_BLOCK_POSTINGS / 2)] = make_uint4(kDocEnd, 0u, kDocEnd, 0u);
-                    o[pb * (DGPU_BLOCK_POSTINGS / 2) + 1] = make_uint4(kDocEnd, 0u, kDocEnd, 0u);
+                    for (int pb = 1; pb <= kPadBlocks; ++pb) {
+                        o[pb * (DGPU_BLOCK_POSTINGS / 2)] = make_uint4(kDocEnd, 0u, kDocEnd, 0u);
+                        o[pb * (DGPU_BLOCK_POSTINGS / 2) + 1] = make_uint4(kDocEnd, 0u, kDocEnd, 0u);
+                    }
+                }
+            }
+            if (SOA) {
+                *reinterpret_cast<uint4*>(out.docs + e0) = make_uint4(ev[0], ev[2], ev[4], ev[6]);
+                *reinterpret_cast<uint4*>(out.scores + e0) = make_uint4(ev[1], ev[3], ev[5], ev[7]);
+                // maximum score of each half block (64 entries = 16 lanes); slots past the postings hold -inf
+                float mx = __uint_as_float(0xFF800000u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4u * lane + q < n) mx = fmaxf(mx, __uint_as_float(ev[2 * q + 1]));
+#pragma unroll
+                for (int o = 8; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+                if ((lane & 15) == 0) out.cmax[e0 >> 6] = mx;
+                if (rel + 1 == nb) {
+#pragma unroll
+                    for (int pb = 1; pb <= kPadBlocks; ++pb) {
+                        *reinterpret_cast<uint4*>(out.docs + e0 + pb * DGPU_BLOCK_POSTINGS) = make_uint4(kDocEnd, kDocEnd, kDocEnd, kDocEnd);
+                        if ((lane & 15) == 0) out.cmax[(e0 >> 6) + 2 * pb] = __uint_as_float(0xFF800000u);
+                    }
                 }
             }
         }
@@ -265,6 +298,9 @@ struct AccumParams {
     uint32_t n_items;
     uint32_t* work_counter;
     const uint2* runs;          // (doc, score bits) entries of every distinct term of the batch
+    const uint32_t* run_docs;   // the same runs as three arrays (union_topk_kernel): doc ids,
+    const float* run_scores;    //   scores,
+    const float* run_cmax;      //   maximum score of every 64 entries
     uint64_t run_total;         // entries allocated in `runs` (bounds checks)
     int k;
     uint32_t W;                 // docs per window (multiple of 32, <= 65536)

@@ -55,6 +55,7 @@ int fail(const char* fmt, ...) {
 
 #include "kernels.cuh"
 #include "batch_kernels.cuh"
+#include "union_kernels.cuh"
 
 namespace {
 
@@ -142,6 +143,10 @@ struct dgpu_engine {
     DevBuf<DItem> d_items;
     DevBuf<QTermRun> d_qruns;
     DevBuf<uint2> d_runs;
+    DevBuf<uint32_t> d_run_docs;        // the runs as three arrays (union_topk_kernel): doc ids,
+    DevBuf<float> d_run_scores;         //   scores,
+    DevBuf<float> d_run_cmax;           //   maximum score of every 64 entries
+    bool runs_aos = true, runs_soa = false;   // which layouts decode_score_kernel writes for the staged batch
     DevBuf<uint64_t> d_part_keys;
     DevBuf<int32_t> d_part_counts;
     DevBuf<int64_t> d_part_hits;
@@ -185,6 +190,7 @@ struct dgpu_engine {
     uint32_t n_lane_items = 0;
     uint32_t batch_filters = 0;                  // range filters of the staged batch
     int lane_ring_entries = 2176;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
+    int union_window_docs = 32768;  // docs per window (one bit each in shared memory) of union_topk_kernel
     int pipeline_chunks = 4;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
     int pipeline_min = 2048;        // batches of fewer queries are not cut
     bool shadow = false;            // shares another engine's uploaded index
@@ -284,6 +290,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     e->d_queries.release(); e->d_terms.release(); e->d_filters.release(); e->d_order.release();
     e->d_counter.release(); e->d_keys.release(); e->d_counts.release(); e->d_hits.release();
     e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_runs.release();
+    e->d_run_docs.release(); e->d_run_scores.release(); e->d_run_cmax.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
     e->d_witems.release(); e->d_part_off.release(); e->d_pool.release();
     e->h_stage.release(); e->h_results.release();
@@ -356,13 +363,19 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         return 0;
     }
     if (!std::strcmp(name, "lane_merge")) {
-        if (value < 0 || value > 2) return fail("lane_merge must be 0 (windows), 1 (staged rings) or 2 (global loads)");
+        if (value < 0 || value > 3)
+            return fail("lane_merge must be 0 (windows), 1 (staged rings), 2 (global loads) or 3 (bitmap union)");
         e->lane_merge = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "lane_ring_entries")) {
         if (value < 512 || value > 8192) return fail("lane_ring_entries must be in [512, 8192]");
         e->lane_ring_entries = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "union_window_docs")) {
+        if (value < 128 || value > 1048576 || (value & 127)) return fail("union_window_docs must be a multiple of 128 in [128, 1048576]");
+        e->union_window_docs = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "pipeline_chunks")) {
@@ -437,6 +450,7 @@ int dgpu_engine_sync_options(dgpu_engine* dst, const dgpu_engine* src) {
     dst->intersect = src->intersect;
     dst->lane_merge = src->lane_merge;
     dst->lane_ring_entries = src->lane_ring_entries;
+    dst->union_window_docs = src->union_window_docs;
     dst->lane_ctas_per_sm = src->lane_ctas_per_sm;
     dst->pool_smem_cap = src->pool_smem_cap;
     dst->pipeline_chunks = src->pipeline_chunks;
@@ -569,7 +583,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             for (uint32_t t = qd.term_begin; all_must && t < qd.term_end; ++t) all_must = b->terms[t].role == DGPU_ROLE_MUST;
             // class of the query: 2 = intersected, 1 = merged document-at-a-time by lanes, 0 = accumulated in windows
             const bool lane = !all_must && e->kernel == 3 && e->lane_merge &&
-                              nt_q <= (e->lane_merge == 1 ? kStagedMergeMaxTerms : kLaneMergeMaxTerms);
+                              nt_q <= (e->lane_merge == 2 ? kLaneMergeMaxTerms : kStagedMergeMaxTerms);
             is_and[q] = all_must ? 2 : (lane ? 1 : 0);
             if (!all_must) {
                 if (lane) pt.lane_max_terms = std::max(pt.lane_max_terms, nt_q);
@@ -782,15 +796,22 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     }
     CU(e->d_witems.ensure(witems.size()));
     if (e->kernel == 3) {
-        const size_t want = static_cast<size_t>(run_entries) + 16384;  // tail slack for ring look-ahead loads
-        if (want > e->d_runs.cap) {
-            // grow with headroom: the scratch is reused by every batch
-            const size_t cap = want + want / 4;
-            if (e->d_runs.ensure(cap) != cudaSuccess)
-                return fail("cannot allocate %zu MB of decode scratch (%s); split the batch", cap * 8 >> 20,
-                            cudaGetErrorString(cudaGetLastError()));
+        // union_topk_kernel reads the runs as separate doc / score arrays, the other kernels as (doc, score) entries
+        e->runs_soa = e->lane_merge == 3 && e->n_lane_items != 0;
+        e->runs_aos = !e->runs_soa || e->n_acc_items != 0 || e->n_and_items != 0;
+        const size_t want = static_cast<size_t>(run_entries) + 16384;  // tail slack for look-ahead loads
+        const size_t cap = want + want / 4;   // grow with headroom: the scratch is reused by every batch
+        cudaError_t ce = cudaSuccess;
+        if (e->runs_aos && want > e->d_runs.cap) ce = e->d_runs.ensure(cap);
+        if (ce == cudaSuccess && e->runs_soa && want > e->d_run_docs.cap) {
+            ce = e->d_run_docs.ensure(cap);
+            if (ce == cudaSuccess) ce = e->d_run_scores.ensure(cap);
+            if (ce == cudaSuccess) ce = e->d_run_cmax.ensure(cap / 64 + 64);
         }
-        CU(cudaMemsetAsync(e->d_runs.p, 0xFF, sizeof(uint2) * kRunPad, e->stream));
+        if (ce != cudaSuccess)
+            return fail("cannot allocate %zu MB of decode scratch (%s); split the batch", cap * 8 >> 20, cudaGetErrorString(ce));
+        if (e->runs_aos) CU(cudaMemsetAsync(e->d_runs.p, 0xFF, sizeof(uint2) * kRunPad, e->stream));
+        if (e->runs_soa) CU(cudaMemsetAsync(e->d_run_docs.p, 0xFF, sizeof(uint32_t) * kRunPad, e->stream));
     }
     if (b->n_queries) {
         const size_t bytes[9] = {sizeof(dgpu_query) * b->n_queries, sizeof(dgpu_qterm) * b->n_terms, sizeof(QTermRun) * b->n_terms,
@@ -912,7 +933,45 @@ static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stre
     return launch_merge_kernel(e, L, stream, kern, LaneMergeBounds<T>::kThreads / 32, T, false);
 }
 
+// lane_merge = 3: union_topk_kernel, one warp per item, kUnionWarps independent warps per CTA
+template <class Kern>
+static int launch_union_kernel(dgpu_engine* e, AccumParams& L, cudaStream_t stream, Kern kern) {
+    const uint32_t cap_smem = e->plan_pool_global ? 0u : e->plan_cap;
+    L.W = static_cast<uint32_t>(e->union_window_docs);
+    L.warp_smem = static_cast<uint32_t>(union_warp_smem_bytes(L.W, cap_smem));
+    const size_t smem = static_cast<size_t>(L.warp_smem) * kUnionWarps;
+    if (smem > static_cast<size_t>(e->max_smem_optin))
+        return fail("union_topk_kernel needs %zu bytes of shared memory, device allows %d", smem, e->max_smem_optin);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kUnionWarps, smem));
+    if (per_sm < 1) return fail("union_topk_kernel does not fit an SM (%zu bytes of shared memory)", smem);
+    if (e->lane_ctas_per_sm) per_sm = std::min(per_sm, e->lane_ctas_per_sm);
+    const uint64_t want_ctas = (static_cast<uint64_t>(L.n_items) + kUnionWarps - 1) / kUnionWarps;
+    const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * per_sm, want_ctas));
+    kern<<<grid, 32 * kUnionWarps, smem, stream>>>(e->ix, L);
+    CU(cudaGetLastError());
+    e->launches++;
+    e->last_window = L.W;
+    return 0;
+}
+
+static int launch_union(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
+    const int mode = e->batch_filters ? 2 : (e->need_cnt ? 1 : 0);
+    if (e->plan_pool_global) {
+        if (!L.pool) return fail("internal: global candidate pool missing");
+        if (mode == 2) return launch_union_kernel(e, L, stream, union_topk_kernel<2, true>);
+        if (mode == 1) return launch_union_kernel(e, L, stream, union_topk_kernel<1, true>);
+        return launch_union_kernel(e, L, stream, union_topk_kernel<0, true>);
+    }
+    if (mode == 2) return launch_union_kernel(e, L, stream, union_topk_kernel<2, false>);
+    if (mode == 1) return launch_union_kernel(e, L, stream, union_topk_kernel<1, false>);
+    return launch_union_kernel(e, L, stream, union_topk_kernel<0, false>);
+}
+
 static int launch_lane_merge(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
+    if (e->lane_merge == 3) return launch_union(e, L, stream);
     const uint32_t nt = e->lane_max_terms;
     if (nt <= 2) return launch_lane_merge_t<2>(e, L, stream);
     if (nt <= 4) return launch_lane_merge_t<4>(e, L, stream);
@@ -937,7 +996,10 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.n_items = e->n_acc_items;
     P.work_counter = e->d_counter.p;
     P.runs = e->d_runs.p;
-    P.run_total = e->d_runs.cap;
+    P.run_docs = e->d_run_docs.p;
+    P.run_scores = e->d_run_scores.p;
+    P.run_cmax = e->d_run_cmax.p;
+    P.run_total = e->runs_soa ? e->d_run_docs.cap : e->d_runs.cap;
     P.k = e->k;
     P.max_terms = (e->max_terms + 3u) & ~3u;
     P.cand_cap = e->plan_cap;
@@ -961,8 +1023,10 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     CU(cudaEventRecord(e->ev0, stream));
     if (e->n_ditems) {
         const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * e->decode_ctas_per_sm));
-        decode_score_kernel<<<grid, kDecodeThreads, 0, stream>>>(e->ix, e->d_dterms.p, e->d_items.p, e->n_ditems,
-                                                                 e->d_runs.p);
+        const RunArrays out{e->d_runs.p, e->d_run_docs.p, e->d_run_scores.p, e->d_run_cmax.p};
+        auto dk = e->runs_soa ? (e->runs_aos ? decode_score_kernel<true, true> : decode_score_kernel<false, true>)
+                              : decode_score_kernel<true, false>;
+        dk<<<grid, kDecodeThreads, 0, stream>>>(e->ix, e->d_dterms.p, e->d_items.p, e->n_ditems, out);
         e->launches++;
         CU(cudaGetLastError());
     }

@@ -68,28 +68,46 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
             assert np.isnan(td.maxScore)
 
 
-# (window_docs, stage_log2, splits, warps per CTA, warps per SM, intersect, lane_merge, lane_ring_entries): small windows
-# walk many windows per query, stage_log2 = 1 pushes almost every term through the global-memory continuation, splits
-# exercises doc-range parts + the device merge, intersect = 0 sends the conjunctions through the counting windows instead
-# of intersect_topk_kernel; lane_merge picks the kernel of the shorter queries (<= 32 terms staged, <= 16 global): 0 = accumulate_topk_kernel
-# (windows), 1 = staged_merge_topk_kernel (rings of lane_ring_entries entries per warp), 2 = lane_merge_topk_kernel
-# (global loads); with 1 and 2 the windows still score the longer queries of the file
-_TUNINGS = [(0, 0, 0, 4, 16, 1, 0, 1024), (1024, 0, 1, 4, 16, 0, 0, 1024), (256, 1, 1, 8, 32, 1, 0, 1024),
-            (4096, 2, 3, 2, 8, 0, 0, 1024), (64, 3, 7, 1, 4, 1, 0, 1024), (2048, 0, 16, 4, 12, 1, 0, 1024),
-            (0, 0, 0, 4, 20, 1, 1, 1024), (0, 0, 1, 4, 20, 0, 1, 512), (512, 0, 3, 4, 20, 0, 1, 2048),
-            (0, 0, 16, 4, 20, 1, 1, 4096), (0, 0, 0, 4, 20, 0, 2, 1024), (0, 0, 5, 4, 20, 1, 2, 1024)]
+# Engine options a tuning overrides; everything else stays at the engine's defaults. Small windows walk many windows per
+# query, stage_log2 = 1 pushes almost every term through the global-memory continuation, splits exercises doc-range
+# parts + the device merge, intersect = 0 sends the conjunctions through the counting paths instead of
+# intersect_topk_kernel; lane_merge picks the kernel of the queries of <= 32 terms: 0 = accumulate_topk_kernel (windows),
+# 1 = staged_merge_topk_kernel (rings of lane_ring_entries entries per warp), 2 = lane_merge_topk_kernel (global loads,
+# <= 16 terms), 3 = union_topk_kernel (bitmap windows of union_window_docs docs); the longer queries of the file are
+# scored by the windows whatever lane_merge says
+_DEFAULTS = {"window_docs": 0, "stage_log2": 0, "splits": 0, "warps": 4, "warps_per_sm": 20, "intersect": 1,
+             "lane_merge": 1, "lane_ring_entries": 2176, "union_window_docs": 32768, "lane_ctas_per_sm": 0}
+_TUNINGS = [
+    dict(lane_merge=0, warps_per_sm=16),
+    dict(lane_merge=0, window_docs=1024, splits=1, warps_per_sm=16, intersect=0),
+    dict(lane_merge=0, window_docs=256, stage_log2=1, splits=1, warps=8, warps_per_sm=32),
+    dict(lane_merge=0, window_docs=4096, stage_log2=2, splits=3, warps=2, warps_per_sm=8, intersect=0),
+    dict(lane_merge=0, window_docs=64, stage_log2=3, splits=7, warps=1, warps_per_sm=4),
+    dict(lane_merge=0, window_docs=2048, splits=16, warps_per_sm=12),
+    dict(lane_merge=1),
+    dict(lane_merge=1, lane_ring_entries=2304),
+    dict(lane_merge=1, splits=1, intersect=0, lane_ring_entries=512),
+    dict(lane_merge=1, window_docs=512, splits=3, intersect=0, lane_ring_entries=2048),
+    dict(lane_merge=1, splits=16, lane_ring_entries=4096),
+    dict(lane_merge=2, intersect=0),
+    dict(lane_merge=2, splits=5),
+    dict(lane_merge=3),
+    dict(lane_merge=3, intersect=0, splits=1),
+    dict(lane_merge=3, union_window_docs=128, splits=3),
+    dict(lane_merge=3, union_window_docs=1024, intersect=0, splits=7),
+    dict(lane_merge=3, union_window_docs=65536, splits=16, lane_ctas_per_sm=2),
+    dict(lane_merge=3, union_window_docs=4096, window_docs=512),
+]
 
 
 @pytest.mark.parametrize("name", ["g1", "g2"])
-@pytest.mark.parametrize("window_docs,stage_log2,splits,warps,warps_per_sm,intersect,lane_merge,ring", _TUNINGS)
-def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, name, window_docs, stage_log2, splits, warps,
-                                                        warps_per_sm, intersect, lane_merge, ring):
+@pytest.mark.parametrize("tuning", _TUNINGS, ids=lambda t: "-".join(f"{k}{v}" for k, v in t.items()))
+def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, name, tuning):
     """dgpu_search_batch_text: the whole query file in one launch; the kernel a query is routed to, window size, staging
     depth, doc-range parts and the warp layout must not change any result."""
     r = readers[name]
-    for opt, v in (("window_docs", window_docs), ("stage_log2", stage_log2), ("splits", splits), ("warps", warps),
-                   ("warps_per_sm", warps_per_sm), ("intersect", intersect), ("lane_merge", lane_merge),
-                   ("lane_ring_entries", ring)):
+    assert set(tuning) <= set(_DEFAULTS)
+    for opt, v in {**_DEFAULTS, **tuning}.items():
         r.set_option(opt, v)
     try:
         searcher = dg.IndexSearcher(r)
@@ -109,8 +127,7 @@ def test_batched_search_matches_golden_for_every_tuning(readers, golden_dir, nam
                     got = [(int(res.docs[q, j]), res.scores[q, j]) for j in range(res.counts[q])]
                     assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {i}")
     finally:
-        for opt, v in (("window_docs", 0), ("stage_log2", 0), ("splits", 0), ("warps", 4), ("warps_per_sm", 20), ("intersect", 1),
-                       ("lane_merge", 1), ("lane_ring_entries", 1024)):
+        for opt, v in _DEFAULTS.items():
             r.set_option(opt, v)
 
 
@@ -378,6 +395,58 @@ def test_wide_queries_and_empty_inputs(readers, g1_dump):
     empty = searcher.search_batch_text(b"", 10)
     assert len(empty.counts) == 0
     assert len(searcher.search_batch([], 10).counts) == 0
+
+
+@pytest.mark.parametrize("window", [128, 2048, 32768])
+def test_union_kernel_edge_shapes(readers, g1_dump, window):
+    """union_topk_kernel (lane_merge = 3) on the shapes its record logic has to get right: the same term in several
+    clauses (every posting of the later clause is a second sighting), dense terms held by 3..8 clauses at once,
+    minimumNumberShouldMatch above 1 (no doc matched by one clause is a hit), exclusions of dense terms, MUST lists with
+    exclusions, range filters, top-k from 1 to 4096 (pool in shared and in global memory), doc-range parts."""
+    import random
+
+    ox = orc.OracleIndex(g1_dump)
+    r = readers["g1"]
+    rnd = random.Random(11)
+    dense = ["t%07d" % i for i in range(1, 13)]
+    mid = ["t%07d" % i for i in range(20, 400)]
+    lines = [
+        "OR body 0 t0000001 t0000001",
+        "OR body 0 t0000002 t0000001 t0000002 t0000003 t0000001",
+        "OR body 0 " + " ".join(dense[:8]),
+        "OR body 0 " + " ".join(dense + rnd.sample(mid, 20)),
+        "OR body 2 " + " ".join(dense[:4] + rnd.sample(mid, 6)),
+        "OR body 3 " + " ".join(rnd.sample(dense, 6) + rnd.sample(mid, 10)),
+        "OR body 7 " + " ".join(dense[:6]),
+        "OR body 4 t0000001 t0000001 t0000002 t0000002",
+        "ANDNOT body 1 t0000002 t0000001",
+        "ANDNOT body 1 t0000001 t0000002 t0000003 t0000004",
+        "ANDNOT body 3 t0000001 t0000002 t0000003 t0000004 t0000150",
+        "ANDNOT body 2 t0000001 t0000001 t0000300",
+        "ORF body price 100000 300000 " + " ".join(dense[:5]),
+        "ORF body price 0 100000000 t0000001 t0000002 t0000001",
+        "ANDF body price 0 500000 t0000001 t0000002 t0000003",
+        "OR body 0 t9999990 t0000007 t9999991",
+        "TERM body t0000001",
+    ]
+    want = {}
+    try:
+        r.set_option("lane_merge", 3)
+        r.set_option("union_window_docs", window)
+        r.set_option("intersect", 0)
+        searcher = dg.IndexSearcher(r)
+        for k, splits in ((1, 0), (10, 0), (10, 5), (100, 3), (1000, 0), (4096, 2)):
+            r.set_option("splits", splits)
+            res = searcher.search_batch_text(("\n".join(lines) + "\n").encode(), k)
+            for q, line in enumerate(lines):
+                if (line, k) not in want:
+                    want[(line, k)] = ox.search(api.parse_line(line), k)
+                h, sd, _ = want[(line, k)]
+                got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
+                assert_same_topdocs(int(res.total_hits[q]), got, h, sd, f"k={k} splits={splits} {line[:60]}")
+    finally:
+        for opt, v in _DEFAULTS.items():
+            r.set_option(opt, v)
 
 
 def test_staging_compiled_slices_equals_one_call(readers, golden_dir):
