@@ -12,14 +12,20 @@
 //   * the scores of a chunk are loaded only when the chunk's maximum score (written by decode_score_kernel next to
 //     the run, one float per 64 entries) reaches the running k-th best score: the sum of a doc matched by one clause
 //     is bounded by that maximum, so nothing that could be collected is skipped;
-//   * every later sighting of a doc and every first sighting whose score reaches the threshold becomes a RECORD
-//     (doc, clause). Records are resolved in batches of 32 (one per lane): the lane bisects the window's slice of
-//     every run of the query for its doc, adds the scores of the clauses that hold it in clause order starting from
-//     0.0f (bit-exact, BooleanQuery.cpp:119-126), counts required / excluded clauses, applies the range filters, and
-//     offers the doc to the top-k pool. A doc matched by n clauses has n - 1 records of the later sightings (clauses
-//     are processed in order, so the first sighting is the lowest clause); the record of the SECOND lowest clause is
-//     the one that collects the doc, the others drop out. A first sighting recorded as a candidate collects the doc
-//     only if no other clause holds it.
+//   * the clauses are streamed SPARSEST FIRST, so a doc that two clauses hold is first seen in the shorter run and
+//     seen again in the longer one. Every later sighting, and every first sighting whose score reaches the
+//     threshold, becomes a RECORD (doc, position in its run, clause); records are resolved at the end of the window,
+//     32 at a time (one per lane):
+//       - a doc seen exactly twice (almost all of them) looks for its ONE earlier sighting by bisecting the window's
+//         slices of the sparser clauses only - short slices; nobody ever bisects the densest run - and stops at the
+//         first hit. The two scores are added in clause order starting from 0.0f (BooleanQuery.cpp:119-126, :232-241);
+//       - third and later sightings are caught by a 1024-bit hashed filter of the docs seen twice (a hit is checked
+//         against the record list): such a doc gets ONE record that bisects every clause of the window and adds the
+//         scores of the clauses that hold it in clause order (the generic path, rare);
+//       - a recorded first sighting collects its doc unless the filter and the list say the doc was seen again.
+//     If the record list fills up inside a window (pathological overlaps, e.g. the same term in two clauses), the
+//     window is abandoned - cursors, hit count and bitmap restored - and walked again at half the size (down to 4
+//     docs, which cannot overflow with 32 clauses); the size grows back when windows stay well below the limit.
 // Instruction cost: ~0.4 warp-instructions per posting for the stream, against 3-5 for a T-way register merge.
 //
 // MODE 0: plain disjunctions / term queries; 1: required-match counts and exclusions (minimumNumberShouldMatch,
@@ -35,11 +41,20 @@ namespace {
 constexpr int kUnionWarps = 1;                 // one warp per CTA: the bitmap starts at shared-memory offset 0, so the
                                                // address of a doc's word is two logic ops on (doc - window start)
 constexpr uint32_t kUnionChunk = 64;           // entries per iteration (lane l: entries 2l, 2l + 1)
-constexpr uint32_t kUnionRecords = 128;        // record list of a warp; resolved when fewer than 64 slots are free
+constexpr uint32_t kUnionRecords = 256;        // record list of a warp; a window that needs more is walked again at half size
+constexpr uint32_t kUnionFilterWords = 32;     // 1024 bits
+constexpr uint32_t kUnionMinWindow = 4;        // 4 docs x 32 clauses cannot overflow the record list
+// record kinds (meta = kind << 30 | stream rank of the clause << 25 | position in the run - position at window start)
+constexpr uint32_t kRecFirst = 0;   // first sighting whose score reaches the threshold: collects if the doc is not seen again
+constexpr uint32_t kRecSecond = 1;  // second sighting: collects the doc with the one earlier sighting
+constexpr uint32_t kRecAll = 2;     // third or later sighting: collects the doc through the all-clause path
+constexpr uint32_t kRecDead = 3;    // second sighting of a doc that was seen a third time
+constexpr uint32_t kRecOffMask = (1u << 25) - 1u;
 
 __host__ __device__ inline size_t union_warp_smem_bytes(uint32_t window_docs, uint32_t cap_smem) {
     size_t b = window_docs / 8;                                  // seen bitmap
-    b += sizeof(uint2) * kUnionRecords;                          // records
+    b += sizeof(uint32_t) * kUnionFilterWords;                   // hashed filter of the docs seen twice
+    b += 2 * sizeof(uint32_t) * kUnionRecords;                   // records: doc, meta
     b += cap_smem ? sizeof(uint64_t) * cap_smem                  // candidate pool in shared memory, or
                   : sizeof(uint32_t) * 256;                      // the digit histogram of warp_select_topk
     return (b + 15) & ~static_cast<size_t>(15);
@@ -61,6 +76,12 @@ __device__ __forceinline__ uint32_t atoms_or_if(bool p, uint32_t addr, uint32_t 
     return old;
 }
 
+// The value as the compiler cannot see through: keeps a loop-invariant in its register instead of recomputing it.
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 template <int MODE, bool BIGK>
 __global__ void __launch_bounds__(32 * kUnionWarps, 32)   // <= 64 registers: 32 one-warp CTAs per SM
 union_topk_kernel(DeviceIndex ix, AccumParams P) {
@@ -74,8 +95,11 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
     uint32_t* seen = reinterpret_cast<uint32_t*>(sp);
     const uint32_t seen_s = static_cast<uint32_t>(__cvta_generic_to_shared(seen));
     sp += W / 8;
-    uint2* recs = reinterpret_cast<uint2*>(sp);
-    sp += sizeof(uint2) * kUnionRecords;
+    uint32_t* filt = reinterpret_cast<uint32_t*>(sp);
+    sp += sizeof(uint32_t) * kUnionFilterWords;
+    uint32_t* rec_doc = reinterpret_cast<uint32_t*>(sp);
+    uint32_t* rec_meta = rec_doc + kUnionRecords;
+    sp += 2 * sizeof(uint32_t) * kUnionRecords;
     uint64_t* cand = BIGK ? P.pool + static_cast<size_t>(blockIdx.x) * P.cand_cap : reinterpret_cast<uint64_t*>(sp);
     uint32_t* hist = reinterpret_cast<uint32_t*>(sp);   // BIGK only
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -84,6 +108,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
     const float* __restrict__ cmax = P.run_cmax;
 
     for (uint32_t i = lane; i < W / 128; i += 32) reinterpret_cast<uint4*>(seen)[i] = make_uint4(0u, 0u, 0u, 0u);
+    filt[lane] = 0u;
     __syncwarp();
 
     for (;;) {
@@ -109,13 +134,23 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         DGPU_ASSERT(nt <= 32u);
         const bool mine = static_cast<uint32_t>(lane) < nt;
 
-        // ---- lane t holds the stream state of clause t: `pos` is the first entry of its run not below the current
-        // window start, `nd` that entry's doc (kDocEnd padding after the run: readable, says "end")
-        uint32_t pos = 0, nd = kDocEnd, rend = 0, role = 0;
+        // ---- stream order: sparsest run first. `rk` (on lane j) is the stream rank of clause j; lane r then takes over
+        // the clause of rank r (`cl`) and holds its stream state: `pos` is the first entry of the run not below the
+        // current window start, `nd` that entry's doc (kDocEnd padding after the run: readable, says "end")
+        uint32_t rk = 0, cl = 0;
+        {
+            const uint32_t my_len = mine ? qt[lane].len : 0xFFFFFFFFu;
+            for (uint32_t i = 0; i < nt; ++i) {
+                const uint32_t li = __shfl_sync(0xFFFFFFFFu, my_len, i);
+                rk += (li < my_len || (li == my_len && i < static_cast<uint32_t>(lane))) ? 1u : 0u;
+            }
+            for (uint32_t i = 0; i < nt; ++i)
+                if (__shfl_sync(0xFFFFFFFFu, rk, i) == static_cast<uint32_t>(lane)) cl = i;
+        }
+        uint32_t pos = 0, nd = kDocEnd, role = 0;
         if (mine) {
-            const QTermRun r = qt[lane];
+            const QTermRun r = qt[cl];
             pos = r.base;
-            rend = r.base + r.len;
             role = r.meta;
             if (lo > ix.doc_lo && r.len) {   // first entry with doc >= lo
                 uint32_t a = 0, b = r.len;
@@ -139,8 +174,9 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
         uint64_t thresh = 0;        // key of the k-th best so far
         float thresh_f = __uint_as_float(0xFF800000u);   // its score (-inf until there is one): the stream's quick test
-        uint32_t hits = 0;          // per lane, modulo 2^32 (mode 1 also takes hits back)
-        uint32_t n_rec = 0;         // records waiting (warp-uniform)
+        uint32_t hits = 0;          // per lane, modulo 2^32 (later sightings and mode 1 also take hits back)
+        uint32_t n_rec = 0;         // records of the current window (warp-uniform)
+        uint32_t w_cur = W;         // docs per window: W unless a window overflowed the record list
         auto prune = [&]() {
             if (BIGK) {   // large pool: select, do not sort
                 if (n_cand < static_cast<uint32_t>(P.k)) return;
@@ -186,51 +222,57 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
             }
             return ok;
         };
+        // is `dd` in the record list? kinds found: bit kRecSecond / kRecAll / kRecDead set in the result; `second_at` =
+        // where its live second sighting is
+        auto list_lookup = [&](uint32_t dd, uint32_t& second_at) -> uint32_t {
+            uint32_t kinds = 0;
+            for (uint32_t rb = 0; rb < n_rec; rb += 32) {
+                const uint32_t e = rb + lane;
+                const bool eq = e < n_rec && rec_doc[e] == dd;
+                const uint32_t ek = eq ? rec_meta[e] >> 30 : kRecFirst;
+                const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, ek == kRecSecond);
+                if (m2) {
+                    second_at = rb + __ffs(m2) - 1;
+                    kinds |= 1u << kRecSecond;
+                }
+                if (__any_sync(0xFFFFFFFFu, ek == kRecAll)) kinds |= 1u << kRecAll;
+                if (__any_sync(0xFFFFFFFFu, ek == kRecDead)) kinds |= 1u << kRecDead;
+            }
+            return kinds;
+        };
 
         for (;;) {
-            // ---- window: W docs from the smallest next doc of any clause
-            const uint32_t ws = __reduce_min_sync(0xFFFFFFFFu, nd);
+            // ---- window: w_cur docs from the smallest next doc of any clause
+            const uint32_t ws = opaque(__reduce_min_sync(0xFFFFFFFFu, nd));
             if (ws >= hi) break;
-            const uint32_t we = (hi - ws > W) ? ws + W : hi;
-            const uint32_t wlen = we - ws;
+            const uint32_t we = opaque((hi - ws > w_cur) ? ws + w_cur : hi);
+            const uint32_t wlen = opaque(we - ws);
             const uint32_t act0 = __ballot_sync(0xFFFFFFFFu, nd < we);   // clauses with entries inside the window
-            const uint32_t wpos = pos;
-            uint32_t act = act0, done = 0;
-            int u = -1;          // clause being streamed (-1: pick the next one)
-            uint32_t c = 0;      // its current chunk (multiple of kUnionChunk)
-            int pf_u = -1;       // clause whose first chunk has been prefetched into pf_d / pf_cm
-            uint2 pf_d = make_uint2(0u, 0u);
-            float pf_cm = 0.0f;
+            const uint32_t wpos = pos, wnd = nd, whits = hits;          // (restored if the window overflows)
+            bool overflow = false;
 
-            for (;;) {
-                // ---- stream clauses in order until the window is done or the record list is nearly full
-                bool full = false;
-                while (!full) {
-                    uint2 d;
-                    float cm;
-                    if (u < 0) {
-                        if (!act) break;
-                        u = __ffs(act) - 1;
-                        act &= act - 1u;
-                        c = __shfl_sync(0xFFFFFFFFu, pos, u) & ~(kUnionChunk - 1u);
-                        if (pf_u == u) {
-                            d = pf_d;
-                            cm = pf_cm;
-                        } else {
-                            d = __ldg(reinterpret_cast<const uint2*>(docs + c) + lane);
-                            cm = __ldg(cmax + (c >> 6));
-                        }
-                        if (act) {   // the first chunk of the next clause is on its way while this one is streamed
-                            pf_u = __ffs(act) - 1;
-                            const uint32_t cn = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
-                            pf_d = __ldg(reinterpret_cast<const uint2*>(docs + cn) + lane);
-                            pf_cm = __ldg(cmax + (cn >> 6));
-                        }
-                    } else {   // resumed after a resolve in the middle of a clause
-                        d = __ldg(reinterpret_cast<const uint2*>(docs + c) + lane);
-                        cm = __ldg(cmax + (c >> 6));
+            // ---- stream the clauses, sparsest first
+            {
+                uint32_t act = act0;
+                int pf_u = __ffs(act) - 1;   // clause whose first chunk is in pf_d / pf_cm
+                uint32_t pf_c = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
+                uint2 pf_d = __ldg(reinterpret_cast<const uint2*>(docs + pf_c) + lane);
+                float pf_cm = __ldg(cmax + (pf_c >> 6));
+                while (act && !overflow) {
+                    const int u = pf_u;
+                    act &= act - 1u;
+                    uint32_t c = pf_c;   // current chunk of the clause (multiple of kUnionChunk)
+                    uint2 d = pf_d;
+                    float cm = pf_cm;
+                    if (act) {   // the first chunk of the next clause is on its way while this one is streamed
+                        pf_u = __ffs(act) - 1;
+                        pf_c = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
+                        pf_d = __ldg(reinterpret_cast<const uint2*>(docs + pf_c) + lane);
+                        pf_cm = __ldg(cmax + (pf_c >> 6));
                     }
                     const bool single_ok = !NEED_CNT || ((single_mask >> u) & 1u);
+                    const uint32_t wpos_u = __shfl_sync(0xFFFFFFFFu, wpos, u);
+                    const uint32_t meta_u = (static_cast<uint32_t>(u) << 25) + 2u * lane - wpos_u;   // + chunk (+ 1): rank and offset of an entry
                     const uint2* pd = reinterpret_cast<const uint2*>(docs + c) + lane;   // this lane's two entries of the chunk
                     const float* pcm = cmax + (c >> 6);
                     for (;;) {
@@ -252,41 +294,92 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         const uint32_t dup = (o0 & b0) | (o1 & b1);   // seen before in this window: a later sighting
                         // mode 2 looks at every first sighting (its filter value decides whether it is a hit); otherwise
                         // only chunks with a later sighting, or whose best score reaches the k-th best so far
-                        if (__any_sync(0xFFFFFFFFu, dup != 0u) || (single_ok && (FILTER || cm >= thresh_f))) {
-                            bool rec0 = (o0 & b0) != 0u, rec1 = (o1 & b1) != 0u;
-                            bool new0 = in0 && !rec0 && single_ok, new1 = in1 && !rec1 && single_ok;
+                        const bool any_later = __any_sync(0xFFFFFFFFu, dup != 0u);
+                        if (any_later || (single_ok && (FILTER || cm >= thresh_f))) {
+                            const bool l0 = (o0 & b0) != 0u, l1 = (o1 & b1) != 0u;   // later sightings
+                            bool rec0 = l0, rec1 = l1;
+                            uint32_t k0 = kRecSecond, k1 = kRecSecond;
                             if (!FILTER) {   // positions count the clause's entries in the window as hits: take these back
-                                if (single_ok) hits -= (rec0 ? 1u : 0u) + (rec1 ? 1u : 0u);
-                            } else {
-                                if (nf) {
-                                    if (new0) new0 = passes(d.x);
-                                    if (new1) new1 = passes(d.y);
-                                }
-                                hits += (new0 ? 1u : 0u) + (new1 ? 1u : 0u);
+                                if (single_ok) hits -= (l0 ? 1u : 0u) + (l1 ? 1u : 0u);
                             }
-                            float cm_adj = cm;
-                            if (FILTER) {
-                                for (uint32_t f = 0; f < nf; ++f) cm_adj = __fadd_rn(cm_adj, 1.0f);   // rounding is monotone
-                            }
-                            if (single_ok && cm_adj >= thresh_f) {   // some first sighting of this chunk may be collected
-                                const float2 s = __ldg(reinterpret_cast<const float2*>(scores + c) + lane);
-                                float s0 = s.x, s1 = s.y;
+                            if (single_ok && (FILTER || cm >= thresh_f)) {   // first sightings: hits of mode 2, candidates
+                                bool new0 = in0 && !l0, new1 = in1 && !l1;
+                                float cm_adj = cm;
                                 if (FILTER) {
-                                    for (uint32_t f = 0; f < nf; ++f) {
-                                        s0 = __fadd_rn(s0, 1.0f);
-                                        s1 = __fadd_rn(s1, 1.0f);
+                                    if (nf) {
+                                        if (new0) new0 = passes(d.x);
+                                        if (new1) new1 = passes(d.y);
+                                    }
+                                    hits += (new0 ? 1u : 0u) + (new1 ? 1u : 0u);
+                                    for (uint32_t f = 0; f < nf; ++f) cm_adj = __fadd_rn(cm_adj, 1.0f);   // rounding is monotone
+                                }
+                                if (cm_adj >= thresh_f) {   // some first sighting of this chunk may be collected
+                                    const float2 s = __ldg(reinterpret_cast<const float2*>(scores + c) + lane);
+                                    float s0 = s.x, s1 = s.y;
+                                    if (FILTER) {
+                                        for (uint32_t f = 0; f < nf; ++f) {
+                                            s0 = __fadd_rn(s0, 1.0f);
+                                            s1 = __fadd_rn(s1, 1.0f);
+                                        }
+                                    }
+                                    if (new0 && s0 >= thresh_f) {
+                                        rec0 = true;
+                                        k0 = kRecFirst;
+                                    }
+                                    if (new1 && s1 >= thresh_f) {
+                                        rec1 = true;
+                                        k1 = kRecFirst;
                                     }
                                 }
-                                rec0 = rec0 || (new0 && s0 >= thresh_f);
-                                rec1 = rec1 || (new1 && s1 >= thresh_f);
+                            }
+                            if (any_later) {
+                                // the hashed filter of the docs seen twice: a bit already set may mean a third sighting
+                                const uint32_t h0 = r0 & (32u * kUnionFilterWords - 1u), h1 = r1 & (32u * kUnionFilterWords - 1u);
+                                bool t0 = false, t1 = false;
+                                if (l0) t0 = ((atomicOr(filt + (h0 >> 5), 1u << (h0 & 31u)) >> (h0 & 31u)) & 1u) != 0u;
+                                if (l1) t1 = ((atomicOr(filt + (h1 >> 5), 1u << (h1 & 31u)) >> (h1 & 31u)) & 1u) != 0u;
+                                if (__any_sync(0xFFFFFFFFu, t0 || t1)) {
+                                    // (rare) a doc that already has a live second sighting gets ONE all-clause record instead;
+                                    // a later sighting of a doc that has one leaves a dead record; else: a hash collision
+                                    __syncwarp();
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j) {
+                                        uint32_t tm = __ballot_sync(0xFFFFFFFFu, j ? t1 : t0);
+                                        while (tm) {
+                                            const int l = __ffs(tm) - 1;
+                                            tm &= tm - 1u;
+                                            const uint32_t dd = __shfl_sync(0xFFFFFFFFu, j ? d.y : d.x, l);
+                                            uint32_t second_at = 0;
+                                            const uint32_t kinds = list_lookup(dd, second_at);
+                                            if (lane == l) {
+                                                uint32_t& kk = j ? k1 : k0;
+                                                if (kinds & (1u << kRecAll)) {
+                                                    kk = kRecDead;
+                                                } else if (kinds & (1u << kRecSecond)) {
+                                                    rec_meta[second_at] = (rec_meta[second_at] & ~(3u << 30)) | (kRecDead << 30);
+                                                    kk = kRecAll;
+                                                }
+                                            }
+                                            __syncwarp();
+                                        }
+                                    }
+                                }
                             }
                             const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, rec0), m1 = __ballot_sync(0xFFFFFFFFu, rec1);
                             DGPU_ASSERT(n_rec + 64u <= kUnionRecords);
-                            if (rec0) recs[n_rec + __popc(m0 & lt_mask)] = make_uint2(d.x, static_cast<uint32_t>(u));
+                            if (rec0) {
+                                const uint32_t e = n_rec + __popc(m0 & lt_mask);
+                                rec_doc[e] = d.x;
+                                rec_meta[e] = (k0 << 30) | (meta_u + c);
+                            }
                             n_rec += __popc(m0);
-                            if (rec1) recs[n_rec + __popc(m1 & lt_mask)] = make_uint2(d.y, static_cast<uint32_t>(u));
+                            if (rec1) {
+                                const uint32_t e = n_rec + __popc(m1 & lt_mask);
+                                rec_doc[e] = d.y;
+                                rec_meta[e] = (k1 << 30) | (meta_u + c + 1u);
+                            }
                             n_rec += __popc(m1);
-                            if (n_rec + 64u > kUnionRecords) full = true;
+                            if (n_rec + 64u > kUnionRecords) overflow = true;
                         }
                         if (!more) {
                             // the clause's next window starts at the first entry >= we: the entries below are a prefix
@@ -301,63 +394,148 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                 pos = c + below;
                                 nd = (below & 1u) ? y : x;
                             }
-                            done |= 1u << u;
-                            u = -1;
                             break;
                         }
+                        if (overflow) break;
                         c += kUnionChunk;
                         pd += 32;
                         pcm += 1;
                         d = dn;
                         cm = cmn;
-                        if (full) break;
                     }
                 }
+            }
+            __syncwarp();
 
-                // ---- resolve the records: lane l takes record base + l and looks its doc up in every clause that has
-                // entries in this window. Slice of clause v: [wpos, pos) once it has been streamed, else everything
-                // up to where the window can reach (docs are distinct and sorted: at most wlen entries)
+            if (overflow) {
+                // ---- too many records: forget this window and walk it again at half the size
+                pos = wpos;
+                nd = wnd;
+                hits = whits;
+                n_rec = 0;
+                for (uint32_t i = lane; i < (wlen + 127u) >> 7; i += 32) reinterpret_cast<uint4*>(seen)[i] = make_uint4(0u, 0u, 0u, 0u);
+                filt[lane] = 0u;
+                DGPU_ASSERT(w_cur > kUnionMinWindow);
+                w_cur = max(kUnionMinWindow, min(w_cur, wlen) >> 1);
                 __syncwarp();
-                uint32_t s_hi = wpos;
-                if ((act0 >> lane) & 1u) s_hi = ((done >> lane) & 1u) ? pos : min(wpos + wlen, rend);
+                continue;
+            }
+
+            // ---- resolve the records, one per lane. The window slice of the clause of rank v is [wpos, pos)
+            {
+                // lower bound of `doc` in the window slice of the clause of rank v (the trip count is warp-uniform; the entry
+                // after a slice is >= we or padding, never `doc`)
+                auto slice_lower_bound = [&](int v, uint32_t doc, uint32_t& b) -> bool {
+                    const uint32_t v_lo = __shfl_sync(0xFFFFFFFFu, wpos, v);
+                    uint32_t len = __shfl_sync(0xFFFFFFFFu, pos, v) - v_lo;
+                    if (len == 0) return false;
+                    b = v_lo;
+                    while (len > 1) {
+                        const uint32_t half = len >> 1;
+                        if (__ldg(docs + b + half - 1u) < doc) b += half;
+                        len -= half;
+                    }
+                    if (__ldg(docs + b) < doc) b += 1u;
+                    DGPU_ASSERT(static_cast<uint64_t>(b) < P.run_total);
+                    return true;
+                };
                 for (uint32_t base = 0; base < n_rec; base += 32) {
                     const bool valid = base + lane < n_rec;
-                    const uint2 rc = valid ? recs[base + lane] : make_uint2(0u, 0xFFu);
-                    const uint32_t doc = rc.x;
+                    const uint32_t doc = valid ? rec_doc[base + lane] : 0u;
+                    const uint32_t meta = valid ? rec_meta[base + lane] : (kRecDead << 30);
+                    const uint32_t kind = meta >> 30, ru = (meta >> 25) & 31u;
+                    const uint32_t rpos = __shfl_sync(0xFFFFFFFFu, wpos, ru) + (meta & kRecOffMask);   // where the sighting is in its run
+                    const bool two = kind == kRecSecond, one = kind == kRecFirst, gen = kind == kRecAll;
                     float sum = 0.0f;
-                    uint32_t cnt = 0, c_ok = 0, first = 0xFFu, second = 0xFEu;
-                    bool excluded = false;
-                    uint32_t am = act0;
-                    while (am) {
-                        const int v = __ffs(am) - 1;
-                        am &= am - 1u;
-                        const uint32_t v_lo = __shfl_sync(0xFFFFFFFFu, wpos, v);
-                        uint32_t len = __shfl_sync(0xFFFFFFFFu, s_hi, v) - v_lo;
-                        const uint32_t rl = NEED_CNT ? __shfl_sync(0xFFFFFFFFu, role, v) : 0u;
-                        if (len == 0) continue;
-                        uint32_t b = v_lo;   // branch-free lower bound; the trip count depends on len only (warp-uniform)
-                        while (len > 1) {
-                            const uint32_t half = len >> 1;
-                            if (__ldg(docs + b + half - 1u) < doc) b += half;
-                            len -= half;
-                        }
-                        if (__ldg(docs + b) < doc) b += 1u;
-                        DGPU_ASSERT(static_cast<uint64_t>(b) < P.run_total);
-                        if (valid && __ldg(docs + b) == doc) {   // (the entry after a slice is >= we or padding: never `doc`)
-                            if (NEED_CNT && rl == DGPU_ROLE_MUST_NOT) {
-                                excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
-                            } else {
-                                sum = __fadd_rn(sum, __ldg(scores + b));
-                                ++c_ok;
+                    uint32_t cnt = 0, c_ok = 0, first = 0u;   // clauses that hold the doc; not excluding ones; rank of the first sighting
+                    bool excluded = false, des = false;       // des: this record collects its doc
+
+                    // -- seen exactly twice: the one earlier sighting is in a sparser clause
+                    if (__any_sync(0xFFFFFFFFu, two)) {
+                        const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, two ? ru : 0u);
+                        uint32_t am = act0 & ((1u << top) - 1u);
+                        bool found = false;
+                        uint32_t fv = 0, fpos = 0;
+                        while (am && __any_sync(0xFFFFFFFFu, two && !found)) {
+                            const int v = __ffs(am) - 1;
+                            am &= am - 1u;
+                            uint32_t b = 0;
+                            if (!slice_lower_bound(v, doc, b)) continue;
+                            if (two && !found && static_cast<uint32_t>(v) < ru && __ldg(docs + b) == doc) {
+                                found = true;
+                                fv = static_cast<uint32_t>(v);
+                                fpos = b;
                             }
-                            if (cnt == 0) first = static_cast<uint32_t>(v);
-                            else if (cnt == 1) second = static_cast<uint32_t>(v);
-                            ++cnt;
+                        }
+                        DGPU_ASSERT(!two || found);
+                        const uint32_t cl_a = __shfl_sync(0xFFFFFFFFu, cl, fv), cl_b = __shfl_sync(0xFFFFFFFFu, cl, ru);
+                        const uint32_t rl_a = __shfl_sync(0xFFFFFFFFu, role, fv), rl_b = __shfl_sync(0xFFFFFFFFu, role, ru);
+                        if (two && found) {
+                            const float s_a = __ldg(scores + fpos), s_b = __ldg(scores + rpos);
+                            const bool a_first = cl_a < cl_b;   // clause order of the sum
+                            const float s_x = a_first ? s_a : s_b, s_y = a_first ? s_b : s_a;
+                            const uint32_t rl_x = a_first ? rl_a : rl_b, rl_y = a_first ? rl_b : rl_a;
+                            if (NEED_CNT && rl_x == DGPU_ROLE_MUST_NOT) excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
+                            else { sum = __fadd_rn(sum, s_x); ++c_ok; }
+                            if (NEED_CNT && rl_y == DGPU_ROLE_MUST_NOT) excluded = true;
+                            else { sum = __fadd_rn(sum, s_y); ++c_ok; }
+                            cnt = 2;
+                            first = fv;
+                            des = true;
                         }
                     }
-                    // who collects the doc: its only clause (a recorded candidate), or the record of the second lowest
-                    const bool des = valid && (cnt == 1 ? rc.y == first : rc.y == second);
-                    DGPU_ASSERT(!valid || cnt >= 1);
+
+                    // -- seen three times or more (rare): every clause of the window, in clause order
+                    if (__any_sync(0xFFFFFFFFu, gen)) {
+                        uint32_t min1 = 0xFFu;   // the lowest stream rank that holds the doc: its first sighting
+                        for (uint32_t j = 0; j < nt; ++j) {
+                            const int v = static_cast<int>(__shfl_sync(0xFFFFFFFFu, rk, j));   // where clause j lives
+                            const uint32_t rl = NEED_CNT ? __shfl_sync(0xFFFFFFFFu, role, v) : 0u;
+                            if (!((act0 >> v) & 1u)) continue;
+                            uint32_t b = 0;
+                            if (!slice_lower_bound(v, doc, b)) continue;
+                            if (gen && __ldg(docs + b) == doc) {
+                                if (NEED_CNT && rl == DGPU_ROLE_MUST_NOT) {
+                                    excluded = true;
+                                } else {
+                                    sum = __fadd_rn(sum, __ldg(scores + b));
+                                    ++c_ok;
+                                }
+                                ++cnt;
+                                min1 = min(min1, static_cast<uint32_t>(v));
+                            }
+                        }
+                        if (gen) {
+                            DGPU_ASSERT(cnt >= 3);
+                            first = min1;
+                            des = true;
+                        }
+                    }
+
+                    // -- a recorded first sighting: collects unless the doc was seen again (filter first, then the list)
+                    if (__any_sync(0xFFFFFFFFu, one)) {
+                        bool again = false;
+                        if (one) {
+                            const uint32_t h = (doc - ws) & (32u * kUnionFilterWords - 1u);
+                            again = ((filt[h >> 5] >> (h & 31u)) & 1u) != 0u;
+                        }
+                        uint32_t qm = __ballot_sync(0xFFFFFFFFu, again);   // (rare) really, or a hash collision?
+                        while (qm) {
+                            const int l = __ffs(qm) - 1;
+                            qm &= qm - 1u;
+                            uint32_t second_at = 0;
+                            const uint32_t kinds = list_lookup(__shfl_sync(0xFFFFFFFFu, doc, l), second_at);
+                            if (lane == l) again = kinds != 0u;
+                        }
+                        if (one && !again) {
+                            sum = __fadd_rn(sum, __ldg(scores + rpos));
+                            c_ok = 1;
+                            cnt = 1;
+                            first = ru;
+                            des = true;
+                        }
+                    }
+
                     bool match = des;
                     if (NEED_CNT)
                         match = des && !excluded && c_ok != 0 && (qd.n_must ? c_ok == qd.n_must : c_ok >= qd.min_should_match);
@@ -372,13 +550,13 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                     }
                     collect(doc, sum, match);
                 }
-                n_rec = 0;
-                __syncwarp();
-                if (!full) break;
             }
 
-            // ---- the window's bits back to zero
+            // ---- the window's bits back to zero; a window that had shrunk grows again when the list stayed short
             for (uint32_t i = lane; i < (wlen + 127u) >> 7; i += 32) reinterpret_cast<uint4*>(seen)[i] = make_uint4(0u, 0u, 0u, 0u);
+            filt[lane] = 0u;
+            if (w_cur < W && n_rec < kUnionRecords / 4) w_cur = min(W, w_cur << 1);
+            n_rec = 0;
             __syncwarp();
         }
 
