@@ -292,6 +292,7 @@ struct WorkItem {       // one (query, doc range) scored by one warp
 struct AccumParams {
     const dgpu_query* queries;
     const QTermRun* terms;
+    const dgpu_qterm* qterms;   // the same slice of the batch's query terms (idf, field)
     const dgpu_qfilter* filters;
     const WorkItem* items;
     const uint32_t* order;      // item ids by decreasing cost

@@ -185,7 +185,7 @@ struct dgpu_engine {
     int part_factor = 2;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
     int decode_ctas_per_sm = 64; // grid of decode_score_kernel (grid-stride over the decode work items)
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
-    int lane_merge = 1;      // queries of <= 16 terms go to lane_merge_topk_kernel (0: accumulated in windows)
+    int lane_merge = 3;      // queries of <= 32 terms: 3 = union_topk_kernel, 1 = staged_merge_topk_kernel, 2 = lane_merge_topk_kernel (<= 16 terms), 0 = accumulated in windows
     uint32_t lane_max_terms = 0;                 // most terms of any lane-merge query of the staged batch
     uint32_t n_lane_items = 0;
     uint32_t batch_filters = 0;                  // range filters of the staged batch
@@ -990,6 +990,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     AccumParams P{};
     P.queries = e->d_queries.p;
     P.terms = e->d_qruns.p;
+    P.qterms = e->d_terms.p;
     P.filters = e->d_filters.p;
     P.items = e->d_witems.p;
     P.order = e->d_order.p;

@@ -3,30 +3,33 @@
 // What a disjunction needs per posting is almost nothing: in a C2 query 98 % of the docs of the union are matched by
 // exactly ONE clause, and the score of such a doc is that clause's score (0.0f + s == s, BooleanQuery.cpp:232-241).
 // The expensive part of a merge - finding, for every doc, which clauses stand on it and adding their scores in clause
-// order - is only needed for the docs matched by two or more clauses and for the handful of docs that can enter the
-// top k. So the warp that owns a work item (a query, or a doc range of one) walks the doc range in windows of W docs
-// (W = 32K..64K: ONE BIT per doc in shared memory) and, per window, streams the runs of the query clause by clause:
+// order - is only needed for the docs that can enter the top k. So the warp that owns a work item (a query, or a doc
+// range of one) walks the doc range in windows of W docs (W = 32K..64K: ONE BIT per doc in shared memory) and, per
+// window, streams the runs of the query clause by clause, DENSEST FIRST:
 //   * 64 entries per iteration, two per lane, doc ids only (one coalesced 256-byte load, next chunk prefetched);
 //     each entry sets its doc's bit with a shared-memory atomicOr; the returned word says whether the doc had been
-//     seen before in this window. A first sighting is a hit (hit counts are exact: every posting is visited);
+//     seen before in this window. Every posting is visited, so hit counts are exact: the entries a clause has in the
+//     window (a difference of run positions) minus the later sightings;
 //   * the scores of a chunk are loaded only when the chunk's maximum score (written by decode_score_kernel next to
 //     the run, one float per 64 entries) reaches the running k-th best score: the sum of a doc matched by one clause
-//     is bounded by that maximum, so nothing that could be collected is skipped;
-//   * the clauses are streamed SPARSEST FIRST, so a doc that two clauses hold is first seen in the shorter run and
-//     seen again in the longer one. Every later sighting, and every first sighting whose score reaches the
-//     threshold, becomes a RECORD (doc, position in its run, clause); records are resolved at the end of the window,
-//     32 at a time (one per lane):
-//       - a doc seen exactly twice (almost all of them) looks for its ONE earlier sighting by bisecting the window's
-//         slices of the sparser clauses only - short slices; nobody ever bisects the densest run - and stops at the
-//         first hit. The two scores are added in clause order starting from 0.0f (BooleanQuery.cpp:119-126, :232-241);
-//       - third and later sightings are caught by a 1024-bit hashed filter of the docs seen twice (a hit is checked
-//         against the record list): such a doc gets ONE record that bisects every clause of the window and adds the
-//         scores of the clauses that hold it in clause order (the generic path, rare);
-//       - a recorded first sighting collects its doc unless the filter and the list say the doc was seen again.
-//     If the record list fills up inside a window (pathological overlaps, e.g. the same term in two clauses), the
-//     window is abandoned - cursors, hit count and bitmap restored - and walked again at half the size (down to 4
-//     docs, which cannot overflow with 32 clauses); the size grows back when windows stay well below the limit.
-// Instruction cost: ~0.4 warp-instructions per posting for the stream, against 3-5 for a T-way register merge.
+//     is bounded by that maximum, so nothing that could be collected is skipped. Such first sightings become RECORDS
+//     (doc, clause, position);
+//   * a later sighting becomes a record only if the doc could be collected. A doc sighted for the second time has
+//     exactly one earlier sighting: its sum is at most the chunk's maximum plus the LARGEST window maximum of the
+//     clauses streamed before. A third or later sighting (told apart by a 1024-bit hashed filter that every later
+//     sighting sets; a collision only loosens the bound) is bounded by the chunk's maximum plus the SUM of those
+//     maxima. The dense clauses come first and have the low scores (low idf), so the pairs of dense clauses - where
+//     nearly all docs held by two clauses are - fail this test once the top-k threshold has formed. Scores are
+//     non-negative, partial sums never exceed the whole sum, the threshold only rises: a doc whose bound is below
+//     the threshold when its last sighting is streamed can never be collected. (Queries with exclusions, required-match counts above
+//     one or negative boosts do not use the bound: every later sighting is recorded.);
+//   * records wait until two lane-fulls of them have gathered (across windows) and are resolved 32 at a time, one per
+//     lane: the lane bisects the slice every clause of the query has streamed since the list was last empty, adds the
+//     scores of the clauses that hold its doc in clause order starting from 0.0f (bit-exact, BooleanQuery.cpp:119-126),
+//     counts required / excluded clauses, applies the range filters and offers the doc to the top-k pool. Several
+//     records may exist for one doc; the one of the LAST clause in stream order that holds the doc collects it (it is
+//     the one whose bound covered every other clause), the others drop out.
+// Instruction cost: ~1.5 warp-instructions per posting, against 5 for a T-way register merge.
 //
 // MODE 0: plain disjunctions / term queries; 1: required-match counts and exclusions (minimumNumberShouldMatch,
 // MUST_NOT, MUST lists that are not intersected); 2: 1 + doc-value range filters (NumericRangeQuery.cpp:129-181).
@@ -41,15 +44,11 @@ namespace {
 constexpr int kUnionWarps = 1;                 // one warp per CTA: the bitmap starts at shared-memory offset 0, so the
                                                // address of a doc's word is two logic ops on (doc - window start)
 constexpr uint32_t kUnionChunk = 64;           // entries per iteration (lane l: entries 2l, 2l + 1)
-constexpr uint32_t kUnionRecords = 256;        // record list of a warp; a window that needs more is walked again at half size
+constexpr uint32_t kUnionRecords = 256;        // record list of a warp (meta = stream rank << 25 | position - slice start)
+constexpr uint32_t kUnionResolveAt = 64;       // records that make a window end resolve the list
+constexpr uint32_t kUnionMaxDefer = 16;        // windows a record may wait
 constexpr uint32_t kUnionFilterWords = 32;     // 1024 bits
-constexpr uint32_t kUnionMinWindow = 4;        // 4 docs x 32 clauses cannot overflow the record list
-// record kinds (meta = kind << 30 | stream rank of the clause << 25 | position in the run - position at window start)
-constexpr uint32_t kRecFirst = 0;   // first sighting whose score reaches the threshold: collects if the doc is not seen again
-constexpr uint32_t kRecSecond = 1;  // second sighting: collects the doc with the one earlier sighting
-constexpr uint32_t kRecAll = 2;     // third or later sighting: collects the doc through the all-clause path
-constexpr uint32_t kRecDead = 3;    // second sighting of a doc that was seen a third time
-constexpr uint32_t kRecOffMask = (1u << 25) - 1u;
+constexpr float kBoundSlack = 1.0001f;         // the bound is summed in stream order, the score in clause order
 
 __host__ __device__ inline size_t union_warp_smem_bytes(uint32_t window_docs, uint32_t cap_smem) {
     size_t b = window_docs / 8;                                  // seen bitmap
@@ -134,24 +133,27 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         DGPU_ASSERT(nt <= 32u);
         const bool mine = static_cast<uint32_t>(lane) < nt;
 
-        // ---- stream order: sparsest run first. `rk` (on lane j) is the stream rank of clause j; lane r then takes over
+        // ---- stream order: densest run first. `rk` (on lane j) is the stream rank of clause j; lane r then takes over
         // the clause of rank r (`cl`) and holds its stream state: `pos` is the first entry of the run not below the
         // current window start, `nd` that entry's doc (kDocEnd padding after the run: readable, says "end")
         uint32_t rk = 0, cl = 0;
         {
-            const uint32_t my_len = mine ? qt[lane].len : 0xFFFFFFFFu;
+            const uint32_t my_len = mine ? qt[lane].len : 0u;
             for (uint32_t i = 0; i < nt; ++i) {
                 const uint32_t li = __shfl_sync(0xFFFFFFFFu, my_len, i);
-                rk += (li < my_len || (li == my_len && i < static_cast<uint32_t>(lane))) ? 1u : 0u;
+                rk += (li > my_len || (li == my_len && i < static_cast<uint32_t>(lane))) ? 1u : 0u;
             }
             for (uint32_t i = 0; i < nt; ++i)
                 if (__shfl_sync(0xFFFFFFFFu, rk, i) == static_cast<uint32_t>(lane)) cl = i;
         }
-        uint32_t pos = 0, nd = kDocEnd, role = 0;
+        uint32_t pos = 0, nd = kDocEnd, rend = 0, role = 0;
+        bool idf_ok = true;
         if (mine) {
             const QTermRun r = qt[cl];
             pos = r.base;
+            rend = r.base + r.len;
             role = r.meta;
+            idf_ok = P.qterms[qd.term_begin + cl].idf >= 0.0f;   // (false for NaN too)
             if (lo > ix.doc_lo && r.len) {   // first entry with doc >= lo
                 uint32_t a = 0, b = r.len;
                 while (a < b) {
@@ -170,13 +172,17 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
             const bool one_ok = qd.n_must ? qd.n_must == 1 : qd.min_should_match <= 1;
             single_mask = one_ok ? ~not_mask : 0u;
         }
+        // the score bound on later sightings holds for plain disjunctions of non-negative scores
+        const bool bounded = single_mask == 0xFFFFFFFFu && __all_sync(0xFFFFFFFFu, idf_ok);
 
         uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
         uint64_t thresh = 0;        // key of the k-th best so far
         float thresh_f = __uint_as_float(0xFF800000u);   // its score (-inf until there is one): the stream's quick test
-        uint32_t hits = 0;          // per lane, modulo 2^32 (later sightings and mode 1 also take hits back)
-        uint32_t n_rec = 0;         // records of the current window (warp-uniform)
-        uint32_t w_cur = W;         // docs per window: W unless a window overflowed the record list
+        uint32_t hits = 0;          // per lane, modulo 2^32 (mode 1 also takes hits back)
+        uint32_t n_later = 0;       // later sightings counted as hits by position (warp-uniform)
+        uint32_t n_rec = 0;         // records waiting (warp-uniform)
+        uint32_t base = pos;        // what the record list refers to: the run position when the list was last empty
+        uint32_t waited = 0;        // windows since then
         auto prune = [&]() {
             if (BIGK) {   // large pool: select, do not sort
                 if (n_cand < static_cast<uint32_t>(P.k)) return;
@@ -222,57 +228,60 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
             }
             return ok;
         };
-        // is `dd` in the record list? kinds found: bit kRecSecond / kRecAll / kRecDead set in the result; `second_at` =
-        // where its live second sighting is
-        auto list_lookup = [&](uint32_t dd, uint32_t& second_at) -> uint32_t {
-            uint32_t kinds = 0;
-            for (uint32_t rb = 0; rb < n_rec; rb += 32) {
-                const uint32_t e = rb + lane;
-                const bool eq = e < n_rec && rec_doc[e] == dd;
-                const uint32_t ek = eq ? rec_meta[e] >> 30 : kRecFirst;
-                const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, ek == kRecSecond);
-                if (m2) {
-                    second_at = rb + __ffs(m2) - 1;
-                    kinds |= 1u << kRecSecond;
-                }
-                if (__any_sync(0xFFFFFFFFu, ek == kRecAll)) kinds |= 1u << kRecAll;
-                if (__any_sync(0xFFFFFFFFu, ek == kRecDead)) kinds |= 1u << kRecDead;
-            }
-            return kinds;
-        };
 
         for (;;) {
-            // ---- window: w_cur docs from the smallest next doc of any clause
+            // ---- window: W docs from the smallest next doc of any clause
             const uint32_t ws = opaque(__reduce_min_sync(0xFFFFFFFFu, nd));
-            if (ws >= hi) break;
-            const uint32_t we = opaque((hi - ws > w_cur) ? ws + w_cur : hi);
+            const bool last = ws >= hi;
+            const uint32_t we = opaque(last ? ws : ((hi - ws > W) ? ws + W : hi));
             const uint32_t wlen = opaque(we - ws);
-            const uint32_t act0 = __ballot_sync(0xFFFFFFFFu, nd < we);   // clauses with entries inside the window
-            const uint32_t wpos = pos, wnd = nd, whits = hits;          // (restored if the window overflows)
-            bool overflow = false;
+            const uint32_t act0 = __ballot_sync(0xFFFFFFFFu, nd < we);   // clauses with entries inside the window (none if last)
+            const uint32_t wpos = pos;
+            if (n_rec == 0) {
+                base = pos;
+                waited = 0;
+            }
+            uint32_t act = act0, done = 0;
+            float pre = 0.0f;    // sum of the window maxima of the clauses streamed so far (warp-uniform)
+            float pmx = 0.0f;    // the largest of them
+            int u = -1;          // clause being streamed (-1: pick the next one)
+            uint32_t c = 0;      // its current chunk (multiple of kUnionChunk)
+            float wm = 0.0f;     // largest chunk maximum of the clause in this window so far
+            int pf_u = -1;       // clause whose first chunk has been prefetched into pf_d / pf_cm
+            uint2 pf_d = make_uint2(0u, 0u);
+            float pf_cm = 0.0f;
 
-            // ---- stream the clauses, sparsest first
-            {
-                uint32_t act = act0;
-                int pf_u = __ffs(act) - 1;   // clause whose first chunk is in pf_d / pf_cm
-                uint32_t pf_c = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
-                uint2 pf_d = __ldg(reinterpret_cast<const uint2*>(docs + pf_c) + lane);
-                float pf_cm = __ldg(cmax + (pf_c >> 6));
-                while (act && !overflow) {
-                    const int u = pf_u;
-                    act &= act - 1u;
-                    uint32_t c = pf_c;   // current chunk of the clause (multiple of kUnionChunk)
-                    uint2 d = pf_d;
-                    float cm = pf_cm;
-                    if (act) {   // the first chunk of the next clause is on its way while this one is streamed
-                        pf_u = __ffs(act) - 1;
-                        pf_c = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
-                        pf_d = __ldg(reinterpret_cast<const uint2*>(docs + pf_c) + lane);
-                        pf_cm = __ldg(cmax + (pf_c >> 6));
+            for (;;) {
+                // ---- stream clauses in order until the window is done or the record list is nearly full
+                bool full = false;
+                while (!full) {
+                    uint2 d;
+                    float cm;
+                    if (u < 0) {
+                        if (!act) break;
+                        u = __ffs(act) - 1;
+                        act &= act - 1u;
+                        c = __shfl_sync(0xFFFFFFFFu, pos, u) & ~(kUnionChunk - 1u);
+                        wm = __uint_as_float(0xFF800000u);
+                        if (pf_u == u) {
+                            d = pf_d;
+                            cm = pf_cm;
+                        } else {
+                            d = __ldg(reinterpret_cast<const uint2*>(docs + c) + lane);
+                            cm = __ldg(cmax + (c >> 6));
+                        }
+                        if (act) {   // the first chunk of the next clause is on its way while this one is streamed
+                            pf_u = __ffs(act) - 1;
+                            const uint32_t cn = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
+                            pf_d = __ldg(reinterpret_cast<const uint2*>(docs + cn) + lane);
+                            pf_cm = __ldg(cmax + (cn >> 6));
+                        }
+                    } else {   // resumed after a resolve in the middle of a clause
+                        d = __ldg(reinterpret_cast<const uint2*>(docs + c) + lane);
+                        cm = __ldg(cmax + (c >> 6));
                     }
                     const bool single_ok = !NEED_CNT || ((single_mask >> u) & 1u);
-                    const uint32_t wpos_u = __shfl_sync(0xFFFFFFFFu, wpos, u);
-                    const uint32_t meta_u = (static_cast<uint32_t>(u) << 25) + 2u * lane - wpos_u;   // + chunk (+ 1): rank and offset of an entry
+                    const uint32_t meta_u = (static_cast<uint32_t>(u) << 25) + 2u * lane - __shfl_sync(0xFFFFFFFFu, base, u);   // + chunk (+ 1)
                     const uint2* pd = reinterpret_cast<const uint2*>(docs + c) + lane;   // this lane's two entries of the chunk
                     const float* pcm = cmax + (c >> 6);
                     for (;;) {
@@ -284,7 +293,9 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         if (more) {
                             dn = __ldg(pd + 32);
                             cmn = __ldg(pcm + 1);
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + 128));   // four chunks ahead
                         }
+                        wm = fmaxf(wm, cm);
                         // entries before the window (consumed earlier) and after it fail the same unsigned compare
                         const uint32_t r0 = d.x - ws, r1 = d.y - ws;
                         const bool in0 = r0 < wlen, in1 = r1 < wlen;
@@ -297,10 +308,29 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         const bool any_later = __any_sync(0xFFFFFFFFu, dup != 0u);
                         if (any_later || (single_ok && (FILTER || cm >= thresh_f))) {
                             const bool l0 = (o0 & b0) != 0u, l1 = (o1 & b1) != 0u;   // later sightings
-                            bool rec0 = l0, rec1 = l1;
-                            uint32_t k0 = kRecSecond, k1 = kRecSecond;
-                            if (!FILTER) {   // positions count the clause's entries in the window as hits: take these back
-                                if (single_ok) hits -= (l0 ? 1u : 0u) + (l1 ? 1u : 0u);
+                            bool rec0 = false, rec1 = false;
+                            if (any_later) {
+                                // positions count the clause's entries in the window as hits: take the later sightings back
+                                if (!FILTER && single_ok) n_later += __popc(__ballot_sync(0xFFFFFFFFu, l0)) + __popc(__ballot_sync(0xFFFFFFFFu, l1));
+                                // every later sighting sets its doc's bit in the hashed filter; a bit already set: the doc may
+                                // have been seen twice before
+                                const uint32_t h0 = r0 & (32u * kUnionFilterWords - 1u), h1 = r1 & (32u * kUnionFilterWords - 1u);
+                                bool t0 = false, t1 = false;
+                                if (l0) t0 = ((atomicOr(filt + (h0 >> 5), 1u << (h0 & 31u)) >> (h0 & 31u)) & 1u) != 0u;
+                                if (l1) t1 = ((atomicOr(filt + (h1 >> 5), 1u << (h1 & 31u)) >> (h1 & 31u)) & 1u) != 0u;
+                                // can a doc seen again here be collected? second sighting: this chunk's maximum plus the largest
+                                // window maximum of the clauses streamed before; later ones: plus the sum of those maxima
+                                float ub2 = __fadd_rn(cm, pmx), ub3 = __fadd_rn(cm, pre);
+                                if (FILTER) {
+                                    for (uint32_t f = 0; f < nf; ++f) {   // (the range clauses score 1.0f each)
+                                        ub2 = __fadd_rn(ub2, 1.0f);
+                                        ub3 = __fadd_rn(ub3, 1.0f);
+                                    }
+                                }
+                                const bool keep2 = !(bounded && __fmul_rn(ub2, kBoundSlack) < thresh_f);
+                                const bool keep3 = !(bounded && __fmul_rn(ub3, kBoundSlack) < thresh_f);
+                                rec0 = l0 && (t0 ? keep3 : keep2);
+                                rec1 = l1 && (t1 ? keep3 : keep2);
                             }
                             if (single_ok && (FILTER || cm >= thresh_f)) {   // first sightings: hits of mode 2, candidates
                                 bool new0 = in0 && !l0, new1 = in1 && !l1;
@@ -322,64 +352,27 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                             s1 = __fadd_rn(s1, 1.0f);
                                         }
                                     }
-                                    if (new0 && s0 >= thresh_f) {
-                                        rec0 = true;
-                                        k0 = kRecFirst;
-                                    }
-                                    if (new1 && s1 >= thresh_f) {
-                                        rec1 = true;
-                                        k1 = kRecFirst;
-                                    }
-                                }
-                            }
-                            if (any_later) {
-                                // the hashed filter of the docs seen twice: a bit already set may mean a third sighting
-                                const uint32_t h0 = r0 & (32u * kUnionFilterWords - 1u), h1 = r1 & (32u * kUnionFilterWords - 1u);
-                                bool t0 = false, t1 = false;
-                                if (l0) t0 = ((atomicOr(filt + (h0 >> 5), 1u << (h0 & 31u)) >> (h0 & 31u)) & 1u) != 0u;
-                                if (l1) t1 = ((atomicOr(filt + (h1 >> 5), 1u << (h1 & 31u)) >> (h1 & 31u)) & 1u) != 0u;
-                                if (__any_sync(0xFFFFFFFFu, t0 || t1)) {
-                                    // (rare) a doc that already has a live second sighting gets ONE all-clause record instead;
-                                    // a later sighting of a doc that has one leaves a dead record; else: a hash collision
-                                    __syncwarp();
-#pragma unroll
-                                    for (int j = 0; j < 2; ++j) {
-                                        uint32_t tm = __ballot_sync(0xFFFFFFFFu, j ? t1 : t0);
-                                        while (tm) {
-                                            const int l = __ffs(tm) - 1;
-                                            tm &= tm - 1u;
-                                            const uint32_t dd = __shfl_sync(0xFFFFFFFFu, j ? d.y : d.x, l);
-                                            uint32_t second_at = 0;
-                                            const uint32_t kinds = list_lookup(dd, second_at);
-                                            if (lane == l) {
-                                                uint32_t& kk = j ? k1 : k0;
-                                                if (kinds & (1u << kRecAll)) {
-                                                    kk = kRecDead;
-                                                } else if (kinds & (1u << kRecSecond)) {
-                                                    rec_meta[second_at] = (rec_meta[second_at] & ~(3u << 30)) | (kRecDead << 30);
-                                                    kk = kRecAll;
-                                                }
-                                            }
-                                            __syncwarp();
-                                        }
-                                    }
+                                    rec0 = rec0 || (new0 && s0 >= thresh_f);
+                                    rec1 = rec1 || (new1 && s1 >= thresh_f);
                                 }
                             }
                             const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, rec0), m1 = __ballot_sync(0xFFFFFFFFu, rec1);
-                            DGPU_ASSERT(n_rec + 64u <= kUnionRecords);
-                            if (rec0) {
-                                const uint32_t e = n_rec + __popc(m0 & lt_mask);
-                                rec_doc[e] = d.x;
-                                rec_meta[e] = (k0 << 30) | (meta_u + c);
+                            if (m0 | m1) {
+                                DGPU_ASSERT(n_rec + 64u <= kUnionRecords);
+                                if (rec0) {
+                                    const uint32_t e = n_rec + __popc(m0 & lt_mask);
+                                    rec_doc[e] = d.x;
+                                    rec_meta[e] = meta_u + c;
+                                }
+                                n_rec += __popc(m0);
+                                if (rec1) {
+                                    const uint32_t e = n_rec + __popc(m1 & lt_mask);
+                                    rec_doc[e] = d.y;
+                                    rec_meta[e] = meta_u + c + 1u;
+                                }
+                                n_rec += __popc(m1);
+                                if (n_rec + 64u > kUnionRecords) full = true;
                             }
-                            n_rec += __popc(m0);
-                            if (rec1) {
-                                const uint32_t e = n_rec + __popc(m1 & lt_mask);
-                                rec_doc[e] = d.y;
-                                rec_meta[e] = (k1 << 30) | (meta_u + c + 1u);
-                            }
-                            n_rec += __popc(m1);
-                            if (n_rec + 64u > kUnionRecords) overflow = true;
                         }
                         if (!more) {
                             // the clause's next window starts at the first entry >= we: the entries below are a prefix
@@ -389,153 +382,72 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                             const uint32_t x = __shfl_sync(0xFFFFFFFFu, d.x, below >> 1), y = __shfl_sync(0xFFFFFFFFu, d.y, below >> 1);
                             if (lane == u) {
                                 // without filters every entry of the clause inside the window counts as a hit here (later
-                                // sightings were taken back above; mode 1: if one matching clause makes a hit at all)
+                                // sightings are taken back; mode 1: if one matching clause makes a hit at all)
                                 if (!FILTER && single_ok) hits += c + below - pos;
                                 pos = c + below;
                                 nd = (below & 1u) ? y : x;
                             }
+                            pre = __fadd_rn(pre, fmaxf(wm, 0.0f));
+                            pmx = fmaxf(pmx, wm);
+                            done |= 1u << u;
+                            u = -1;
                             break;
                         }
-                        if (overflow) break;
                         c += kUnionChunk;
                         pd += 32;
                         pcm += 1;
                         d = dn;
                         cm = cmn;
+                        if (full) break;
                     }
                 }
-            }
-            __syncwarp();
-
-            if (overflow) {
-                // ---- too many records: forget this window and walk it again at half the size
-                pos = wpos;
-                nd = wnd;
-                hits = whits;
-                n_rec = 0;
-                for (uint32_t i = lane; i < (wlen + 127u) >> 7; i += 32) reinterpret_cast<uint4*>(seen)[i] = make_uint4(0u, 0u, 0u, 0u);
-                filt[lane] = 0u;
-                DGPU_ASSERT(w_cur > kUnionMinWindow);
-                w_cur = max(kUnionMinWindow, min(w_cur, wlen) >> 1);
                 __syncwarp();
-                continue;
-            }
+                // resolve now? inside a window when the list is nearly full; at a window end when two lane-fulls have
+                // gathered or the oldest record has waited long enough; at the end of the item
+                ++waited;
+                if (!(full || last || n_rec >= kUnionResolveAt || (n_rec && waited >= kUnionMaxDefer))) break;
 
-            // ---- resolve the records, one per lane. The window slice of the clause of rank v is [wpos, pos)
-            {
-                // lower bound of `doc` in the window slice of the clause of rank v (the trip count is warp-uniform; the entry
-                // after a slice is >= we or padding, never `doc`)
-                auto slice_lower_bound = [&](int v, uint32_t doc, uint32_t& b) -> bool {
-                    const uint32_t v_lo = __shfl_sync(0xFFFFFFFFu, wpos, v);
-                    uint32_t len = __shfl_sync(0xFFFFFFFFu, pos, v) - v_lo;
-                    if (len == 0) return false;
-                    b = v_lo;
-                    while (len > 1) {
-                        const uint32_t half = len >> 1;
-                        if (__ldg(docs + b + half - 1u) < doc) b += half;
-                        len -= half;
-                    }
-                    if (__ldg(docs + b) < doc) b += 1u;
-                    DGPU_ASSERT(static_cast<uint64_t>(b) < P.run_total);
-                    return true;
-                };
-                for (uint32_t base = 0; base < n_rec; base += 32) {
-                    const bool valid = base + lane < n_rec;
-                    const uint32_t doc = valid ? rec_doc[base + lane] : 0u;
-                    const uint32_t meta = valid ? rec_meta[base + lane] : (kRecDead << 30);
-                    const uint32_t kind = meta >> 30, ru = (meta >> 25) & 31u;
-                    const uint32_t rpos = __shfl_sync(0xFFFFFFFFu, wpos, ru) + (meta & kRecOffMask);   // where the sighting is in its run
-                    const bool two = kind == kRecSecond, one = kind == kRecFirst, gen = kind == kRecAll;
+                // ---- resolve the records, one per lane: where is the doc among the entries every clause has streamed
+                // since `base`? A clause that is still being streamed in this window is searched up to where the
+                // window can reach (docs are distinct and sorted: at most wlen entries from wpos)
+                uint32_t s_hi = pos;
+                if (((act0 & ~done) >> lane) & 1u) s_hi = min(wpos + wlen, rend);
+                for (uint32_t rb = 0; rb < n_rec; rb += 32) {
+                    const bool valid = rb + lane < n_rec;
+                    const uint32_t doc = valid ? rec_doc[rb + lane] : 0u;
+                    const uint32_t ru = valid ? rec_meta[rb + lane] >> 25 : 0xFFu;
                     float sum = 0.0f;
-                    uint32_t cnt = 0, c_ok = 0, first = 0u;   // clauses that hold the doc; not excluding ones; rank of the first sighting
-                    bool excluded = false, des = false;       // des: this record collects its doc
-
-                    // -- seen exactly twice: the one earlier sighting is in a sparser clause
-                    if (__any_sync(0xFFFFFFFFu, two)) {
-                        const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, two ? ru : 0u);
-                        uint32_t am = act0 & ((1u << top) - 1u);
-                        bool found = false;
-                        uint32_t fv = 0, fpos = 0;
-                        while (am && __any_sync(0xFFFFFFFFu, two && !found)) {
-                            const int v = __ffs(am) - 1;
-                            am &= am - 1u;
-                            uint32_t b = 0;
-                            if (!slice_lower_bound(v, doc, b)) continue;
-                            if (two && !found && static_cast<uint32_t>(v) < ru && __ldg(docs + b) == doc) {
-                                found = true;
-                                fv = static_cast<uint32_t>(v);
-                                fpos = b;
+                    uint32_t cnt = 0, c_ok = 0, first = 0xFFu, top = 0u;   // clauses that hold the doc; not excluding ones; lowest, highest rank
+                    bool excluded = false;
+                    for (uint32_t j = 0; j < nt; ++j) {   // clause order: the order of the sum
+                        const int v = static_cast<int>(__shfl_sync(0xFFFFFFFFu, rk, j));   // where clause j lives
+                        const uint32_t rl = NEED_CNT ? __shfl_sync(0xFFFFFFFFu, role, v) : 0u;
+                        const uint32_t v_lo = __shfl_sync(0xFFFFFFFFu, base, v);
+                        uint32_t len = __shfl_sync(0xFFFFFFFFu, s_hi, v) - v_lo;
+                        if (len == 0) continue;
+                        uint32_t b = v_lo;   // branch-free lower bound; the trip count depends on len only (warp-uniform)
+                        while (len > 1) {
+                            const uint32_t half = len >> 1;
+                            if (__ldg(docs + b + half - 1u) < doc) b += half;
+                            len -= half;
+                        }
+                        if (__ldg(docs + b) < doc) b += 1u;
+                        DGPU_ASSERT(static_cast<uint64_t>(b) < P.run_total);
+                        if (valid && __ldg(docs + b) == doc) {   // (the entry after a slice is a later doc or padding: never `doc`)
+                            if (NEED_CNT && rl == DGPU_ROLE_MUST_NOT) {
+                                excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
+                            } else {
+                                sum = __fadd_rn(sum, __ldg(scores + b));
+                                ++c_ok;
                             }
-                        }
-                        DGPU_ASSERT(!two || found);
-                        const uint32_t cl_a = __shfl_sync(0xFFFFFFFFu, cl, fv), cl_b = __shfl_sync(0xFFFFFFFFu, cl, ru);
-                        const uint32_t rl_a = __shfl_sync(0xFFFFFFFFu, role, fv), rl_b = __shfl_sync(0xFFFFFFFFu, role, ru);
-                        if (two && found) {
-                            const float s_a = __ldg(scores + fpos), s_b = __ldg(scores + rpos);
-                            const bool a_first = cl_a < cl_b;   // clause order of the sum
-                            const float s_x = a_first ? s_a : s_b, s_y = a_first ? s_b : s_a;
-                            const uint32_t rl_x = a_first ? rl_a : rl_b, rl_y = a_first ? rl_b : rl_a;
-                            if (NEED_CNT && rl_x == DGPU_ROLE_MUST_NOT) excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
-                            else { sum = __fadd_rn(sum, s_x); ++c_ok; }
-                            if (NEED_CNT && rl_y == DGPU_ROLE_MUST_NOT) excluded = true;
-                            else { sum = __fadd_rn(sum, s_y); ++c_ok; }
-                            cnt = 2;
-                            first = fv;
-                            des = true;
+                            ++cnt;
+                            first = min(first, static_cast<uint32_t>(v));
+                            top = max(top, static_cast<uint32_t>(v));
                         }
                     }
-
-                    // -- seen three times or more (rare): every clause of the window, in clause order
-                    if (__any_sync(0xFFFFFFFFu, gen)) {
-                        uint32_t min1 = 0xFFu;   // the lowest stream rank that holds the doc: its first sighting
-                        for (uint32_t j = 0; j < nt; ++j) {
-                            const int v = static_cast<int>(__shfl_sync(0xFFFFFFFFu, rk, j));   // where clause j lives
-                            const uint32_t rl = NEED_CNT ? __shfl_sync(0xFFFFFFFFu, role, v) : 0u;
-                            if (!((act0 >> v) & 1u)) continue;
-                            uint32_t b = 0;
-                            if (!slice_lower_bound(v, doc, b)) continue;
-                            if (gen && __ldg(docs + b) == doc) {
-                                if (NEED_CNT && rl == DGPU_ROLE_MUST_NOT) {
-                                    excluded = true;
-                                } else {
-                                    sum = __fadd_rn(sum, __ldg(scores + b));
-                                    ++c_ok;
-                                }
-                                ++cnt;
-                                min1 = min(min1, static_cast<uint32_t>(v));
-                            }
-                        }
-                        if (gen) {
-                            DGPU_ASSERT(cnt >= 3);
-                            first = min1;
-                            des = true;
-                        }
-                    }
-
-                    // -- a recorded first sighting: collects unless the doc was seen again (filter first, then the list)
-                    if (__any_sync(0xFFFFFFFFu, one)) {
-                        bool again = false;
-                        if (one) {
-                            const uint32_t h = (doc - ws) & (32u * kUnionFilterWords - 1u);
-                            again = ((filt[h >> 5] >> (h & 31u)) & 1u) != 0u;
-                        }
-                        uint32_t qm = __ballot_sync(0xFFFFFFFFu, again);   // (rare) really, or a hash collision?
-                        while (qm) {
-                            const int l = __ffs(qm) - 1;
-                            qm &= qm - 1u;
-                            uint32_t second_at = 0;
-                            const uint32_t kinds = list_lookup(__shfl_sync(0xFFFFFFFFu, doc, l), second_at);
-                            if (lane == l) again = kinds != 0u;
-                        }
-                        if (one && !again) {
-                            sum = __fadd_rn(sum, __ldg(scores + rpos));
-                            c_ok = 1;
-                            cnt = 1;
-                            first = ru;
-                            des = true;
-                        }
-                    }
-
+                    // the record of the last clause in stream order that holds the doc collects it
+                    DGPU_ASSERT(!valid || (cnt >= 1 && ru <= top && ru >= first));
+                    const bool des = valid && ru == top;
                     bool match = des;
                     if (NEED_CNT)
                         match = des && !excluded && c_ok != 0 && (qd.n_must ? c_ok == qd.n_must : c_ok >= qd.min_should_match);
@@ -550,19 +462,23 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                     }
                     collect(doc, sum, match);
                 }
+                n_rec = 0;
+                base = wpos;   // what is recorded in the rest of this window lies behind the window start
+                waited = 0;
+                __syncwarp();
+                if (!full) break;
             }
+            if (last) break;
 
-            // ---- the window's bits back to zero; a window that had shrunk grows again when the list stayed short
+            // ---- the window's bits back to zero
             for (uint32_t i = lane; i < (wlen + 127u) >> 7; i += 32) reinterpret_cast<uint4*>(seen)[i] = make_uint4(0u, 0u, 0u, 0u);
             filt[lane] = 0u;
-            if (w_cur < W && n_rec < kUnionRecords / 4) w_cur = min(W, w_cur << 1);
-            n_rec = 0;
             __syncwarp();
         }
 
         // ---- final select
         __syncwarp();
-        hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+        hits = __reduce_add_sync(0xFFFFFFFFu, hits) - n_later;
         if (BIGK && n_cand > static_cast<uint32_t>(P.k)) prune();   // sort k keys, not the whole pool
         const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
         for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;

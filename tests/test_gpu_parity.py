@@ -76,7 +76,7 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
 # <= 16 terms), 3 = union_topk_kernel (bitmap windows of union_window_docs docs); the longer queries of the file are
 # scored by the windows whatever lane_merge says
 _DEFAULTS = {"window_docs": 0, "stage_log2": 0, "splits": 0, "warps": 4, "warps_per_sm": 20, "intersect": 1,
-             "lane_merge": 1, "lane_ring_entries": 2176, "union_window_docs": 32768, "lane_ctas_per_sm": 0}
+             "lane_merge": 3, "lane_ring_entries": 2176, "union_window_docs": 32768, "lane_ctas_per_sm": 0}
 _TUNINGS = [
     dict(lane_merge=0, warps_per_sm=16),
     dict(lane_merge=0, window_docs=1024, splits=1, warps_per_sm=16, intersect=0),

@@ -21,11 +21,9 @@ for r in rows:
 src = open('diagon_b200/csrc/union_kernels.cuh').read().split('\n')
 def ln(pat):
     return next(i for i, l in enumerate(src, 1) if pat in l)
-marks = [('item setup', ln('uint32_t ticket = 0;')), ('window setup', ln('// ---- window: w_cur docs from')), ('visit', ln('while (act && !overflow) {')),
+marks = [('item setup', ln('uint32_t ticket = 0;')), ('window setup', ln('// ---- window: W docs from')), ('visit', ln('while (!full) {')),
          ('stream fast', ln('DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk')), ('slow path', ln('const bool l0 = (o0 & b0)')), ('term end', ln('if (!more) {')),
-         ('overflow', ln('if (overflow) {')), ('resolve bisect', ln('auto slice_lower_bound')), ('resolve two', ln('// -- seen exactly twice')),
-         ('resolve all', ln('// -- seen three times or more')), ('resolve one', ln('// -- a recorded first sighting: collects unless')),
-         ('resolve tail', ln('bool match = des;')), ('clear+final', ln("// ---- the window's bits back to zero")), ('end', len(src) + 1)]
+         ('resolve', ln('// resolve now?')), ('clear+final', ln("// ---- the window's bits back to zero")), ('end', len(src) + 1)]
 tot = sum(agg.values()); ts = sum(samp.values())
 print(f"total warp instructions {tot} = {tot / postings:.3f} per posting")
 for (name, a), (_, b) in zip(marks, marks[1:]):
@@ -36,10 +34,9 @@ i = sum(v for (f, l), v in agg.items() if not f.startswith('union_kernels')); s 
 print(f"inlined headers  instr {i / tot * 100:5.1f}% ({i / postings:.3f}/posting) samples {s / ts * 100:5.1f}%")
 i = sum(v for (f, l), v in agg.items() if f.startswith('union_kernels') and l < marks[0][1])
 print(f"helpers          ({i / postings:.3f}/posting)")
-for pat, what in (('const uint32_t ws = opaque', 'windows'), ('const int u = pf_u;', 'visits'), ('const bool more =', 'chunk iterations'), ('const bool l0 =', 'slow path'),
-                  ('if (overflow) {', 'window ends'), ('w_cur = max(kUnionMinWindow', 'overflows'), ('const bool valid = base + lane < n_rec;', 'record batches'),
-                  ('if (!slice_lower_bound(v, doc, b)) continue;', 'clause searches'), ('if (__ldg(docs + b + half - 1u) < doc) b += half;', 'bisect steps'),
-                  ('while (tm) {', 'third-sighting lookups')):
+for pat, what in (('const uint32_t ws = opaque', 'windows'), ('u = __ffs(act) - 1;', 'visits'), ('const bool more =', 'chunk iterations'), ('const bool l0 =', 'slow path'),
+                  ('const uint32_t m0 = __ballot_sync', 'slow path (m0)'), ('rec_meta[e] = meta_u + c;', 'appends'), ('const bool valid = rb + lane < n_rec;', 'record batches'),
+                  ('if (len == 0) continue;', 'clause searches'), ('if (__ldg(docs + b + half - 1u) < doc) b += half;', 'bisect steps')):
     for i, l in enumerate(src, 1):
         if pat in l and ('union_kernels.cuh', i) in per:
             xs = per[('union_kernels.cuh', i)]
