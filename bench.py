@@ -77,6 +77,7 @@ def parse_args():
     ap.add_argument("--pipeline-chunks", type=int, default=0, help="chunks of the end-to-end text call (1 = no host/device overlap)")
     ap.add_argument("--lane-ring-entries", type=int, default=0)
     ap.add_argument("--union-window-docs", type=int, default=0, help="docs per window (bits of shared memory) of union_topk_kernel")
+    ap.add_argument("--union-max-overlap", type=int, default=-1, help="percent of expected later sightings above which a query goes to staged_merge_topk_kernel")
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -268,13 +269,13 @@ def reference_arm(args, corpus_name, log_name, kind, k, steps, warmup, full):
 
 # ------------------------------------------------------------------------------------------------ main
 def lane_kernel_name(bstats):
-    return {1: "staged_merge_topk_kernel", 2: "lane_merge_topk_kernel", 3: "union_topk_kernel"}.get(int(bstats[11]), "accumulate_topk_kernel")
+    return "lane_merge_topk_kernel" if int(bstats[11]) == 2 else "staged_merge_topk_kernel"
 
 
 def dominant_kernel(bstats):
     """The scoring kernel most work items of the batch went to (they run one after the other in phase [1])."""
     items = {"accumulate_topk_kernel": int(bstats[6]), "intersect_topk_kernel": int(bstats[7]),
-             lane_kernel_name(bstats): int(bstats[10])}
+             lane_kernel_name(bstats): int(bstats[10]), "union_topk_kernel": int(bstats[13])}
     return max(items, key=items.get)
 
 
@@ -359,6 +360,8 @@ def main():
         reader.set_option("lane_merge", args.lane_merge)
     if args.union_window_docs:
         reader.set_option("union_window_docs", args.union_window_docs)
+    if args.union_max_overlap >= 0:
+        reader.set_option("union_max_overlap", args.union_max_overlap)
     if args.lane_ring_entries:
         reader.set_option("lane_ring_entries", args.lane_ring_entries)
     if args.pipeline_chunks:
@@ -537,7 +540,7 @@ def main():
                 "postings_per_s": stats["postings"] / (float(kt[0]) / 1e3),
                 "step_ms_by_kernel": {"decode_score_kernel": med[0], "scoring_kernels": med[1], "merge_items_kernel": med[2]},
                 "work_items": {"accumulate_topk_kernel": int(bstats[6]), "intersect_topk_kernel": int(bstats[7]),
-                               lane_kernel_name(bstats): int(bstats[10])}}
+                               lane_kernel_name(bstats): int(bstats[10]), "union_topk_kernel": int(bstats[13])}}
     if batched and int(bstats[10]) and int(bstats[11]) == 1:
         roofline["ring_entries_per_warp"] = int(bstats[12])
     if batched and med[0] > 0:

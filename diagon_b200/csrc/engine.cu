@@ -187,10 +187,13 @@ struct dgpu_engine {
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
     int lane_merge = 3;      // queries of <= 32 terms: 3 = union_topk_kernel, 1 = staged_merge_topk_kernel, 2 = lane_merge_topk_kernel (<= 16 terms), 0 = accumulated in windows
     uint32_t lane_max_terms = 0;                 // most terms of any lane-merge query of the staged batch
-    uint32_t n_lane_items = 0;
+    uint32_t n_lane_items = 0;                   // items of the register-merge kernels (staged / lane merge)
+    uint32_t n_union_items = 0;                  // items of union_topk_kernel
     uint32_t batch_filters = 0;                  // range filters of the staged batch
     int lane_ring_entries = 2176;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
     int union_window_docs = 32768;  // docs per window (one bit each in shared memory) of union_topk_kernel
+    int union_max_overlap = 15;     // lane_merge = 3: a query whose expected later sightings exceed this percentage of its
+                                    // postings (dense terms on a small index) is merged in registers by staged_merge_topk_kernel
     int pipeline_chunks = 4;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
     int pipeline_min = 2048;        // batches of fewer queries are not cut
     bool shadow = false;            // shares another engine's uploaded index
@@ -378,6 +381,11 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->union_window_docs = static_cast<int>(value);
         return 0;
     }
+    if (!std::strcmp(name, "union_max_overlap")) {
+        if (value < 0 || value > 100000) return fail("union_max_overlap (percent) must be in [0, 100000]");
+        e->union_max_overlap = static_cast<int>(value);
+        return 0;
+    }
     if (!std::strcmp(name, "pipeline_chunks")) {
         if (value < 1 || value > 64) return fail("pipeline_chunks must be in [1, 64]");
         e->pipeline_chunks = static_cast<int>(value);
@@ -451,6 +459,7 @@ int dgpu_engine_sync_options(dgpu_engine* dst, const dgpu_engine* src) {
     dst->lane_merge = src->lane_merge;
     dst->lane_ring_entries = src->lane_ring_entries;
     dst->union_window_docs = src->union_window_docs;
+    dst->union_max_overlap = src->union_max_overlap;
     dst->lane_ctas_per_sm = src->lane_ctas_per_sm;
     dst->pool_smem_cap = src->pool_smem_cap;
     dst->pipeline_chunks = src->pipeline_chunks;
@@ -566,6 +575,10 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         std::string error;
     };
     std::vector<Partial> partial(256);
+    uint32_t pool_cap = 64;   // (as plan_batched sizes the candidate pool)
+    while (pool_cap < 2u * static_cast<uint32_t>(k) || pool_cap < static_cast<uint32_t>(k) + 32u) pool_cap <<= 1;
+    const bool union_fits = pool_cap <= static_cast<uint32_t>(e->pool_smem_cap) &&
+                            static_cast<uint64_t>(e->ix.doc_hi - e->ix.doc_lo) > 2ull * static_cast<uint64_t>(e->union_window_docs);
     dgpu::parallel_for(b->n_queries, n_threads, [&](size_t q_lo, size_t q_hi, int th) {
         Partial& pt = partial[static_cast<size_t>(th) & 255];
         auto bad = [&](uint32_t q, const char* what) {
@@ -581,16 +594,13 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             // a pure conjunction (every term MUST) of 2..32 terms is intersected, everything else is accumulated
             bool all_must = e->kernel == 3 && e->intersect && nt_q >= 2 && nt_q <= 32 && qd.n_must == nt_q;
             for (uint32_t t = qd.term_begin; all_must && t < qd.term_end; ++t) all_must = b->terms[t].role == DGPU_ROLE_MUST;
-            // class of the query: 2 = intersected, 1 = merged document-at-a-time by lanes, 0 = accumulated in windows
+            // class of the query: 3 = intersected, 2 = bitmap union, 1 = merged document-at-a-time in registers, 0 = accumulated
+            // in windows (2 or 1 is settled below, when the lengths of its posting lists are known)
             const bool lane = !all_must && e->kernel == 3 && e->lane_merge &&
                               nt_q <= (e->lane_merge == 2 ? kLaneMergeMaxTerms : kStagedMergeMaxTerms);
-            is_and[q] = all_must ? 2 : (lane ? 1 : 0);
-            if (!all_must) {
-                if (lane) pt.lane_max_terms = std::max(pt.lane_max_terms, nt_q);
-                else pt.max_terms = std::max(pt.max_terms, nt_q);
-                if (qd.n_must > 1 || qd.min_should_match > 1) pt.need_cnt = true;
-            }
+            if (!all_must && (qd.n_must > 1 || qd.min_should_match > 1)) pt.need_cnt = true;
             uint64_t c = 0, lead = ~0ull;
+            double sum_len = 0.0, sum_sq = 0.0;
             uint32_t heavy_nb = 0;
             for (uint32_t t = qd.term_begin; t < qd.term_end; ++t) {
                 const dgpu_qterm& qt = b->terms[t];
@@ -609,10 +619,23 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
                     }
                     run.pad = tb;
                     run.len = nb * DGPU_BLOCK_POSTINGS;
+                    sum_len += run.len;
+                    sum_sq += static_cast<double>(run.len) * run.len;
                 } else {
                     lead = 0;   // a term that is absent here: a conjunction has no hits on this GPU
                 }
                 qruns[t] = run;
+            }
+            // union_topk_kernel pays per doc that several clauses hold (independent lists: sum over pairs of len_i * len_j / docs)
+            const double later = (sum_len * sum_len - sum_sq) * 0.5 / std::max(1.0, static_cast<double>(e->ix.doc_hi - e->ix.doc_lo));
+            // ... needs a top-k threshold high enough to set most of them aside (small k: the pool in shared memory) and an
+            // index of more than a couple of windows
+            const bool uni = lane && e->lane_merge == 3 && later * 100.0 <= sum_len * e->union_max_overlap && union_fits;
+            is_and[q] = all_must ? 3 : (uni ? 2 : (lane ? 1 : 0));
+            if (!all_must) {
+                if (uni) {}
+                else if (lane) pt.lane_max_terms = std::max(pt.lane_max_terms, nt_q);
+                else pt.max_terms = std::max(pt.max_terms, nt_q);
             }
             cost[q] = c;
             lead_cost[q] = lead;
@@ -710,7 +733,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     bool split_any = false;
     if (e->kernel == 3) {
         for (uint32_t q = 0; q < b->n_queries; ++q)
-            if (is_and[q] == 2) cost[q] = 1 + 8 * std::min<uint64_t>(lead_cost[q], cost[q]);   // ~8 probes per lead posting and term
+            if (is_and[q] == 3) cost[q] = 1 + 8 * std::min<uint64_t>(lead_cost[q], cost[q]);   // ~8 probes per lead posting and term
         uint64_t total_cost = 0;
         for (uint32_t q = 0; q < b->n_queries; ++q) total_cost += cost[q];
         const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) * e->plan_ctas * e->plan_wpc;
@@ -747,6 +770,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->n_acc_items = n_items;
     e->n_and_items = 0;
     e->n_lane_items = 0;
+    e->n_union_items = 0;
     if (e->kernel == 3) {
         // one sort of packed keys: class (accumulate first); cost class descending (powers of two: long items
         // start first); inside a cost class the items that stream the same long list are neighbours, so the warps
@@ -756,11 +780,12 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             bool operator<(const Key& o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
         };
         std::vector<Key> keys(n_items);
-        uint32_t n_and = 0, n_lane = 0;
+        uint32_t n_and = 0, n_lane = 0, n_union = 0;
         for (uint32_t i = 0; i < n_items; ++i) {
             const uint32_t q = witems[i].query;
             const uint64_t cls = is_and[q];
-            n_and += cls == 2 ? 1u : 0u;
+            n_and += cls == 3 ? 1u : 0u;
+            n_union += cls == 2 ? 1u : 0u;
             n_lane += cls == 1 ? 1u : 0u;
             const uint64_t c = std::max<uint64_t>(1, item_cost[i]);
             const uint64_t lg = 63 - static_cast<uint64_t>(__builtin_clzll(c));
@@ -772,7 +797,8 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         for (uint32_t i = 0; i < n_items; ++i) order[i] = static_cast<uint32_t>(keys[i].lo);
         e->n_and_items = n_and;
         e->n_lane_items = n_lane;
-        e->n_acc_items = n_items - n_and - n_lane;
+        e->n_union_items = n_union;
+        e->n_acc_items = n_items - n_and - n_lane - n_union;
     } else {
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
     }
@@ -797,8 +823,8 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     CU(e->d_witems.ensure(witems.size()));
     if (e->kernel == 3) {
         // union_topk_kernel reads the runs as separate doc / score arrays, the other kernels as (doc, score) entries
-        e->runs_soa = e->lane_merge == 3 && e->n_lane_items != 0;
-        e->runs_aos = !e->runs_soa || e->n_acc_items != 0 || e->n_and_items != 0;
+        e->runs_soa = e->n_union_items != 0;
+        e->runs_aos = !e->runs_soa || e->n_acc_items != 0 || e->n_and_items != 0 || e->n_lane_items != 0;
         const size_t want = static_cast<size_t>(run_entries) + 16384;  // tail slack for look-ahead loads
         const size_t cap = want + want / 4;   // grow with headroom: the scratch is reused by every batch
         cudaError_t ce = cudaSuccess;
@@ -928,7 +954,7 @@ static int launch_staged_only_t(dgpu_engine* e, AccumParams& L, cudaStream_t str
 
 template <int T>
 static int launch_lane_merge_t(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
-    if (e->lane_merge == 1) return launch_staged_only_t<T>(e, L, stream);
+    if (e->lane_merge != 2) return launch_staged_only_t<T>(e, L, stream);
     auto kern = e->need_cnt ? lane_merge_topk_kernel<T, true> : lane_merge_topk_kernel<T, false>;
     return launch_merge_kernel(e, L, stream, kern, LaneMergeBounds<T>::kThreads / 32, T, false);
 }
@@ -971,7 +997,6 @@ static int launch_union(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
 }
 
 static int launch_lane_merge(dgpu_engine* e, AccumParams& L, cudaStream_t stream) {
-    if (e->lane_merge == 3) return launch_union(e, L, stream);
     const uint32_t nt = e->lane_max_terms;
     if (nt <= 2) return launch_lane_merge_t<2>(e, L, stream);
     if (nt <= 4) return launch_lane_merge_t<4>(e, L, stream);
@@ -1049,9 +1074,16 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
         L.work_counter = e->d_counter.p + 2;
         if (launch_lane_merge(e, L, stream)) return -1;
     }
+    if (e->n_union_items) {
+        AccumParams U = P;
+        U.order = e->d_order.p + e->n_acc_items + e->n_lane_items;
+        U.n_items = e->n_union_items;
+        U.work_counter = e->d_counter.p + 3;
+        if (launch_union(e, U, stream)) return -1;
+    }
     if (e->n_and_items) {
         AccumParams Q = P;
-        Q.order = e->d_order.p + e->n_acc_items + e->n_lane_items;
+        Q.order = e->d_order.p + e->n_acc_items + e->n_lane_items + e->n_union_items;
         Q.n_items = e->n_and_items;
         Q.work_counter = e->d_counter.p + 1;
         CU(cudaFuncSetAttribute(intersect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1153,8 +1185,9 @@ int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[16]) {
     out[9] = static_cast<uint64_t>(e->n_queries) * (static_cast<uint64_t>(e->k) * 8 + 12);   // keys + count + hits
     out[10] = e->n_lane_items;
     out[11] = static_cast<uint64_t>(e->lane_merge);
+    out[13] = e->n_union_items;
     out[12] = static_cast<uint64_t>(e->lane_ring_entries) & ~63ull;
-    out[13] = out[14] = out[15] = 0;
+    out[14] = out[15] = 0;
     return 0;
 }
 

@@ -10,10 +10,12 @@
 //     each entry sets its doc's bit with a shared-memory atomicOr; the returned word says whether the doc had been
 //     seen before in this window. Every posting is visited, so hit counts are exact: the entries a clause has in the
 //     window (a difference of run positions) minus the later sightings;
-//   * the scores of a chunk are loaded only when the chunk's maximum score (written by decode_score_kernel next to
-//     the run, one float per 64 entries) reaches the running k-th best score: the sum of a doc matched by one clause
-//     is bounded by that maximum, so nothing that could be collected is skipped. Such first sightings become RECORDS
-//     (doc, clause, position);
+//   * scores are not touched while streaming. At the end of a window the chunk maxima of the slices just streamed
+//     (written by decode_score_kernel next to the run, one float per 64 entries, 32 of them per load) say which
+//     chunks hold a score that reaches the running k-th best: only those are read again, with their scores. An entry
+//     that reaches the threshold and whose doc was sighted once (its bit in the hashed filter below is clear) is
+//     collected on the spot - 0.0f + s == s; if the bit is set (a real second sighting or a hash collision) the
+//     entry becomes a candidate RECORD;
 //   * a later sighting becomes a record only if the doc could be collected. A doc sighted for the second time has
 //     exactly one earlier sighting: its sum is at most the chunk's maximum plus the LARGEST window maximum of the
 //     clauses streamed before. A third or later sighting (told apart by a 1024-bit hashed filter that every later
@@ -27,8 +29,9 @@
 //     lane: the lane bisects the slice every clause of the query has streamed since the list was last empty, adds the
 //     scores of the clauses that hold its doc in clause order starting from 0.0f (bit-exact, BooleanQuery.cpp:119-126),
 //     counts required / excluded clauses, applies the range filters and offers the doc to the top-k pool. Several
-//     records may exist for one doc; the one of the LAST clause in stream order that holds the doc collects it (it is
-//     the one whose bound covered every other clause), the others drop out.
+//     records may exist for one doc; the later-sighting record of the LAST clause in stream order that holds the doc
+//     collects it (it is the one whose bound covered every other clause), the others drop out; a candidate record
+//     collects only a doc held by no other clause.
 // Instruction cost: ~1.5 warp-instructions per posting, against 5 for a T-way register merge.
 //
 // MODE 0: plain disjunctions / term queries; 1: required-match counts and exclusions (minimumNumberShouldMatch,
@@ -44,34 +47,27 @@ namespace {
 constexpr int kUnionWarps = 1;                 // one warp per CTA: the bitmap starts at shared-memory offset 0, so the
                                                // address of a doc's word is two logic ops on (doc - window start)
 constexpr uint32_t kUnionChunk = 64;           // entries per iteration (lane l: entries 2l, 2l + 1)
-constexpr uint32_t kUnionRecords = 256;        // record list of a warp (meta = stream rank << 25 | position - slice start)
+constexpr uint32_t kUnionRecords = 256;        // record list of a warp (doc; meta = stream rank << 25 | flags)
 constexpr uint32_t kUnionResolveAt = 64;       // records that make a window end resolve the list
 constexpr uint32_t kUnionMaxDefer = 16;        // windows a record may wait
 constexpr uint32_t kUnionFilterWords = 32;     // 1024 bits
+constexpr uint32_t kRecCandidate = 1u << 30;   // meta flag: recorded by the window-end pass, collects only if no other clause holds the doc
 constexpr float kBoundSlack = 1.0001f;         // the bound is summed in stream order, the score in clause order
 
 __host__ __device__ inline size_t union_warp_smem_bytes(uint32_t window_docs, uint32_t cap_smem) {
     size_t b = window_docs / 8;                                  // seen bitmap
     b += sizeof(uint32_t) * kUnionFilterWords;                   // hashed filter of the docs seen twice
+    b += sizeof(uint32_t) * 32;                                  // one word per lane for the atomics of entries outside the window
     b += 2 * sizeof(uint32_t) * kUnionRecords;                   // records: doc, meta
     b += cap_smem ? sizeof(uint64_t) * cap_smem                  // candidate pool in shared memory, or
                   : sizeof(uint32_t) * 256;                      // the digit histogram of warp_select_topk
     return (b + 15) & ~static_cast<size_t>(15);
 }
 
-// Sets `bit` in the shared-memory word at byte address `addr` if p; returns the word's previous value (0 if !p).
-__device__ __forceinline__ uint32_t atoms_or_if(bool p, uint32_t addr, uint32_t bit) {
+// ORs `bit` into the shared-memory word at byte address `addr`; returns the word's previous value.
+__device__ __forceinline__ uint32_t atoms_or(uint32_t addr, uint32_t bit) {
     uint32_t old;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %3, 0;\n\t"
-        "mov.b32 %0, 0;\n\t"
-        "@p atom.shared.or.b32 %0, [%1], %2;\n\t"
-        "}\n"
-        : "=r"(old)
-        : "r"(addr), "r"(bit), "r"(static_cast<uint32_t>(p))
-        : "memory");
+    asm volatile("atom.shared.or.b32 %0, [%1], %2;\n" : "=r"(old) : "r"(addr), "r"(bit) : "memory");
     return old;
 }
 
@@ -95,7 +91,12 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
     const uint32_t seen_s = static_cast<uint32_t>(__cvta_generic_to_shared(seen));
     sp += W / 8;
     uint32_t* filt = reinterpret_cast<uint32_t*>(sp);
+    const uint32_t filt_s = static_cast<uint32_t>(__cvta_generic_to_shared(filt));
     sp += sizeof(uint32_t) * kUnionFilterWords;
+    // a lane whose entry lies outside the window ORs 0 into a word of its own: no branch around the atomic
+    const uint32_t idle_s = static_cast<uint32_t>(__cvta_generic_to_shared(sp)) + 4u * lane;
+    reinterpret_cast<uint32_t*>(sp)[lane] = 0u;
+    sp += sizeof(uint32_t) * 32;
     uint32_t* rec_doc = reinterpret_cast<uint32_t*>(sp);
     uint32_t* rec_meta = rec_doc + kUnionRecords;
     sp += 2 * sizeof(uint32_t) * kUnionRecords;
@@ -178,8 +179,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
         uint64_t thresh = 0;        // key of the k-th best so far
         float thresh_f = __uint_as_float(0xFF800000u);   // its score (-inf until there is one): the stream's quick test
-        uint32_t hits = 0;          // per lane, modulo 2^32 (mode 1 also takes hits back)
-        uint32_t n_later = 0;       // later sightings counted as hits by position (warp-uniform)
+        uint32_t hits = 0;          // per lane, modulo 2^32 (later sightings and mode 1 take hits back)
         uint32_t n_rec = 0;         // records waiting (warp-uniform)
         uint32_t base = pos;        // what the record list refers to: the run position when the list was last empty
         uint32_t waited = 0;        // windows since then
@@ -242,6 +242,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                 waited = 0;
             }
             uint32_t act = act0, done = 0;
+            uint32_t cand_am = act0 & (NEED_CNT ? single_mask : 0xFFFFFFFFu);   // clauses the window-end pass still has to look at
+            uint32_t cres = pos;   // where that pass starts in the clause's run (moves on when the pass is interrupted)
             float pre = 0.0f;    // sum of the window maxima of the clauses streamed so far (warp-uniform)
             float pmx = 0.0f;    // the largest of them
             int u = -1;          // clause being streamed (-1: pick the next one)
@@ -281,7 +283,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         cm = __ldg(cmax + (c >> 6));
                     }
                     const bool single_ok = !NEED_CNT || ((single_mask >> u) & 1u);
-                    const uint32_t meta_u = (static_cast<uint32_t>(u) << 25) + 2u * lane - __shfl_sync(0xFFFFFFFFu, base, u);   // + chunk (+ 1)
+                    const uint32_t meta_u = static_cast<uint32_t>(u) << 25;
                     const uint2* pd = reinterpret_cast<const uint2*>(docs + c) + lane;   // this lane's two entries of the chunk
                     const float* pcm = cmax + (c >> 6);
                     for (;;) {
@@ -299,25 +301,31 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         // entries before the window (consumed earlier) and after it fail the same unsigned compare
                         const uint32_t r0 = d.x - ws, r1 = d.y - ws;
                         const bool in0 = r0 < wlen, in1 = r1 < wlen;
-                        const uint32_t b0 = __funnelshift_l(0u, 1u, r0), b1 = __funnelshift_l(0u, 1u, r1);   // 1 << (r & 31)
-                        const uint32_t o0 = atoms_or_if(in0, seen_s + ((r0 >> 3) & ~3u), b0);
-                        const uint32_t o1 = atoms_or_if(in1, seen_s + ((r1 >> 3) & ~3u), b1);
+                        const uint32_t b0 = in0 ? __funnelshift_l(0u, 1u, r0) : 0u, b1 = in1 ? __funnelshift_l(0u, 1u, r1) : 0u;   // 1 << (r & 31)
+                        const uint32_t o0 = atoms_or(in0 ? seen_s + ((r0 >> 3) & ~3u) : idle_s, b0);
+                        const uint32_t o1 = atoms_or(in1 ? seen_s + ((r1 >> 3) & ~3u) : idle_s, b1);
                         const uint32_t dup = (o0 & b0) | (o1 & b1);   // seen before in this window: a later sighting
-                        // mode 2 looks at every first sighting (its filter value decides whether it is a hit); otherwise
-                        // only chunks with a later sighting, or whose best score reaches the k-th best so far
+                        // mode 2 looks at every first sighting (its filter value decides whether it is a hit); otherwise only
+                        // chunks with a later sighting leave the straight path
                         const bool any_later = __any_sync(0xFFFFFFFFu, dup != 0u);
-                        if (any_later || (single_ok && (FILTER || cm >= thresh_f))) {
+                        if (any_later || (FILTER && single_ok)) {
                             const bool l0 = (o0 & b0) != 0u, l1 = (o1 & b1) != 0u;   // later sightings
-                            bool rec0 = false, rec1 = false;
+                            if (FILTER && single_ok) {
+                                bool new0 = in0 && !l0, new1 = in1 && !l1;
+                                if (nf) {
+                                    if (new0) new0 = passes(d.x);
+                                    if (new1) new1 = passes(d.y);
+                                }
+                                hits += (new0 ? 1u : 0u) + (new1 ? 1u : 0u);
+                            }
                             if (any_later) {
                                 // positions count the clause's entries in the window as hits: take the later sightings back
-                                if (!FILTER && single_ok) n_later += __popc(__ballot_sync(0xFFFFFFFFu, l0)) + __popc(__ballot_sync(0xFFFFFFFFu, l1));
-                                // every later sighting sets its doc's bit in the hashed filter; a bit already set: the doc may
-                                // have been seen twice before
-                                const uint32_t h0 = r0 & (32u * kUnionFilterWords - 1u), h1 = r1 & (32u * kUnionFilterWords - 1u);
-                                bool t0 = false, t1 = false;
-                                if (l0) t0 = ((atomicOr(filt + (h0 >> 5), 1u << (h0 & 31u)) >> (h0 & 31u)) & 1u) != 0u;
-                                if (l1) t1 = ((atomicOr(filt + (h1 >> 5), 1u << (h1 & 31u)) >> (h1 & 31u)) & 1u) != 0u;
+                                if (!FILTER && single_ok) hits -= (l0 ? 1u : 0u) + (l1 ? 1u : 0u);
+                                // every later sighting sets its doc's bit in the hashed filter (1024 bits: bit r mod 1024, in
+                                // the word (r / 32) mod 32, the same bit of the word as in the bitmap); a bit already set: the
+                                // doc may have been seen twice before
+                                const bool t0 = (atoms_or(l0 ? filt_s + ((r0 >> 3) & 124u) : idle_s, l0 ? b0 : 0u) & b0) != 0u && l0;
+                                const bool t1 = (atoms_or(l1 ? filt_s + ((r1 >> 3) & 124u) : idle_s, l1 ? b1 : 0u) & b1) != 0u && l1;
                                 // can a doc seen again here be collected? second sighting: this chunk's maximum plus the largest
                                 // window maximum of the clauses streamed before; later ones: plus the sum of those maxima
                                 float ub2 = __fadd_rn(cm, pmx), ub3 = __fadd_rn(cm, pre);
@@ -329,49 +337,24 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                 }
                                 const bool keep2 = !(bounded && __fmul_rn(ub2, kBoundSlack) < thresh_f);
                                 const bool keep3 = !(bounded && __fmul_rn(ub3, kBoundSlack) < thresh_f);
-                                rec0 = l0 && (t0 ? keep3 : keep2);
-                                rec1 = l1 && (t1 ? keep3 : keep2);
-                            }
-                            if (single_ok && (FILTER || cm >= thresh_f)) {   // first sightings: hits of mode 2, candidates
-                                bool new0 = in0 && !l0, new1 = in1 && !l1;
-                                float cm_adj = cm;
-                                if (FILTER) {
-                                    if (nf) {
-                                        if (new0) new0 = passes(d.x);
-                                        if (new1) new1 = passes(d.y);
+                                if (keep3) {   // (keep2 implies keep3)
+                                    const bool rec0 = l0 && (t0 || keep2), rec1 = l1 && (t1 || keep2);
+                                    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, rec0), m1 = __ballot_sync(0xFFFFFFFFu, rec1);
+                                    DGPU_ASSERT(n_rec + 64u <= kUnionRecords);
+                                    if (rec0) {
+                                        const uint32_t e = n_rec + __popc(m0 & lt_mask);
+                                        rec_doc[e] = d.x;
+                                        rec_meta[e] = meta_u;
                                     }
-                                    hits += (new0 ? 1u : 0u) + (new1 ? 1u : 0u);
-                                    for (uint32_t f = 0; f < nf; ++f) cm_adj = __fadd_rn(cm_adj, 1.0f);   // rounding is monotone
-                                }
-                                if (cm_adj >= thresh_f) {   // some first sighting of this chunk may be collected
-                                    const float2 s = __ldg(reinterpret_cast<const float2*>(scores + c) + lane);
-                                    float s0 = s.x, s1 = s.y;
-                                    if (FILTER) {
-                                        for (uint32_t f = 0; f < nf; ++f) {
-                                            s0 = __fadd_rn(s0, 1.0f);
-                                            s1 = __fadd_rn(s1, 1.0f);
-                                        }
+                                    n_rec += __popc(m0);
+                                    if (rec1) {
+                                        const uint32_t e = n_rec + __popc(m1 & lt_mask);
+                                        rec_doc[e] = d.y;
+                                        rec_meta[e] = meta_u;
                                     }
-                                    rec0 = rec0 || (new0 && s0 >= thresh_f);
-                                    rec1 = rec1 || (new1 && s1 >= thresh_f);
+                                    n_rec += __popc(m1);
+                                    if (n_rec + 64u > kUnionRecords) full = true;
                                 }
-                            }
-                            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, rec0), m1 = __ballot_sync(0xFFFFFFFFu, rec1);
-                            if (m0 | m1) {
-                                DGPU_ASSERT(n_rec + 64u <= kUnionRecords);
-                                if (rec0) {
-                                    const uint32_t e = n_rec + __popc(m0 & lt_mask);
-                                    rec_doc[e] = d.x;
-                                    rec_meta[e] = meta_u + c;
-                                }
-                                n_rec += __popc(m0);
-                                if (rec1) {
-                                    const uint32_t e = n_rec + __popc(m1 & lt_mask);
-                                    rec_doc[e] = d.y;
-                                    rec_meta[e] = meta_u + c + 1u;
-                                }
-                                n_rec += __popc(m1);
-                                if (n_rec + 64u > kUnionRecords) full = true;
                             }
                         }
                         if (!more) {
@@ -389,6 +372,13 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                             }
                             pre = __fadd_rn(pre, fmaxf(wm, 0.0f));
                             pmx = fmaxf(pmx, wm);
+                            {   // no chunk of the clause reaches the threshold: nothing for the window-end pass
+                                float wm_adj = wm;
+                                if (FILTER) {
+                                    for (uint32_t f = 0; f < nf; ++f) wm_adj = __fadd_rn(wm_adj, 1.0f);
+                                }
+                                if (!(wm_adj >= thresh_f)) cand_am &= ~(1u << u);
+                            }
                             done |= 1u << u;
                             u = -1;
                             break;
@@ -402,6 +392,66 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                     }
                 }
                 __syncwarp();
+
+                // ---- end of the window: first sightings that can be collected. Chunk maxima pick the chunks worth
+                // a second look (lane i tests chunk i of the clause's slice); a doc whose filter bit is clear was sighted
+                // once and is collected with its score as it is, otherwise the entry goes to the record list
+                if (!full) {   // (a single match of a clause outside cand_am is no hit)
+                    while (cand_am && !full) {
+                        const int v = __ffs(cand_am) - 1;
+                        const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, cres, v), c1 = __shfl_sync(0xFFFFFFFFu, pos, v);
+                        bool clause_done = true;
+                        for (uint32_t cb = c0 & ~(kUnionChunk - 1u); cb < c1 && !full; cb += 32u * kUnionChunk) {
+                            const uint32_t mine_c = cb + kUnionChunk * lane;
+                            float cmv = __uint_as_float(0xFF800000u);
+                            if (mine_c < c1) cmv = __ldg(cmax + (mine_c >> 6));
+                            if (FILTER) {
+                                for (uint32_t f = 0; f < nf; ++f) cmv = __fadd_rn(cmv, 1.0f);   // rounding is monotone
+                            }
+                            uint32_t fm = __ballot_sync(0xFFFFFFFFu, mine_c < c1 && cmv >= thresh_f);   // (-inf >= -inf holds)
+                            while (fm) {
+                                const int l = __ffs(fm) - 1;
+                                fm &= fm - 1u;
+                                const uint32_t cc = cb + kUnionChunk * l;
+                                const uint2 dd = __ldg(reinterpret_cast<const uint2*>(docs + cc) + lane);
+                                const float2 ss = __ldg(reinterpret_cast<const float2*>(scores + cc) + lane);
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint32_t doc = j ? dd.y : dd.x;
+                                    float sc = j ? ss.y : ss.x;
+                                    if (FILTER) {
+                                        for (uint32_t f = 0; f < nf; ++f) sc = __fadd_rn(sc, 1.0f);   // constant score of a range clause (NumericRangeQuery.cpp:117-120)
+                                    }
+                                    const uint32_t r = doc - ws;
+                                    // inside the window, not looked at before (a resumed clause), able to enter the pool
+                                    bool cnd = r < wlen && cc + 2u * lane + j >= c0 && sc >= thresh_f;
+                                    if (FILTER && nf && cnd) cnd = passes(doc);
+                                    const bool again = cnd && ((filt[(r >> 5) & (kUnionFilterWords - 1u)] >> (r & 31u)) & 1u) != 0u;
+                                    collect(doc, sc, cnd && !again);
+                                    const uint32_t ma = __ballot_sync(0xFFFFFFFFu, again);
+                                    if (ma) {
+                                        DGPU_ASSERT(n_rec + 32u <= kUnionRecords);
+                                        if (again) {
+                                            const uint32_t e = n_rec + __popc(ma & lt_mask);
+                                            rec_doc[e] = doc;
+                                            rec_meta[e] = (static_cast<uint32_t>(v) << 25) | kRecCandidate;
+                                        }
+                                        n_rec += __popc(ma);
+                                    }
+                                }
+                                if (n_rec + 64u > kUnionRecords) {
+                                    // the list is nearly full: resolve it and come back for the rest of this clause
+                                    full = true;
+                                    if (lane == v) cres = cc + kUnionChunk;
+                                    clause_done = cc + kUnionChunk >= c1;
+                                    break;
+                                }
+                            }
+                        }
+                        if (clause_done) cand_am &= cand_am - 1u;
+                    }
+                    __syncwarp();
+                }
                 // resolve now? inside a window when the list is nearly full; at a window end when two lane-fulls have
                 // gathered or the oldest record has waited long enough; at the end of the item
                 ++waited;
@@ -415,7 +465,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                 for (uint32_t rb = 0; rb < n_rec; rb += 32) {
                     const bool valid = rb + lane < n_rec;
                     const uint32_t doc = valid ? rec_doc[rb + lane] : 0u;
-                    const uint32_t ru = valid ? rec_meta[rb + lane] >> 25 : 0xFFu;
+                    const uint32_t meta = valid ? rec_meta[rb + lane] : 0u;
+                    const uint32_t ru = (meta >> 25) & 31u;
                     float sum = 0.0f;
                     uint32_t cnt = 0, c_ok = 0, first = 0xFFu, top = 0u;   // clauses that hold the doc; not excluding ones; lowest, highest rank
                     bool excluded = false;
@@ -445,9 +496,10 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                             top = max(top, static_cast<uint32_t>(v));
                         }
                     }
-                    // the record of the last clause in stream order that holds the doc collects it
+                    // the later-sighting record of the last clause in stream order that holds the doc collects it; a candidate
+                    // record (a first sighting whose filter bit was set) only if that was a hash collision
                     DGPU_ASSERT(!valid || (cnt >= 1 && ru <= top && ru >= first));
-                    const bool des = valid && ru == top;
+                    const bool des = valid && ((meta & kRecCandidate) ? cnt == 1 : ru == top);
                     bool match = des;
                     if (NEED_CNT)
                         match = des && !excluded && c_ok != 0 && (qd.n_must ? c_ok == qd.n_must : c_ok >= qd.min_should_match);
@@ -478,7 +530,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
 
         // ---- final select
         __syncwarp();
-        hits = __reduce_add_sync(0xFFFFFFFFu, hits) - n_later;
+        hits = __reduce_add_sync(0xFFFFFFFFu, hits);
         if (BIGK && n_cand > static_cast<uint32_t>(P.k)) prune();   // sort k keys, not the whole pool
         const uint32_t nsort = min(P.cand_cap, pow2_at_least(n_cand));
         for (uint32_t i = n_cand + lane; i < nsort; i += 32) cand[i] = 0;

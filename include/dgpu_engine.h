@@ -169,8 +169,9 @@ int dgpu_engine_last_phase_ms(const dgpu_engine* e, float out[3]);
  * reads), [5] docs per window of accumulate_topk_kernel, [6] work items of accumulate_topk_kernel, [7] work items
  * of intersect_topk_kernel (pure conjunctions), [8] host-to-device bytes of the staged descriptors, [9] device-to-host
  * bytes of one result fetch, [10] work items of the document-at-a-time merge kernel (queries of <= 32 terms; <= 16 for lane_merge_topk_kernel),
- * [11] which one that is: 1 = staged_merge_topk_kernel, 2 = lane_merge_topk_kernel, [12] ring entries per warp of
- * staged_merge_topk_kernel, [13..15] reserved (0). */
+ * [11] option lane_merge (3 = union_topk_kernel for the queries it suits and staged_merge_topk_kernel for the overlap-heavy
+ * ones, 1 = staged_merge_topk_kernel, 2 = lane_merge_topk_kernel), [12] ring entries per warp of staged_merge_topk_kernel,
+ * [13] work items of union_topk_kernel (not counted in [10]), [14..15] reserved (0). */
 int dgpu_engine_batch_stats(const dgpu_engine* e, uint64_t out[16]);
 
 /* Tunables. Returns 0 or -1 for an unknown name / bad value. */

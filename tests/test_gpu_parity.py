@@ -76,7 +76,8 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
 # <= 16 terms), 3 = union_topk_kernel (bitmap windows of union_window_docs docs); the longer queries of the file are
 # scored by the windows whatever lane_merge says
 _DEFAULTS = {"window_docs": 0, "stage_log2": 0, "splits": 0, "warps": 4, "warps_per_sm": 20, "intersect": 1,
-             "lane_merge": 3, "lane_ring_entries": 2176, "union_window_docs": 32768, "lane_ctas_per_sm": 0}
+             "lane_merge": 3, "lane_ring_entries": 2176, "union_window_docs": 32768, "lane_ctas_per_sm": 0,
+             "union_max_overlap": 15}
 _TUNINGS = [
     dict(lane_merge=0, warps_per_sm=16),
     dict(lane_merge=0, window_docs=1024, splits=1, warps_per_sm=16, intersect=0),
@@ -92,11 +93,13 @@ _TUNINGS = [
     dict(lane_merge=2, intersect=0),
     dict(lane_merge=2, splits=5),
     dict(lane_merge=3),
-    dict(lane_merge=3, intersect=0, splits=1),
-    dict(lane_merge=3, union_window_docs=128, splits=3),
-    dict(lane_merge=3, union_window_docs=1024, intersect=0, splits=7),
-    dict(lane_merge=3, union_window_docs=65536, splits=16, lane_ctas_per_sm=2),
-    dict(lane_merge=3, union_window_docs=4096, window_docs=512),
+    dict(lane_merge=3, union_max_overlap=100000),   # every query of <= 32 terms on union_topk_kernel, however dense
+    dict(lane_merge=3, union_max_overlap=100000, intersect=0, splits=1),
+    dict(lane_merge=3, union_max_overlap=100000, union_window_docs=128, splits=3),
+    dict(lane_merge=3, union_max_overlap=100000, union_window_docs=1024, intersect=0, splits=7),
+    dict(lane_merge=3, union_max_overlap=100000, union_window_docs=65536, splits=16, lane_ctas_per_sm=2),
+    dict(lane_merge=3, union_max_overlap=100000, union_window_docs=4096, window_docs=512),
+    dict(lane_merge=3, union_max_overlap=0, splits=2),   # ... and none of them
 ]
 
 
@@ -432,6 +435,7 @@ def test_union_kernel_edge_shapes(readers, g1_dump, window):
     want = {}
     try:
         r.set_option("lane_merge", 3)
+        r.set_option("union_max_overlap", 100000)
         r.set_option("union_window_docs", window)
         r.set_option("intersect", 0)
         searcher = dg.IndexSearcher(r)

@@ -1,6 +1,6 @@
 # iteration loop for union_topk_kernel: parity (bounds-checked build), bench lines, per-line counters at full size
 mkdir -p gpurun_out
-DGPU_LIB=$PWD/diagon_b200/libdiagon_b200_chk.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "union or lane_merge3" > gpurun_out/pytest_union_chk.log 2>&1; rc=$?
+DGPU_LIB=$PWD/diagon_b200/libdiagon_b200_chk.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "union or lane_merge3 or named or wide" > gpurun_out/pytest_union_chk.log 2>&1; rc=$?
 echo "pytest(chk) rc=$rc"; tail -4 gpurun_out/pytest_union_chk.log
 [ $rc -ne 0 ] && { grep -E "Error|error|assert" gpurun_out/pytest_union_chk.log | head -20; exit 1; }
 for cfg in "--lane-merge 3" "--lane-merge 3 --union-window-docs 65536" "--lane-merge 3 --union-window-docs 16384" ${EXTRA_CFGS}; do
@@ -16,3 +16,4 @@ except Exception as e:
 PY
 done
 bash tools/union_ncu_full.sh
+bash tools/workloads.sh

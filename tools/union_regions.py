@@ -23,7 +23,7 @@ def ln(pat):
     return next(i for i, l in enumerate(src, 1) if pat in l)
 marks = [('item setup', ln('uint32_t ticket = 0;')), ('window setup', ln('// ---- window: W docs from')), ('visit', ln('while (!full) {')),
          ('stream fast', ln('DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk')), ('slow path', ln('const bool l0 = (o0 & b0)')), ('term end', ln('if (!more) {')),
-         ('resolve', ln('// resolve now?')), ('clear+final', ln("// ---- the window's bits back to zero")), ('end', len(src) + 1)]
+         ('candidates', ln('// ---- end of the window: first sightings')), ('resolve', ln('// resolve now?')), ('clear+final', ln("// ---- the window's bits back to zero")), ('end', len(src) + 1)]
 tot = sum(agg.values()); ts = sum(samp.values())
 print(f"total warp instructions {tot} = {tot / postings:.3f} per posting")
 for (name, a), (_, b) in zip(marks, marks[1:]):
