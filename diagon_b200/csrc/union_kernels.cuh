@@ -6,7 +6,7 @@
 // order - is only needed for the docs that can enter the top k. So the warp that owns a work item (a query, or a doc
 // range of one) walks the doc range in windows of W docs (W = 32K..64K: ONE BIT per doc in shared memory) and, per
 // window, streams the runs of the query clause by clause, DENSEST FIRST:
-//   * 64 entries per iteration, two per lane, doc ids only (one coalesced 256-byte load, next chunk prefetched);
+//   * 128 entries per iteration, four per lane, doc ids only (one coalesced 512-byte load, next chunk prefetched);
 //     each entry sets its doc's bit with a shared-memory atomicOr; the returned word says whether the doc had been
 //     seen before in this window. Every posting is visited, so hit counts are exact: the entries a clause has in the
 //     window (a difference of run positions) minus the later sightings;
@@ -46,7 +46,8 @@ namespace {
 
 constexpr int kUnionWarps = 1;                 // one warp per CTA: the bitmap starts at shared-memory offset 0, so the
                                                // address of a doc's word is two logic ops on (doc - window start)
-constexpr uint32_t kUnionChunk = 64;           // entries per iteration (lane l: entries 2l, 2l + 1)
+constexpr uint32_t kUnionChunk = 128;          // entries per iteration (lane l: entries 4l .. 4l + 3)
+constexpr uint32_t kMaxChunk = 64;             // entries per chunk maximum (decode_score_kernel: RunArrays::cmax)
 constexpr uint32_t kUnionRecords = 256;        // record list of a warp (doc; meta = stream rank << 25 | flags)
 constexpr uint32_t kUnionResolveAt = 64;       // records that make a window end resolve the list
 constexpr uint32_t kUnionMaxDefer = 16;        // windows a record may wait
@@ -250,14 +251,20 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
             uint32_t c = 0;      // its current chunk (multiple of kUnionChunk)
             float wm = 0.0f;     // largest chunk maximum of the clause in this window so far
             int pf_u = -1;       // clause whose first chunk has been prefetched into pf_d / pf_cm
-            uint2 pf_d = make_uint2(0u, 0u);
+            uint4 pf_d = make_uint4(0u, 0u, 0u, 0u);
             float pf_cm = 0.0f;
+            // the docs of a chunk (this lane's four) and the larger of its two chunk maxima
+            auto load_chunk = [&](uint32_t at, uint4& dd, float& mx) {
+                dd = __ldg(reinterpret_cast<const uint4*>(docs + at) + lane);
+                const float2 m2 = __ldg(reinterpret_cast<const float2*>(cmax + (at >> 6)));
+                mx = fmaxf(m2.x, m2.y);
+            };
 
             for (;;) {
                 // ---- stream clauses in order until the window is done or the record list is nearly full
                 bool full = false;
                 while (!full) {
-                    uint2 d;
+                    uint4 d;
                     float cm;
                     if (u < 0) {
                         if (!act) break;
@@ -269,63 +276,58 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                             d = pf_d;
                             cm = pf_cm;
                         } else {
-                            d = __ldg(reinterpret_cast<const uint2*>(docs + c) + lane);
-                            cm = __ldg(cmax + (c >> 6));
+                            load_chunk(c, d, cm);
                         }
                         if (act) {   // the first chunk of the next clause is on its way while this one is streamed
                             pf_u = __ffs(act) - 1;
-                            const uint32_t cn = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
-                            pf_d = __ldg(reinterpret_cast<const uint2*>(docs + cn) + lane);
-                            pf_cm = __ldg(cmax + (cn >> 6));
+                            load_chunk(__shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u), pf_d, pf_cm);
                         }
                     } else {   // resumed after a resolve in the middle of a clause
-                        d = __ldg(reinterpret_cast<const uint2*>(docs + c) + lane);
-                        cm = __ldg(cmax + (c >> 6));
+                        load_chunk(c, d, cm);
                     }
                     const bool single_ok = !NEED_CNT || ((single_mask >> u) & 1u);
                     const uint32_t meta_u = static_cast<uint32_t>(u) << 25;
-                    const uint2* pd = reinterpret_cast<const uint2*>(docs + c) + lane;   // this lane's two entries of the chunk
-                    const float* pcm = cmax + (c >> 6);
                     for (;;) {
                         DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk <= P.run_total);
                         // sorted run: the chunk's last entry tells whether the clause goes on inside this window
-                        const bool more = __shfl_sync(0xFFFFFFFFu, d.y, 31) < we;
-                        uint2 dn = make_uint2(0u, 0u);
+                        const bool more = __shfl_sync(0xFFFFFFFFu, d.w, 31) < we;
+                        uint4 dn = make_uint4(0u, 0u, 0u, 0u);
                         float cmn = 0.0f;
                         if (more) {
-                            dn = __ldg(pd + 32);
-                            cmn = __ldg(pcm + 1);
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + 128));   // four chunks ahead
+                            load_chunk(c + kUnionChunk, dn, cmn);
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(docs + c + 3u * kUnionChunk) + lane));
                         }
                         wm = fmaxf(wm, cm);
-                        // entries before the window (consumed earlier) and after it fail the same unsigned compare
-                        const uint32_t r0 = d.x - ws, r1 = d.y - ws;
-                        const bool in0 = r0 < wlen, in1 = r1 < wlen;
-                        const uint32_t b0 = in0 ? __funnelshift_l(0u, 1u, r0) : 0u, b1 = in1 ? __funnelshift_l(0u, 1u, r1) : 0u;   // 1 << (r & 31)
-                        const uint32_t o0 = atoms_or(in0 ? seen_s + ((r0 >> 3) & ~3u) : idle_s, b0);
-                        const uint32_t o1 = atoms_or(in1 ? seen_s + ((r1 >> 3) & ~3u) : idle_s, b1);
-                        const uint32_t dup = (o0 & b0) | (o1 & b1);   // seen before in this window: a later sighting
+                        // entries before the window (consumed earlier) and after it fail the same unsigned compare; a lane whose
+                        // entry is outside ORs 0 into a word of its own
+                        const uint32_t dv[4] = {d.x, d.y, d.z, d.w};
+                        uint32_t r[4], b[4], o[4];
+                        bool in[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            r[j] = dv[j] - ws;
+                            in[j] = r[j] < wlen;
+                            b[j] = in[j] ? __funnelshift_l(0u, 1u, r[j]) : 0u;   // 1 << (r & 31)
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[j] = atoms_or(in[j] ? seen_s + ((r[j] >> 3) & ~3u) : idle_s, b[j]);
+                        const uint32_t dup = (o[0] & b[0]) | (o[1] & b[1]) | (o[2] & b[2]) | (o[3] & b[3]);   // seen before in this window
                         // mode 2 looks at every first sighting (its filter value decides whether it is a hit); otherwise only
                         // chunks with a later sighting leave the straight path
                         const bool any_later = __any_sync(0xFFFFFFFFu, dup != 0u);
                         if (any_later || (FILTER && single_ok)) {
-                            const bool l0 = (o0 & b0) != 0u, l1 = (o1 & b1) != 0u;   // later sightings
+                            bool lt[4];   // later sightings
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) lt[j] = (o[j] & b[j]) != 0u;
                             if (FILTER && single_ok) {
-                                bool new0 = in0 && !l0, new1 = in1 && !l1;
-                                if (nf) {
-                                    if (new0) new0 = passes(d.x);
-                                    if (new1) new1 = passes(d.y);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    bool nw = in[j] && !lt[j];
+                                    if (nf && nw) nw = passes(dv[j]);
+                                    hits += nw ? 1u : 0u;
                                 }
-                                hits += (new0 ? 1u : 0u) + (new1 ? 1u : 0u);
                             }
                             if (any_later) {
-                                // positions count the clause's entries in the window as hits: take the later sightings back
-                                if (!FILTER && single_ok) hits -= (l0 ? 1u : 0u) + (l1 ? 1u : 0u);
-                                // every later sighting sets its doc's bit in the hashed filter (1024 bits: bit r mod 1024, in
-                                // the word (r / 32) mod 32, the same bit of the word as in the bitmap); a bit already set: the
-                                // doc may have been seen twice before
-                                const bool t0 = (atoms_or(l0 ? filt_s + ((r0 >> 3) & 124u) : idle_s, l0 ? b0 : 0u) & b0) != 0u && l0;
-                                const bool t1 = (atoms_or(l1 ? filt_s + ((r1 >> 3) & 124u) : idle_s, l1 ? b1 : 0u) & b1) != 0u && l1;
                                 // can a doc seen again here be collected? second sighting: this chunk's maximum plus the largest
                                 // window maximum of the clauses streamed before; later ones: plus the sum of those maxima
                                 float ub2 = __fadd_rn(cm, pmx), ub3 = __fadd_rn(cm, pre);
@@ -336,39 +338,44 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                     }
                                 }
                                 const bool keep2 = !(bounded && __fmul_rn(ub2, kBoundSlack) < thresh_f);
-                                const bool keep3 = !(bounded && __fmul_rn(ub3, kBoundSlack) < thresh_f);
-                                if (keep3) {   // (keep2 implies keep3)
-                                    const bool rec0 = l0 && (t0 || keep2), rec1 = l1 && (t1 || keep2);
-                                    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, rec0), m1 = __ballot_sync(0xFFFFFFFFu, rec1);
-                                    DGPU_ASSERT(n_rec + 64u <= kUnionRecords);
-                                    if (rec0) {
-                                        const uint32_t e = n_rec + __popc(m0 & lt_mask);
-                                        rec_doc[e] = d.x;
-                                        rec_meta[e] = meta_u;
+                                const bool keep3 = !(bounded && __fmul_rn(ub3, kBoundSlack) < thresh_f);   // (keep2 implies keep3)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    // positions count the clause's entries in the window as hits: take the later sightings back
+                                    if (!FILTER && single_ok) hits -= lt[j] ? 1u : 0u;
+                                    // every later sighting sets its doc's bit in the hashed filter (1024 bits: bit r mod 1024, in
+                                    // the word (r / 32) mod 32, the same bit of the word as in the bitmap); a bit already set: the
+                                    // doc may have been seen twice before
+                                    const bool t = (atoms_or(lt[j] ? filt_s + ((r[j] >> 3) & 124u) : idle_s, lt[j] ? b[j] : 0u) & b[j]) != 0u && lt[j];
+                                    if (keep3) {
+                                        const bool rec = lt[j] && (t || keep2);
+                                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, rec);
+                                        DGPU_ASSERT(n_rec + 32u <= kUnionRecords);
+                                        if (rec) {
+                                            const uint32_t e = n_rec + __popc(m & lt_mask);
+                                            rec_doc[e] = dv[j];
+                                            rec_meta[e] = meta_u;
+                                        }
+                                        n_rec += __popc(m);
                                     }
-                                    n_rec += __popc(m0);
-                                    if (rec1) {
-                                        const uint32_t e = n_rec + __popc(m1 & lt_mask);
-                                        rec_doc[e] = d.y;
-                                        rec_meta[e] = meta_u;
-                                    }
-                                    n_rec += __popc(m1);
-                                    if (n_rec + 64u > kUnionRecords) full = true;
                                 }
+                                if (n_rec + kUnionChunk > kUnionRecords) full = true;
                             }
                         }
                         if (!more) {
                             // the clause's next window starts at the first entry >= we: the entries below are a prefix
-                            const uint32_t g0 = __ballot_sync(0xFFFFFFFFu, d.x >= we), g1 = __ballot_sync(0xFFFFFFFFu, d.y >= we);
-                            const uint32_t below = kUnionChunk - __popc(g0) - __popc(g1);
+                            uint32_t below = kUnionChunk;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) below -= __popc(__ballot_sync(0xFFFFFFFFu, dv[j] >= we));
                             DGPU_ASSERT(below < kUnionChunk);
-                            const uint32_t x = __shfl_sync(0xFFFFFFFFu, d.x, below >> 1), y = __shfl_sync(0xFFFFFFFFu, d.y, below >> 1);
+                            const uint32_t e01 = __shfl_sync(0xFFFFFFFFu, (below & 1u) ? d.y : d.x, below >> 2);
+                            const uint32_t e23 = __shfl_sync(0xFFFFFFFFu, (below & 1u) ? d.w : d.z, below >> 2);
                             if (lane == u) {
                                 // without filters every entry of the clause inside the window counts as a hit here (later
                                 // sightings are taken back; mode 1: if one matching clause makes a hit at all)
                                 if (!FILTER && single_ok) hits += c + below - pos;
                                 pos = c + below;
-                                nd = (below & 1u) ? y : x;
+                                nd = (below & 2u) ? e23 : e01;
                             }
                             pre = __fadd_rn(pre, fmaxf(wm, 0.0f));
                             pmx = fmaxf(pmx, wm);
@@ -384,8 +391,6 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                             break;
                         }
                         c += kUnionChunk;
-                        pd += 32;
-                        pcm += 1;
                         d = dn;
                         cm = cmn;
                         if (full) break;
@@ -401,8 +406,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         const int v = __ffs(cand_am) - 1;
                         const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, cres, v), c1 = __shfl_sync(0xFFFFFFFFu, pos, v);
                         bool clause_done = true;
-                        for (uint32_t cb = c0 & ~(kUnionChunk - 1u); cb < c1 && !full; cb += 32u * kUnionChunk) {
-                            const uint32_t mine_c = cb + kUnionChunk * lane;
+                        for (uint32_t cb = c0 & ~(kMaxChunk - 1u); cb < c1 && !full; cb += 32u * kMaxChunk) {
+                            const uint32_t mine_c = cb + kMaxChunk * lane;
                             float cmv = __uint_as_float(0xFF800000u);
                             if (mine_c < c1) cmv = __ldg(cmax + (mine_c >> 6));
                             if (FILTER) {
@@ -412,7 +417,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                             while (fm) {
                                 const int l = __ffs(fm) - 1;
                                 fm &= fm - 1u;
-                                const uint32_t cc = cb + kUnionChunk * l;
+                                const uint32_t cc = cb + kMaxChunk * l;
                                 const uint2 dd = __ldg(reinterpret_cast<const uint2*>(docs + cc) + lane);
                                 const float2 ss = __ldg(reinterpret_cast<const float2*>(scores + cc) + lane);
 #pragma unroll
@@ -442,8 +447,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                 if (n_rec + 64u > kUnionRecords) {
                                     // the list is nearly full: resolve it and come back for the rest of this clause
                                     full = true;
-                                    if (lane == v) cres = cc + kUnionChunk;
-                                    clause_done = cc + kUnionChunk >= c1;
+                                    if (lane == v) cres = cc + kMaxChunk;
+                                    clause_done = cc + kMaxChunk >= c1;
                                     break;
                                 }
                             }
@@ -470,30 +475,58 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                     float sum = 0.0f;
                     uint32_t cnt = 0, c_ok = 0, first = 0xFFu, top = 0u;   // clauses that hold the doc; not excluding ones; lowest, highest rank
                     bool excluded = false;
-                    for (uint32_t j = 0; j < nt; ++j) {   // clause order: the order of the sum
-                        const int v = static_cast<int>(__shfl_sync(0xFFFFFFFFu, rk, j));   // where clause j lives
-                        const uint32_t rl = NEED_CNT ? __shfl_sync(0xFFFFFFFFu, role, v) : 0u;
-                        const uint32_t v_lo = __shfl_sync(0xFFFFFFFFu, base, v);
-                        uint32_t len = __shfl_sync(0xFFFFFFFFu, s_hi, v) - v_lo;
-                        if (len == 0) continue;
-                        uint32_t b = v_lo;   // branch-free lower bound; the trip count depends on len only (warp-uniform)
-                        while (len > 1) {
-                            const uint32_t half = len >> 1;
-                            if (__ldg(docs + b + half - 1u) < doc) b += half;
-                            len -= half;
+                    // four clauses at a time, in clause order (the order of the sum): their bisections are independent
+                    // chains of loads, interleaved step by step
+                    for (uint32_t j0 = 0; j0 < nt; j0 += 4) {
+                        int v[4];
+                        uint32_t rl[4], b[4], len[4];
+                        bool any[4];
+                        uint32_t longest = 0;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint32_t j = min(j0 + g, nt - 1u);
+                            v[g] = static_cast<int>(__shfl_sync(0xFFFFFFFFu, rk, j));   // where clause j lives
+                            rl[g] = NEED_CNT ? __shfl_sync(0xFFFFFFFFu, role, v[g]) : 0u;
+                            b[g] = __shfl_sync(0xFFFFFFFFu, base, v[g]);
+                            len[g] = j0 + g < nt ? __shfl_sync(0xFFFFFFFFu, s_hi, v[g]) - b[g] : 0u;
+                            any[g] = len[g] != 0u;
+                            longest = max(longest, len[g]);
                         }
-                        if (__ldg(docs + b) < doc) b += 1u;
-                        DGPU_ASSERT(static_cast<uint64_t>(b) < P.run_total);
-                        if (valid && __ldg(docs + b) == doc) {   // (the entry after a slice is a later doc or padding: never `doc`)
-                            if (NEED_CNT && rl == DGPU_ROLE_MUST_NOT) {
-                                excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
-                            } else {
-                                sum = __fadd_rn(sum, __ldg(scores + b));
-                                ++c_ok;
+                        // branch-free lower bounds; the trip counts depend on the slice lengths only (warp-uniform)
+                        for (; longest > 1; longest -= longest >> 1) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (len[g] > 1) {
+                                    const uint32_t half = len[g] >> 1;
+                                    if (__ldg(docs + b[g] + half - 1u) < doc) b[g] += half;
+                                    len[g] -= half;
+                                }
                             }
-                            ++cnt;
-                            first = min(first, static_cast<uint32_t>(v));
-                            top = max(top, static_cast<uint32_t>(v));
+                        }
+                        uint32_t at[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) at[g] = any[g] ? __ldg(docs + b[g]) : kDocEnd;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (any[g] && at[g] < doc) {
+                                b[g] += 1u;
+                                at[g] = __ldg(docs + b[g]);   // (the entry after a slice is a later doc or padding: never `doc`)
+                            }
+                            DGPU_ASSERT(static_cast<uint64_t>(b[g]) < P.run_total);
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (valid && any[g] && at[g] == doc) {
+                                if (NEED_CNT && rl[g] == DGPU_ROLE_MUST_NOT) {
+                                    excluded = true;   // ReqExclScorer, BooleanQuery.cpp:259-308
+                                } else {
+                                    sum = __fadd_rn(sum, __ldg(scores + b[g]));
+                                    ++c_ok;
+                                }
+                                ++cnt;
+                                first = min(first, static_cast<uint32_t>(v[g]));
+                                top = max(top, static_cast<uint32_t>(v[g]));
+                            }
                         }
                     }
                     // the later-sighting record of the last clause in stream order that holds the doc collects it; a candidate

@@ -36,7 +36,7 @@ i = sum(v for (f, l), v in agg.items() if f.startswith('union_kernels') and l < 
 print(f"helpers          ({i / postings:.3f}/posting)")
 for pat, what in (('const uint32_t ws = opaque', 'windows'), ('u = __ffs(act) - 1;', 'visits'), ('const bool more =', 'chunk iterations'), ('const bool l0 =', 'slow path'),
                   ('const uint32_t m0 = __ballot_sync', 'slow path (m0)'), ('rec_meta[e] = meta_u + c;', 'appends'), ('const bool valid = rb + lane < n_rec;', 'record batches'),
-                  ('if (len == 0) continue;', 'clause searches'), ('if (__ldg(docs + b + half - 1u) < doc) b += half;', 'bisect steps')):
+                  ('for (; longest > 1; longest -= longest >> 1) {', 'clause groups'), ('if (__ldg(docs + b[g] + half - 1u) < doc) b[g] += half;', 'bisect steps')):
     for i, l in enumerate(src, 1):
         if pat in l and ('union_kernels.cuh', i) in per:
             xs = per[('union_kernels.cuh', i)]
