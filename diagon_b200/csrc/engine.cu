@@ -115,11 +115,14 @@ struct dgpu_engine {
     int sm_count = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_hi = nullptr;   // decode_score_kernel: takes SM slots ahead of the scoring kernels of an earlier batch
+    cudaEvent_t ev_staged = nullptr, ev_decoded = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // index
     DeviceIndex ix{};
     uint32_t n_terms = 0;
     uint32_t n_fields = 0;
+    uint32_t n_dv = 0;                  // doc-values columns of the uploaded index (range filters are checked against it)
     uint64_t n_blocks = 0;
     std::vector<uint32_t> h_term_block_start;
     std::vector<uint32_t> h_block_meta;
@@ -182,7 +185,7 @@ struct dgpu_engine {
     int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
     int warps_per_sm = 20;   // independent scoring warps per SM (each owns 1/n of the shared memory)
     int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
-    int part_factor = 2;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
+    int part_factor = 1;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
     int decode_ctas_per_sm = 64; // grid of decode_score_kernel (grid-stride over the decode work items)
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
     int lane_merge = 3;      // queries of <= 32 terms: 3 = union_topk_kernel, 1 = staged_merge_topk_kernel, 2 = lane_merge_topk_kernel (<= 16 terms), 0 = accumulated in windows
@@ -194,7 +197,7 @@ struct dgpu_engine {
     int union_window_docs = 32768;  // docs per window (one bit each in shared memory) of union_topk_kernel
     int union_max_overlap = 15;     // lane_merge = 3: a query whose expected later sightings exceed this percentage of its
                                     // postings (dense terms on a small index) is merged in registers by staged_merge_topk_kernel
-    int pipeline_chunks = 4;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
+    int pipeline_chunks = 3;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
     int pipeline_min = 2048;        // batches of fewer queries are not cut
     bool shadow = false;            // shares another engine's uploaded index
     int pool_smem_cap = 256;        // candidate pools of up to this many keys live in shared memory, larger ones in global
@@ -277,7 +280,14 @@ int dgpu_engine_create(int device, dgpu_engine** out) {
     CU(cudaGetDeviceProperties(&prop, device));
     eng->sm_count = prop.multiProcessorCount;
     eng->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
-    CU(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    {
+        int lo_prio = 0, hi_prio = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CU(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, lo_prio));
+        CU(cudaStreamCreateWithPriority(&eng->stream_hi, cudaStreamNonBlocking, hi_prio));
+        CU(cudaEventCreateWithFlags(&eng->ev_staged, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&eng->ev_decoded, cudaEventDisableTiming));
+    }
     CU(cudaEventCreate(&eng->ev0));
     CU(cudaEventCreate(&eng->ev1));
     CU(cudaEventCreate(&eng->ev_a));
@@ -301,6 +311,9 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_a) cudaEventDestroy(e->ev_a);
     if (e->ev_b) cudaEventDestroy(e->ev_b);
+    if (e->ev_staged) cudaEventDestroy(e->ev_staged);
+    if (e->ev_decoded) cudaEventDestroy(e->ev_decoded);
+    if (e->stream_hi) cudaStreamDestroy(e->stream_hi);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -420,6 +433,7 @@ int dgpu_engine_upload(dgpu_engine* e, const dgpu_index_image* im) {
     e->n_terms = im->n_terms;
     e->n_blocks = im->n_blocks;
     e->n_fields = im->n_fields;
+    e->n_dv = im->n_dv;
     e->h_term_block_start.assign(im->term_block_start, im->term_block_start + im->n_terms + 1);
     e->h_block_meta.assign(im->block_meta, im->block_meta + im->n_blocks);
     e->h_block_off.assign(im->block_data_off, im->block_data_off + im->n_blocks + 1);
@@ -477,6 +491,7 @@ int dgpu_engine_create_shadow(dgpu_engine* primary, dgpu_engine** out) {
     e->n_terms = primary->n_terms;
     e->n_blocks = primary->n_blocks;
     e->n_fields = primary->n_fields;
+    e->n_dv = primary->n_dv;
     e->h_term_block_start = primary->h_term_block_start;
     e->h_block_meta = primary->h_block_meta;
     e->h_block_off = primary->h_block_off;
@@ -640,7 +655,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             cost[q] = c;
             lead_cost[q] = lead;
             for (uint32_t f = qd.filter_begin; f < qd.filter_end; ++f)
-                if (b->filters[f].column < 0) bad(q, "bad filter column");
+                if (b->filters[f].column < 0 || static_cast<uint32_t>(b->filters[f].column) >= e->n_dv) bad(q, "bad filter column");
         }
     });
     uint32_t max_terms = 1, lane_max_terms = 0;
@@ -736,7 +751,11 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             if (is_and[q] == 3) cost[q] = 1 + 8 * std::min<uint64_t>(lead_cost[q], cost[q]);   // ~8 probes per lead posting and term
         uint64_t total_cost = 0;
         for (uint32_t q = 0; q < b->n_queries; ++q) total_cost += cost[q];
-        const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) * e->plan_ctas * e->plan_wpc;
+        // warps that will pull items: union_topk_kernel runs 32 one-warp CTAs per SM, the others plan_ctas x plan_wpc
+        uint32_t n_union_q = 0;
+        for (uint32_t q = 0; q < b->n_queries; ++q) n_union_q += is_and[q] == 2 ? 1u : 0u;
+        const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) *
+                                 (2 * n_union_q > b->n_queries ? 32u : static_cast<uint32_t>(e->plan_ctas * e->plan_wpc));
         const uint64_t target = std::max<uint64_t>(64, total_cost / (n_warps * static_cast<uint64_t>(e->part_factor)) + 1);   // posting blocks per item
         // every part keeps its own top-k and the merge compares all pairs of parts: large k gets fewer parts
         const uint32_t cap_parts = e->max_parts ? static_cast<uint32_t>(e->max_parts)
@@ -974,8 +993,7 @@ static int launch_union_kernel(dgpu_engine* e, AccumParams& L, cudaStream_t stre
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kUnionWarps, smem));
     if (per_sm < 1) return fail("union_topk_kernel does not fit an SM (%zu bytes of shared memory)", smem);
     if (e->lane_ctas_per_sm) per_sm = std::min(per_sm, e->lane_ctas_per_sm);
-    const uint64_t want_ctas = (static_cast<uint64_t>(L.n_items) + kUnionWarps - 1) / kUnionWarps;
-    const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * per_sm, want_ctas));
+    const int grid = static_cast<int>(L.n_items);   // one item per (one-warp) CTA
     kern<<<grid, 32 * kUnionWarps, smem, stream>>>(e->ix, L);
     CU(cudaGetLastError());
     e->launches++;
@@ -1052,7 +1070,19 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
         const RunArrays out{e->d_runs.p, e->d_run_docs.p, e->d_run_scores.p, e->d_run_cmax.p};
         auto dk = e->runs_soa ? (e->runs_aos ? decode_score_kernel<true, true> : decode_score_kernel<false, true>)
                               : decode_score_kernel<true, false>;
-        dk<<<grid, kDecodeThreads, 0, stream>>>(e->ix, e->d_dterms.p, e->d_items.p, e->n_ditems, out);
+        // on the engine's own stream the decode runs at high priority: when another engine's scoring kernel fills the GPU
+        // (pipelined chunks of a batch), its blocks get the SM slots that free up first, so this batch's scoring kernel
+        // is ready to take over when the other one runs out of work
+        cudaStream_t ds = stream == e->stream ? e->stream_hi : stream;
+        if (ds != stream) {
+            CU(cudaEventRecord(e->ev_staged, stream));
+            CU(cudaStreamWaitEvent(ds, e->ev_staged, 0));
+        }
+        dk<<<grid, kDecodeThreads, 0, ds>>>(e->ix, e->d_dterms.p, e->d_items.p, e->n_ditems, out);
+        if (ds != stream) {
+            CU(cudaEventRecord(e->ev_decoded, ds));
+            CU(cudaStreamWaitEvent(stream, e->ev_decoded, 0));
+        }
         e->launches++;
         CU(cudaGetLastError());
     }

@@ -112,7 +112,9 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
     filt[lane] = 0u;
     __syncwarp();
 
-    for (;;) {
+    // one item per CTA (the grid is the item list): SM slots free up all the time, so the kernels of the next chunk of a
+    // pipelined batch flow in as this one runs out of work; items are handed out in cost order by the ticket counter
+    for (int once = 0; once < 1; ++once) {
         uint32_t ticket = 0;
         if (lane == 0) ticket = atomicAdd(P.work_counter, 1u);
         ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);

@@ -61,28 +61,6 @@ std::vector<LineSpan> split_lines(const char* text, int64_t len) {
     return lines;
 }
 
-// Parses lines [lo, hi) on all host threads.
-std::vector<std::unique_ptr<Query>> parse_lines(const std::vector<LineSpan>& lines, size_t lo, size_t hi) {
-    std::vector<std::unique_ptr<Query>> out(hi - lo);
-    parallel_for(hi - lo, hi - lo < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
-        for (size_t i = b; i < e; ++i) out[i] = parse_query_line(std::string(lines[lo + i].first, lines[lo + i].second));
-    });
-    return out;
-}
-
-// Splits a text batch into lines and parses them on all host threads.
-std::vector<std::unique_ptr<Query>> parse_batch(const char* text, int64_t len) {
-    const auto lines = split_lines(text, len);
-    return parse_lines(lines, 0, lines.size());
-}
-
-// a 10K-query batch is ~500K small heap objects: release them on all threads, not serially in the destructor
-void release_parsed(std::vector<std::unique_ptr<Query>>& parsed) {
-    parallel_for(parsed.size(), parsed.size() < 256 ? 1 : 0, [&](size_t b, size_t e, int) {
-        for (size_t i = b; i < e; ++i) parsed[i].reset();
-    });
-}
-
 void unpack(const std::vector<uint64_t>& keys, const std::vector<int32_t>& counts, int32_t n, int32_t k,
             int32_t* out_docs, float* out_scores) {
     for (int32_t q = 0; q < n; ++q)
@@ -100,6 +78,8 @@ void unpack(const std::vector<uint64_t>& keys, const std::vector<int32_t>& count
         }
 }
 
+void concat(std::vector<CompiledBatch>& parts, CompiledBatch& out);
+
 // Compiles queries in parallel (per-thread CompiledBatch, then concatenated in order).
 void compile_all(IndexSearcher& s, const std::vector<const Query*>& qs, CompiledBatch& out) {
     size_t n = qs.size();
@@ -114,6 +94,11 @@ void compile_all(IndexSearcher& s, const std::vector<const Query*>& qs, Compiled
         begins[static_cast<size_t>(t)] = b;
         for (size_t i = b; i < e; ++i) s.compile(*qs[i], parts[static_cast<size_t>(t)]);
     });
+    concat(parts, out);
+}
+
+// Appends the per-thread pieces of a batch in order.
+void concat(std::vector<CompiledBatch>& parts, CompiledBatch& out) {
     for (auto& p : parts) {
         uint32_t toff = static_cast<uint32_t>(out.terms.size()), foff = static_cast<uint32_t>(out.filters.size());
         for (auto q : p.queries) {
@@ -125,6 +110,63 @@ void compile_all(IndexSearcher& s, const std::vector<const Query*>& qs, Compiled
         out.filters.insert(out.filters.end(), p.filters.begin(), p.filters.end());
         out.algorithmic_bytes += p.algorithmic_bytes;
     }
+}
+
+// Compiles lines [lo, hi) of a text batch on all host threads: straight from the bytes where the line is one of the
+// common shapes (IndexSearcher::compile_text_line), through parse_query_line + compile otherwise (same results, same
+// errors: the first failing line's exception is rethrown).
+void compile_lines(IndexSearcher& s, const std::vector<LineSpan>& lines, size_t lo, size_t hi, CompiledBatch& out) {
+    static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t n = hi - lo;
+    const int threads = n < 512 ? 1 : static_cast<int>(std::min<size_t>(std::thread::hardware_concurrency(), 32));
+    std::vector<CompiledBatch> parts(static_cast<size_t>(std::max(threads, 1)));
+    std::vector<std::exception_ptr> errors(parts.size());
+    std::vector<size_t> error_at(parts.size(), ~static_cast<size_t>(0));
+    parallel_for(n, std::max(threads, 1), [&](size_t b, size_t e, int t) {
+        CompiledBatch& part = parts[static_cast<size_t>(t)];
+        part.queries.reserve(e - b);
+        part.terms.reserve((e - b) * 8);
+        for (size_t i = b; i < e; ++i) {
+            const LineSpan& l = lines[lo + i];
+            if (s.compile_text_line(l.first, l.second, part)) continue;
+            try {
+                s.compile(*parse_query_line(std::string(l.first, l.second)), part);
+            } catch (...) {
+                errors[static_cast<size_t>(t)] = std::current_exception();
+                error_at[static_cast<size_t>(t)] = i;
+                return;
+            }
+        }
+    });
+    size_t first = ~static_cast<size_t>(0);
+    for (size_t t = 0; t < parts.size(); ++t)
+        if (errors[t] && error_at[t] < first) first = error_at[t];
+    for (size_t t = 0; t < parts.size(); ++t)
+        if (errors[t] && error_at[t] == first) std::rethrow_exception(errors[t]);
+    const auto t1 = std::chrono::steady_clock::now();
+    concat(parts, out);
+    if (trace) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[dgpu trace]   compile_lines %zu lines: compile %.3f ms (%d threads), concat %.3f ms\n", n, ms(t0, t1),
+                     threads, ms(t1, std::chrono::steady_clock::now()));
+    }
+}
+
+int run_compiled(IndexSearcher& s, const CompiledBatch& batch, int32_t k, int32_t* out_docs, float* out_scores,
+                 int32_t* out_counts, int64_t* out_total_hits) {
+    const size_t n = batch.queries.size();
+    std::vector<uint64_t> keys(n * static_cast<size_t>(k));
+    std::vector<int32_t> counts(n);
+    dgpu_results res{keys.data(), counts.data(), out_total_hits};
+    dgpu_query_batch view = batch.view();
+    auto guard = s.getIndexReader().lock_engines();
+    if (n && !s.getIndexReader().engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
+    if (n && dgpu_engine_search(s.getIndexReader().engine(), &view, k, &res) != 0)
+        throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
+    unpack(keys, counts, static_cast<int32_t>(n), k, out_docs, out_scores);
+    std::memcpy(out_counts, counts.data(), n * sizeof(int32_t));
+    return static_cast<int>(n);
 }
 
 int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, int32_t* out_docs, float* out_scores,
@@ -140,6 +182,7 @@ int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, 
     std::vector<int32_t> counts(n);
     dgpu_results res{keys.data(), counts.data(), out_total_hits};
     dgpu_query_batch view = batch.view();
+    auto guard = s.getIndexReader().lock_engines();
     if (n && !s.getIndexReader().engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
     if (n && dgpu_engine_search(s.getIndexReader().engine(), &view, k, &res) != 0)
         throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
@@ -163,11 +206,20 @@ int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int
     static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     IndexReader& rd = s.getIndexReader();
-    dgpu_engine* eng[2] = {rd.engine(), rd.shadow_engine()};
+    auto guard = rd.lock_engines();
+    // the chunks rotate over up to four engines that share the device index: a chunk is staged while the kernels of the
+    // chunks before it run, and an engine's buffers are not reused before its last chunk has been fetched
+    dgpu_engine* eng[1 + IndexReader::kMaxShadows] = {rd.engine(), nullptr, nullptr, nullptr};
+    int n_eng = 1;
+    while (n_eng < 1 + IndexReader::kMaxShadows && n_eng < chunks) {
+        dgpu_engine* sh = rd.shadow_engine(n_eng - 1);
+        if (!sh) break;
+        eng[n_eng++] = sh;
+    }
     const size_t n = lines.size();
     std::vector<uint64_t> keys(n * static_cast<size_t>(k));
     std::vector<int32_t> counts(n);
-    struct Inflight { size_t q0 = 0; bool active = false; } fly[2];
+    struct Inflight { size_t q0 = 0; bool active = false; } fly[1 + IndexReader::kMaxShadows];
     auto fetch = [&](int slot) {
         if (!fly[slot].active) return;
         fly[slot].active = false;
@@ -177,28 +229,34 @@ int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int
             throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
     };
     try {
+        // the first chunk is half a share: its host work is the only one the GPU waits for
+        const size_t shares = 2 * static_cast<size_t>(chunks) - 1;
+        auto cut = [&](int c) { return c <= 0 ? static_cast<size_t>(0) : n * (2 * static_cast<size_t>(c) - 1) / shares; };
         for (int c = 0; c < chunks; ++c) {
-            const size_t q0 = n * static_cast<size_t>(c) / chunks, q1 = n * static_cast<size_t>(c + 1) / chunks;
+            const size_t q0 = cut(c), q1 = c + 1 == chunks ? n : cut(c + 1);
             if (q1 == q0) continue;
-            const int slot = c & 1;
-            auto parsed = parse_lines(lines, q0, q1);
-            std::vector<const Query*> qs;
-            qs.reserve(parsed.size());
-            for (auto& q : parsed) qs.push_back(q.get());
+            const int slot = c % n_eng;
+            auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+            const double ta = now_ms();
             CompiledBatch batch;
-            compile_all(s, qs, batch);
-            release_parsed(parsed);
+            compile_lines(s, lines, q0, q1, batch);
+            const double tb = now_ms();
             fetch(slot);   // the chunk before last ran on this engine: its results leave before its buffers are reused
+            const double tc = now_ms();
             dgpu_query_batch view = batch.view();
             if (dgpu_engine_stage_batch(eng[slot], &view, k) != 0 || dgpu_engine_search_staged(eng[slot], nullptr) != 0)
                 throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
             fly[slot] = Inflight{q0, true};
+            if (trace)
+                std::fprintf(stderr, "[dgpu trace] chunk %d (%zu queries): compile %.3f..%.3f, fetch of the engine's last chunk ..%.3f, stage + launch ..%.3f ms\n",
+                             c, q1 - q0, ta, tb, tc, now_ms());
         }
-        fetch(0);
-        fetch(1);
+        for (int c = 0; c < n_eng; ++c) fetch((chunks + c) % n_eng);   // oldest first
+        if (trace)
+            std::fprintf(stderr, "[dgpu trace] drained at %.3f ms\n",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     } catch (...) {
-        dgpu_engine_wait(eng[0]);
-        dgpu_engine_wait(eng[1]);
+        for (int i = 0; i < n_eng; ++i) dgpu_engine_wait(eng[i]);
         throw;
     }
     const auto t1 = std::chrono::steady_clock::now();
@@ -527,6 +585,7 @@ int dgpu_reader_set_doc_freqs(DiagonIndexReader r, const int64_t* in, int64_t n)
     auto& df = as_reader(r)->index().term_doc_freq;
     if (n != static_cast<int64_t>(df.size())) { set_error("size mismatch"); return -1; }
     std::memcpy(df.data(), in, df.size() * sizeof(int64_t));
+    as_reader(r)->index().stats_changed();
     return 0;
 }
 int dgpu_reader_get_field_totals(DiagonIndexReader r, const char* field, int64_t* sum_ttf, int64_t* max_doc) {
@@ -552,6 +611,7 @@ int dgpu_reader_set_field_totals(DiagonIndexReader r, const char* field, int64_t
         auto& ix = rd->index();
         int f = ix.field_id(field);
         if (f < 0) { set_error("unknown field"); return -1; }
+        auto guard = rd->lock_engines();
         ix.set_global_stats(f, sum_ttf, max_doc_total);
         // the k table depends on avgdl: refresh the device copy
         if (rd->engine() && dgpu_engine_set_ktab(rd->engine(), ix.image.ktab.data(), ix.image.n_fields) != 0) {
@@ -591,6 +651,7 @@ int64_t dgpu_reader_decode_term(DiagonIndexReader r, const char* field, const ui
         if (!out_docs || !out_freqs) return n;
         if (capacity < n) { set_error("capacity too small"); return -1; }
         uint64_t offs[2];
+        auto guard = rd->lock_engines();
         if (dgpu_engine_decode_terms(rd->engine(), &id, 1, out_docs, out_freqs, offs, nullptr) != 0) {
             set_error(dgpu_engine_last_error());
             return -1;
@@ -627,30 +688,26 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
                 s.getIndexReader().shadow_engine())
                 return run_text_pipelined(s, lines, pl[0], k, out_docs, out_scores, out_counts, out_total_hits);
         }
-        auto parsed = parse_lines(lines, 0, lines.size());
+        if (k <= 0) throw std::invalid_argument("numHits must be > 0");
+        CompiledBatch batch;
+        compile_lines(s, lines, 0, lines.size(), batch);
         if (std::getenv("DGPU_TRACE"))
-            std::fprintf(stderr, "[dgpu trace] parse %.3f ms\n",
+            std::fprintf(stderr, "[dgpu trace] parse + compile %.3f ms\n",
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count());
-        std::vector<const Query*> qs;
-        qs.reserve(parsed.size());
-        for (auto& q : parsed) qs.push_back(q.get());
-        const int rc = run_batch(s, qs, k, out_docs, out_scores, out_counts, out_total_hits);
-        release_parsed(parsed);
-        return rc;
+        return run_compiled(s, batch, k, out_docs, out_scores, out_counts, out_total_hits);
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
 
 int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats) {
     if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
     try {
-        auto parsed = parse_batch(text, text_len);
-        std::vector<const Query*> qs;
-        for (auto& q : parsed) qs.push_back(q.get());
+        const auto lines = split_lines(text, text_len);
         CompiledBatch batch;
-        compile_all(*as_searcher(searcher), qs, batch);
+        compile_lines(*as_searcher(searcher), lines, 0, lines.size(), batch);
         dgpu_query_batch view = batch.view();
         auto* rd = &as_searcher(searcher)->getIndexReader();
         if (!rd->engine()) { set_error("host-only reader: no GPU engine, and there is no CPU fallback"); return -1; }
+        auto guard = rd->lock_engines();
         if (dgpu_engine_stage_batch(rd->engine(), &view, k) != 0) { set_error(dgpu_engine_last_error()); return -1; }
         if (out_stats) {
             out_stats[0] = static_cast<int64_t>(batch.queries.size());
@@ -673,12 +730,9 @@ int64_t dgpu_compile_batch_text(DiagonIndexSearcher searcher, const char* text, 
                                 int64_t capacity) {
     if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
     try {
-        auto parsed = parse_batch(text, text_len);
-        std::vector<const Query*> qs;
-        qs.reserve(parsed.size());
-        for (auto& q : parsed) qs.push_back(q.get());
+        const auto lines = split_lines(text, text_len);
         CompiledBatch batch;
-        compile_all(*as_searcher(searcher), qs, batch);
+        compile_lines(*as_searcher(searcher), lines, 0, lines.size(), batch);
         const uint32_t hdr[4] = {0x42504744u /* "DGPB" */, static_cast<uint32_t>(batch.queries.size()),
                                  static_cast<uint32_t>(batch.terms.size()), static_cast<uint32_t>(batch.filters.size())};
         const size_t nq = batch.queries.size() * sizeof(dgpu_query), nt = batch.terms.size() * sizeof(dgpu_qterm),
@@ -731,6 +785,7 @@ int dgpu_stage_compiled(DiagonIndexSearcher searcher, const uint8_t* const* blob
         dgpu_query_batch view = batch.view();
         auto* rd = &as_searcher(searcher)->getIndexReader();
         if (!rd->engine()) { set_error("host-only reader: no GPU engine, and there is no CPU fallback"); return -1; }
+        auto guard = rd->lock_engines();
         if (dgpu_engine_stage_batch(rd->engine(), &view, k) != 0) { set_error(dgpu_engine_last_error()); return -1; }
         return static_cast<int>(batch.queries.size());
     } catch (const std::exception& e) { set_error(e); return -1; }

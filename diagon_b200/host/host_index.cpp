@@ -236,6 +236,24 @@ float HostIndex::idf_for(uint32_t term_id, float boost) const {
     return idf_formula(df, max_doc_total) * boost;
 }
 
+const HostIndex::TermQuick* HostIndex::term_quick() const {
+    const uint64_t want = stats_version_.load(std::memory_order_acquire);
+    if (quick_version_.load(std::memory_order_acquire) != want) {
+        std::lock_guard<std::mutex> lock(quick_mutex_);
+        if (quick_version_.load(std::memory_order_relaxed) != want) {
+            std::vector<TermQuick> q(term_doc_freq.size());
+            parallel_for(q.size(), q.size() < 65536 ? 1 : 0, [&](size_t b, size_t e, int) {
+                for (size_t t = b; t < e; ++t)
+                    q[t] = TermQuick{idf_for(static_cast<uint32_t>(t), 1.0f), term_doc_freq[t] != 0 ? 1u : 0u,
+                                     term_encoded_bytes(static_cast<uint32_t>(t))};
+            });
+            quick_.swap(q);
+            quick_version_.store(want, std::memory_order_release);
+        }
+    }
+    return quick_.data();
+}
+
 float HostIndex::idf_for_missing(float boost) const {
     return idf_formula(max_doc_total / 10, max_doc_total) * boost;  // TermQuery.cpp:250-253
 }
@@ -250,6 +268,7 @@ void HostIndex::set_global_stats(int field, int64_t sum_total_term_freq, int64_t
 // k(norm) = k1 * (1 - b + b * L(norm) * (1/avgdl)), in the reference's float evaluation order
 // (BM25Similarity.h:141-153); the translation unit is compiled with -ffp-contract=off.
 void HostIndex::finalize_tables() {
+    stats_changed();
     image.n_fields = static_cast<uint32_t>(fields.size());
     image.ktab.assign(static_cast<size_t>(image.n_fields) * DGPU_KTAB_SIZE, 0.0f);
     const float k1 = 1.2f, b = 0.75f;

@@ -14,7 +14,9 @@
 #include "index_image.h"
 #include "synth_corpus.h"
 
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <iosfwd>
 #include <functional>
 #include <memory>
@@ -100,8 +102,22 @@ public:
         return term_id < image.term_bytes.size() ? image.term_bytes[term_id] : 0;
     }
 
+    // What compiling a query term needs, in one cache line per term: idf_for(id, 1.0f), whether docFreq > 0, and
+    // term_encoded_bytes(id). Built on first use, rebuilt after the statistics change (stats_changed()).
+    struct TermQuick {
+        float idf;
+        uint32_t present;
+        uint64_t encoded_bytes;
+    };
+    const TermQuick* term_quick() const;
+    void stats_changed() { ++stats_version_; }
+
 private:
     std::vector<int64_t> global_sum_ttf_override_;  // per field, -1 = none
+    std::atomic<uint64_t> stats_version_{1};
+    mutable std::atomic<uint64_t> quick_version_{0};
+    mutable std::mutex quick_mutex_;
+    mutable std::vector<TermQuick> quick_;
 };
 
 // Collects segments / terms handed over by an index reader (the reference's DirectoryReader through

@@ -68,19 +68,20 @@ IndexReader::IndexReader(std::shared_ptr<HostIndex> index, int device) : index_(
 }
 
 IndexReader::~IndexReader() {
-    if (shadow_) dgpu_engine_destroy(shadow_);
+    for (dgpu_engine* sh : shadow_)
+        if (sh) dgpu_engine_destroy(sh);
     if (engine_) dgpu_engine_destroy(engine_);
 }
 
-dgpu_engine* IndexReader::shadow_engine() {
-    if (!engine_ || shadow_failed_) return nullptr;
-    if (!shadow_ && dgpu_engine_create_shadow(engine_, &shadow_) != 0) {
-        shadow_ = nullptr;
-        shadow_failed_ = true;   // the caller runs the batch on engine() alone; not retried on every call
+dgpu_engine* IndexReader::shadow_engine(int i) {
+    if (!engine_ || shadow_failed_ || i < 0 || i >= kMaxShadows) return nullptr;
+    if (!shadow_[i] && dgpu_engine_create_shadow(engine_, &shadow_[i]) != 0) {
+        shadow_[i] = nullptr;
+        shadow_failed_ = true;   // the caller runs the batch on the engines it has; not retried on every call
         return nullptr;
     }
-    dgpu_engine_sync_options(shadow_, engine_);
-    return shadow_;
+    dgpu_engine_sync_options(shadow_[i], engine_);
+    return shadow_[i];
 }
 
 // ------------------------------------------------------------------ compilation
@@ -220,12 +221,175 @@ void IndexSearcher::compile(const Query& query, CompiledBatch& out) const {
     c.compile(query);
 }
 
+// ------------------------------------------------------------------ text lines, compiled directly
+namespace {
+
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// the next whitespace-separated token of [p, end), as operator>> of an istringstream cuts them
+inline bool next_token(const char*& p, const char* end, const char*& tb, const char*& te) {
+    while (p < end && is_space(*p)) ++p;
+    if (p == end) return false;
+    tb = p;
+    while (p < end && !is_space(*p)) ++p;
+    te = p;
+    return true;
+}
+
+inline bool token_is(const char* b, const char* e, const char* lit) {
+    const size_t n = std::strlen(lit);
+    return static_cast<size_t>(e - b) == n && std::memcmp(b, lit, n) == 0;
+}
+
+// a plain decimal integer that fits comfortably (anything else goes to the generic path)
+inline bool token_int(const char* b, const char* e, long long& v) {
+    bool neg = false;
+    if (b < e && (*b == '-' || *b == '+')) neg = *b++ == '-';
+    if (b == e || e - b > 17) return false;
+    long long x = 0;
+    for (; b < e; ++b) {
+        if (*b < '0' || *b > '9') return false;
+        x = x * 10 + (*b - '0');
+    }
+    v = neg ? -x : x;
+    return true;
+}
+
+}  // namespace
+
+bool IndexSearcher::compile_text_line(const char* p, const char* end, CompiledBatch& out) const {
+    const HostIndex& ix = reader_.index();
+    const size_t t0 = out.terms.size(), f0 = out.filters.size();
+    const uint64_t bytes0 = out.algorithmic_bytes;
+    auto give_up = [&]() {
+        out.terms.resize(t0);
+        out.filters.resize(f0);
+        out.algorithmic_bytes = bytes0;
+        return false;
+    };
+    const char *kb, *ke, *fb, *fe, *tb, *te;
+    if (!next_token(p, end, kb, ke) || !next_token(p, end, fb, fe)) return false;
+    enum { TERM, OR, AND, ORF, ANDF, ANDNOT } kind;
+    if (token_is(kb, ke, "OR")) kind = OR;
+    else if (token_is(kb, ke, "TERM")) kind = TERM;
+    else if (token_is(kb, ke, "AND")) kind = AND;
+    else if (token_is(kb, ke, "ORF")) kind = ORF;
+    else if (token_is(kb, ke, "ANDF")) kind = ANDF;
+    else if (token_is(kb, ke, "ANDNOT")) kind = ANDNOT;
+    else return false;
+    const int field = ix.field_id(std::string(fb, fe));
+    const HostIndex::TermQuick* quick = ix.term_quick();
+
+    // what Compiler::add_term does with a TermQuery of this field
+    auto add_term = [&](const char* b, const char* e, uint8_t role) -> bool {
+        if (field < 0) return false;
+        const uint32_t id = ix.dict.find(static_cast<uint16_t>(field), reinterpret_cast<const uint8_t*>(b), static_cast<size_t>(e - b));
+        if (id == TermDictionary::kNotFound || !quick[id].present) return false;
+        dgpu_qterm t{};
+        t.term_id = id;
+        t.idf = quick[id].idf;
+        t.field = static_cast<uint16_t>(field);
+        t.role = role;
+        out.terms.push_back(t);
+        out.algorithmic_bytes += quick[id].encoded_bytes;
+        return true;
+    };
+
+    int n_should = 0, n_must = 0, msm = 1;
+    bool dead = false;
+    if (kind == TERM) {
+        if (!next_token(p, end, tb, te)) return give_up();   // (an empty term: generic path)
+        if (add_term(tb, te, DGPU_ROLE_SHOULD)) n_should = 1;
+    } else if (kind == OR) {
+        long long m = 0;
+        if (!next_token(p, end, tb, te) || !token_int(tb, te, m) || m < 0 || m > 60000) return give_up();
+        int clauses = 0;
+        while (next_token(p, end, tb, te)) {
+            ++clauses;
+            if (add_term(tb, te, DGPU_ROLE_SHOULD)) ++n_should;
+        }
+        if (clauses == 0) return give_up();
+        msm = std::max(1, static_cast<int>(m));
+    } else if (kind == AND || kind == ANDF || kind == ORF) {
+        long long lo = 0, hi = 0;
+        int dv = -1;
+        if (kind != AND) {
+            const char *db, *de;
+            if (!next_token(p, end, db, de)) return give_up();
+            dv = ix.dv_id(std::string(db, de));
+            if (!next_token(p, end, tb, te) || !token_int(tb, te, lo)) return give_up();
+            if (!next_token(p, end, tb, te) || !token_int(tb, te, hi)) return give_up();
+            if (lo > hi) return give_up();   // (NumericRangeQuery throws)
+        }
+        int clauses = 0;
+        while (next_token(p, end, tb, te)) {
+            ++clauses;
+            if (kind == ORF) {
+                if (add_term(tb, te, DGPU_ROLE_SHOULD)) ++n_should;
+            } else {
+                if (add_term(tb, te, DGPU_ROLE_MUST)) ++n_must; else dead = true;
+            }
+        }
+        if (clauses == 0) return give_up();
+        if (kind == ORF) {
+            if (n_should == 0) dead = true;   // the nested disjunction has no scorer
+        } else {
+            if (n_must == 0) return give_up();   // (the generic path rejects a required set without a term)
+            if (n_must > 255) return give_up();
+        }
+        if (kind != AND) {
+            if (dv < 0) {
+                dead = true;   // no values anywhere => no scorer (NumericRangeQuery.cpp:225-228)
+            } else {
+                dgpu_qfilter f{};
+                f.column = dv;
+                f.lo = lo;
+                f.hi = hi;
+                out.filters.push_back(f);
+            }
+        }
+    } else {   // ANDNOT n t1 .. tn x1 ..: the first n terms are required, the others excluded
+        long long n = 0;
+        if (!next_token(p, end, tb, te) || !token_int(tb, te, n)) return give_up();
+        long long i = 0;
+        std::vector<std::pair<const char*, const char*>> nots;
+        while (next_token(p, end, tb, te)) {
+            if (i++ < n) {
+                if (add_term(tb, te, DGPU_ROLE_MUST)) ++n_must; else dead = true;
+            } else {
+                nots.emplace_back(tb, te);
+            }
+        }
+        const long long required = std::min(i, std::max(0ll, n));
+        if (required == 0) dead = true;                       // only exclusions (or nothing): no scorer
+        else if (n_must == 0 || n_must > 255) return give_up();   // (generic path: rejected)
+        for (const auto& t : nots) add_term(t.first, t.second, DGPU_ROLE_MUST_NOT);
+    }
+
+    dgpu_query d{};
+    d.term_begin = static_cast<uint32_t>(t0);
+    d.filter_begin = static_cast<uint32_t>(f0);
+    if (dead || (n_must == 0 && n_should == 0)) {
+        out.terms.resize(t0);
+        out.filters.resize(f0);
+        n_must = 0;
+        msm = 1;
+    }
+    d.term_end = static_cast<uint32_t>(out.terms.size());
+    d.filter_end = static_cast<uint32_t>(out.filters.size());
+    d.n_must = static_cast<uint8_t>(n_must);
+    d.min_should_match = static_cast<uint16_t>(n_must > 0 && n_should == 0 ? 0 : msm);
+    out.queries.push_back(d);
+    return true;
+}
+
 // ------------------------------------------------------------------ search
 std::vector<TopDocs> IndexSearcher::search(const std::vector<const Query*>& queries, int numHits) {
     if (numHits <= 0) throw std::invalid_argument("numHits must be > 0");  // TopScoreDocCollector.cpp:49-51
     if (numHits > DGPU_MAX_K) throw std::invalid_argument("numHits exceeds DGPU_MAX_K");
     CompiledBatch batch;
     for (const Query* q : queries) compile(*q, batch);
+    auto guard = reader_.lock_engines();
     size_t n = queries.size();
     std::vector<uint64_t> keys(n * static_cast<size_t>(numHits));
     std::vector<int32_t> counts(n);

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -173,14 +174,20 @@ public:
     HostIndex& index() { return *index_; }
     const HostIndex& index() const { return *index_; }
     dgpu_engine* engine() const { return engine_; }
-    // A second engine over the same device index (created on first use): the batch call stages one chunk on it while
-    // the kernels of the previous chunk run on engine(). nullptr for a host-only reader or when it cannot be created.
-    dgpu_engine* shadow_engine();
+    // i-th extra engine over the same device index (own stream, staging and result buffers): the chunks of a pipelined
+    // batch rotate over engine() and these. nullptr when it cannot be created (the caller makes do with fewer).
+    dgpu_engine* shadow_engine(int i = 0);
+    static constexpr int kMaxShadows = 3;
+    // The engines of a reader hold per-batch state (staging buffers, scratch, results): every call that stages, launches
+    // or fetches takes this lock, so concurrent callers of one reader / searcher are serialised instead of racing
+    // (the reference builds its per-query state per call; throughput comes from the batch calls, not from threads).
+    std::unique_lock<std::recursive_mutex> lock_engines() { return std::unique_lock<std::recursive_mutex>(engine_mutex_); }
 
 private:
+    std::recursive_mutex engine_mutex_;
     std::shared_ptr<HostIndex> index_;
     dgpu_engine* engine_ = nullptr;
-    dgpu_engine* shadow_ = nullptr;
+    dgpu_engine* shadow_[kMaxShadows] = {nullptr, nullptr, nullptr};
     bool shadow_failed_ = false;
 };
 
@@ -230,6 +237,11 @@ public:
 
     // Query compilation (weight creation, TermQuery.cpp:184-260 + BooleanQuery.cpp:331-449 routing).
     void compile(const Query& query, CompiledBatch& out) const;
+    // The same for one line of the text form (parse_query_line), without building Query objects: the common shapes of a
+    // batch (TERM / OR / AND / ORF / ANDF / ANDNOT over known or unknown terms) are compiled straight from the bytes.
+    // Returns false - and leaves `out` as it was - for anything else, including every case in which the generic path
+    // throws: the caller then parses the line and calls compile(), so results and errors never differ.
+    bool compile_text_line(const char* begin, const char* end, CompiledBatch& out) const;
 
 private:
     IndexReader& reader_;

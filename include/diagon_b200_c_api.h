@@ -10,6 +10,13 @@
  *
  * Part 2 (dgpu_*) is what the reference has no equivalent for: handing a segment's postings to the
  * GPU once (upload), and scoring a whole batch of queries in one call.
+ *
+ * Threading: query and term handles are plain data and may be built on any thread. A reader (and the searchers
+ * created on it) owns GPU engines with per-batch state; every call that searches, stages, decodes or changes the
+ * statistics of one reader takes that reader's lock, so concurrent callers are safe and run one after the other
+ * (the reference's IndexSearcher is not thread-safe at all: IndexSearcher.h:290). Throughput comes from the batch
+ * calls, which use all host threads and pipeline host work with the kernels; use one reader per GPU.
+ * dgpu_reader_engine / dgpu_engine_* (dgpu_engine.h) bypass the lock: single-owner, tests and benchmarks only.
  */
 #ifndef DIAGON_B200_C_API_H
 #define DIAGON_B200_C_API_H

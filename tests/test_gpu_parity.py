@@ -154,7 +154,7 @@ def test_pipelined_text_batch_matches_golden(readers, golden_dir, name, chunks):
                     got = [(int(res.docs[q, j]), res.scores[q, j]) for j in range(res.counts[q])]
                     assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
     finally:
-        r.set_option("pipeline_chunks", 4)
+        r.set_option("pipeline_chunks", 3)
         r.set_option("pipeline_min", 2048)
 
 

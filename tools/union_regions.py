@@ -22,7 +22,7 @@ src = open('diagon_b200/csrc/union_kernels.cuh').read().split('\n')
 def ln(pat):
     return next(i for i, l in enumerate(src, 1) if pat in l)
 marks = [('item setup', ln('uint32_t ticket = 0;')), ('window setup', ln('// ---- window: W docs from')), ('visit', ln('while (!full) {')),
-         ('stream fast', ln('DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk')), ('slow path', ln('const bool l0 = (o0 & b0)')), ('term end', ln('if (!more) {')),
+         ('stream fast', ln('DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk')), ('slow path', ln('bool lt[4];   // later sightings')), ('term end', ln('if (!more) {')),
          ('candidates', ln('// ---- end of the window: first sightings')), ('resolve', ln('// resolve now?')), ('clear+final', ln("// ---- the window's bits back to zero")), ('end', len(src) + 1)]
 tot = sum(agg.values()); ts = sum(samp.values())
 print(f"total warp instructions {tot} = {tot / postings:.3f} per posting")
@@ -34,8 +34,8 @@ i = sum(v for (f, l), v in agg.items() if not f.startswith('union_kernels')); s 
 print(f"inlined headers  instr {i / tot * 100:5.1f}% ({i / postings:.3f}/posting) samples {s / ts * 100:5.1f}%")
 i = sum(v for (f, l), v in agg.items() if f.startswith('union_kernels') and l < marks[0][1])
 print(f"helpers          ({i / postings:.3f}/posting)")
-for pat, what in (('const uint32_t ws = opaque', 'windows'), ('u = __ffs(act) - 1;', 'visits'), ('const bool more =', 'chunk iterations'), ('const bool l0 =', 'slow path'),
-                  ('const uint32_t m0 = __ballot_sync', 'slow path (m0)'), ('rec_meta[e] = meta_u + c;', 'appends'), ('const bool valid = rb + lane < n_rec;', 'record batches'),
+for pat, what in (('const uint32_t ws = opaque', 'windows'), ('u = __ffs(act) - 1;', 'visits'), ('const bool more =', 'chunk iterations'), ('bool lt[4];', 'slow path'),
+                  ('const bool rec = lt[j] && (t || keep2);', 'slow path keep3'), ('const bool valid = rb + lane < n_rec;', 'record batches'),
                   ('for (; longest > 1; longest -= longest >> 1) {', 'clause groups'), ('if (__ldg(docs + b[g] + half - 1u) < doc) b[g] += half;', 'bisect steps')):
     for i, l in enumerate(src, 1):
         if pat in l and ('union_kernels.cuh', i) in per:
