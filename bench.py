@@ -328,8 +328,9 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        # torch.distributed is plumbing here: it ships the 128-byte NCCL id to the ranks and reduces the timings; the
+        # search itself, its collective included, is inside libdiagon_b200.so (dgpu_sharded_*)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        cpu_group = dist.new_group(backend="gloo")   # host-side exchange of compiled query slices (e2e path)
 
     lib = _lib.load()
     spec = dg.named_corpus(corpus_name, args.scale)
@@ -370,16 +371,16 @@ def main():
         reader.set_option("pool_smem_cap", args.pool_smem_cap)
     if args.lane_ctas_per_sm:
         reader.set_option("lane_ctas_per_sm", args.lane_ctas_per_sm)
+    sharded = None
     if world > 1:
-        # global statistics: idf / avgdl must be identical on every rank
-        df = torch.from_numpy(reader.get_doc_freqs()).cuda()
-        dist.all_reduce(df)
-        ttf, md = reader.get_field_totals("body")
-        tot = torch.tensor([ttf, md], dtype=torch.int64, device="cuda")
-        dist.all_reduce(tot)
-        reader.set_doc_freqs(df.cpu().numpy())
-        reader.set_field_totals("body", int(tot[0]), int(tot[1]))
-    searcher = dg.IndexSearcher(reader)
+        # every rank joins the library's NCCL communicator; creating the sharded searcher also sums docFreq and the field
+        # totals over the ranks (idf / avgdl must be the global ones on every rank)
+        uid = [dg.ShardedSearcher.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sharded = dg.ShardedSearcher(reader, uid[0], rank, world)
+        searcher = sharded.local
+    else:
+        searcher = dg.IndexSearcher(reader)
     text = dg.query_log_text(log_name, spec.vocab, batch, kind)
     nq = text.count(b"\n")
     stats = searcher.stage_batch_text(text, k)
@@ -388,39 +389,13 @@ def main():
     torch.cuda.set_stream(stream)         # the NCCL collectives and the timing events
     sptr = C.c_void_p(stream.cuda_stream)
 
-    dres = _lib.Results()
-    lib.dgpu_engine_device_results(eng, C.byref(dres))
-    if world > 1:
-        g_keys = torch.zeros((world, nq, k), dtype=torch.int64, device="cuda")
-        g_counts = torch.zeros((world, nq), dtype=torch.int32, device="cuda")
-        g_hits = torch.zeros((world, nq), dtype=torch.int64, device="cuda")
-        m_keys = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
-        m_counts = torch.zeros(nq, dtype=torch.int32, device="cuda")
-        m_hits = torch.zeros(nq, dtype=torch.int64, device="cuda")
-
     def device_step():
-        """Kernels only (plus, for N > 1, the all-gather and the device merge). Returns nothing; async."""
-        if lib.dgpu_engine_search_staged(eng, sptr) != 0:
+        """Kernels only (plus, for N > 1, the exchange: pack, ONE ncclAllGather, merge - all inside the library, on the
+        same stream). Returns nothing; async."""
+        if sharded is not None:
+            sharded.search_staged(stream.cuda_stream)
+        elif lib.dgpu_engine_search_staged(eng, sptr) != 0:
             raise RuntimeError(lib.dgpu_engine_last_error().decode())
-        if world > 1:
-            # local results -> torch views over the engine's device buffers (same stream, no copy)
-            lk = _wrap(dres.keys, (nq, k), torch.int64)
-            lc = _wrap(dres.counts, (nq,), torch.int32)
-            lh = _wrap(dres.total_hits, (nq,), torch.int64)
-            dist.all_gather_into_tensor(g_keys.view(-1), lk.view(-1))
-            dist.all_gather_into_tensor(g_counts.view(-1), lc.view(-1))
-            dist.all_gather_into_tensor(g_hits.view(-1), lh.view(-1))
-            if lib.dgpu_engine_merge_parts(eng, g_keys.data_ptr(), g_counts.data_ptr(), g_hits.data_ptr(), world, nq, k,
-                                           m_keys.data_ptr(), m_counts.data_ptr(), m_hits.data_ptr(), sptr) != 0:
-                raise RuntimeError(lib.dgpu_engine_last_error().decode())
-
-    def _wrap(ptr, shape, dtype):
-        class _CAI:  # __cuda_array_interface__ view of an engine-owned device buffer
-            pass
-        o = _CAI()
-        typestr = {torch.int64: "<i8", torch.int32: "<i4"}[dtype]
-        o.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-        return torch.as_tensor(o, device="cuda")
 
     def barrier():
         if dist is not None:
@@ -463,44 +438,20 @@ def main():
     value = nq / (ms_per_step / 1e3)
 
     # ---- end to end through the C ABI with host buffers: query text in host memory -> results in host memory.
-    # N == 1: one call, dgpu_search_batch_text. N > 1: the ranks divide the parse + compile work, exchange the compiled
-    # slices, stage the batch (H2D), run their kernels, the NCCL all-gather and the device merge, and copy the merged
-    # top-k back to the host.
+    # N == 1: one call, dgpu_search_batch_text. N > 1: one call per rank, dgpu_sharded_search_batch_text (the collective
+    # is inside the library).
     out = searcher._alloc(nq, k)
     e2e_times = []
-    if world > 1:
-        all_lines = text.split(b"\n")[:nq]
-        my_text = b"\n".join(all_lines[nq * rank // world: nq * (rank + 1) // world]) + b"\n"
     n_warm = max(2, min(args.warmup, 3))
     for i in range(n_warm + args.steps):
         barrier()
         t1 = time.perf_counter()
-        if world == 1:
+        if sharded is None:
             res = searcher.search_batch_text(text, k, nq, out)
         else:
-            # every rank parses + compiles 1/N of the query lines, one gloo all_gather exchanges the compiled slices
-            # (descriptors depend on global statistics only), then each rank stages the whole batch on its GPU
-            tt = [time.perf_counter()]
-            blob = searcher.compile_batch_text(my_text)
-            tt.append(time.perf_counter())
-            sz = torch.tensor([blob.size], dtype=torch.int64)
-            sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-            dist.all_gather(sizes, sz, group=cpu_group)
-            cap = max(int(x[0]) for x in sizes)
-            mine = torch.zeros(cap, dtype=torch.uint8)
-            mine[: blob.size] = torch.from_numpy(blob)
-            gathered = [torch.zeros(cap, dtype=torch.uint8) for _ in range(world)]
-            dist.all_gather(gathered, mine, group=cpu_group)
-            tt.append(time.perf_counter())
-            searcher.stage_compiled([g.numpy()[: int(n[0])] for g, n in zip(gathered, sizes)], k)
-            tt.append(time.perf_counter())
-            lib.dgpu_engine_device_results(eng, C.byref(dres))
-            device_step()
-            _ = (m_keys.cpu(), m_counts.cpu(), m_hits.cpu())   # D2H on the bench stream, synchronising
-            tt.append(time.perf_counter())
-            if os.environ.get("DGPU_TRACE") and rank == 0:
-                sys.stderr.write("[bench trace] compile %.2f ms, exchange %.2f ms, stage %.2f ms, device+merge+d2h %.2f ms\n"
-                                 % tuple(1e3 * (b - a) for a, b in zip(tt, tt[1:])))
+            # every rank hands the same batch to the library: parse + compile, H2D, kernels on its shard, one all-gather
+            # per chunk, merge, D2H of the merged top-k into host arrays
+            res = sharded.search_batch_text(text, k, nq, out)
         t2 = time.perf_counter()
         if i >= n_warm:
             e2e_times.append(t2 - t1)
@@ -564,16 +515,17 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_text(spec),
-                       "sharding": f"{nseg} segments over {world} GPU(s), {'NCCL all-gather + device merge' if world > 1 else 'single GPU'}",
+                       "sharding": f"{nseg} segments over {world} GPU(s), {'one NCCL all-gather per batch + device merge, inside the library' if world > 1 else 'single GPU'}",
                        "l2": "inputs larger than L2 (device image %.0f MB per GPU)" % (reader.image_bytes() / 1e6),
                        "index_build_s": build_s, "postings_on_gpu": reader.num_postings(), "image_bytes": reader.image_bytes(),
                        "kernel_path": "batched" if batched else "fused-windows"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": ("dgpu_search_batch_text (host text -> host results; the batch is cut into chunks, chunk i + 1 is parsed, "
-                             "compiled and staged on a second engine while the kernels of chunk i run)" if world == 1 else
-                             "per rank: dgpu_compile_batch_text on 1/N of the lines, gloo all_gather of the slices, "
-                             "dgpu_stage_compiled, kernels, NCCL all_gather, device merge, D2H of the merged top-k"),
+                             "compiled and staged on another engine while the kernels of chunk i run)" if world == 1 else
+                             "dgpu_sharded_search_batch_text on every rank (host text -> merged host results: parse + compile, "
+                             "H2D, kernels on the rank's shard, ONE ncclAllGather of k keys + count + hits per query and chunk, "
+                             "device merge, D2H)"),
                     "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
             "roofline": roofline,
         }

@@ -5,7 +5,7 @@ Python mirror of the reference's search API used by tests and bench.py; it conta
 """
 from .api import (  # noqa: F401
     BatchResult, BooleanClause, BooleanQuery, DiagonError, IndexBuilder, IndexReader, IndexSearcher,
-    NumericRangeQuery, Occur, Query, ScoreDoc, Term, TermQuery, TopDocs, TotalHits, and_query, named_corpus,
+    NumericRangeQuery, Occur, Query, ScoreDoc, ShardedSearcher, Term, TermQuery, TopDocs, TotalHits, and_query, named_corpus,
     or_query, parse_line, query_log_text, write_synthetic_dump,
 )
 from .dumpfile import read_dump  # noqa: F401

@@ -99,6 +99,19 @@ PROTOTYPES = {
     "dgpu_search_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "dgpu_stage_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p]),
     "dgpu_compile_batch_text": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "dgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "dgpu_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "dgpu_comm_destroy": (None, [C.c_void_p]),
+    "dgpu_comm_rank": (C.c_int, [C.c_void_p]),
+    "dgpu_comm_world": (C.c_int, [C.c_void_p]),
+    "dgpu_comm_allreduce_sum_i64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dgpu_engine_exchange_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dgpu_sharded_unique_id": (C.c_int, [C.c_void_p]),
+    "dgpu_sharded_searcher_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "dgpu_sharded_searcher_free": (None, [C.c_void_p]),
+    "dgpu_sharded_searcher_local": (C.c_void_p, [C.c_void_p]),
+    "dgpu_sharded_search_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "dgpu_sharded_search_staged": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dgpu_stage_compiled": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     "dgpu_create_long_range_query": (C.c_void_p, [C.c_char_p, C.c_int64, C.c_int64, C.c_bool, C.c_bool]),
     "dgpu_parse_query": (C.c_void_p, [C.c_char_p]),

@@ -481,9 +481,9 @@ class IndexSearcher:
         return r
 
     def close(self):
-        if self._ptr:
+        if self._ptr and not getattr(self, "_borrowed", False):
             _lib.load().diagon_free_index_searcher(self._ptr)
-            self._ptr = None
+        self._ptr = None
 
     def __del__(self):
         try:
@@ -514,3 +514,48 @@ def query_log_text(config: str, vocab: int, num_queries: int, kind: str) -> byte
 def write_synthetic_dump(spec, path: str):
     if _lib.load().dgpu_write_synthetic_dump(C.byref(spec), str(path).encode()) != 0:
         raise DiagonError(_lib.last_error())
+
+
+class ShardedSearcher:
+    """dgpu_sharded_searcher_*: this rank's shard of a segment-sharded index, searched together with the other ranks'
+    (one NCCL all-gather of the local top k per batch). Collective: every rank makes the same calls in the same order."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        if _lib.load().dgpu_sharded_unique_id(C.addressof(buf)) != 0:
+            raise DiagonError(_lib.last_error())
+        return bytes(buf)
+
+    def __init__(self, reader: IndexReader, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == 128
+        self.reader = reader
+        self._id = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ptr = _lib.load().dgpu_sharded_searcher_create(reader._ptr, C.addressof(self._id), rank, world)
+        if not self._ptr:
+            raise DiagonError(_lib.last_error())
+        # the rank's ordinary searcher (borrowed: freed with the sharded searcher)
+        self.local = IndexSearcher.__new__(IndexSearcher)
+        self.local.reader = reader
+        self.local._ptr = _lib.load().dgpu_sharded_searcher_local(self._ptr)
+        self.local._borrowed = True
+
+    def search_batch_text(self, text: bytes, k: int, max_queries: Optional[int] = None, out=None) -> BatchResult:
+        if max_queries is None:
+            max_queries = text.count(b"\n") + 1
+        docs, scores, counts, hits = out if out is not None else self.local._alloc(max_queries, k)
+        r = _lib.load().dgpu_sharded_search_batch_text(self._ptr, text, len(text), k, docs.ctypes.data, scores.ctypes.data,
+                                                       counts.ctypes.data, hits.ctypes.data, max_queries)
+        if r < 0:
+            raise DiagonError(_lib.last_error())
+        return BatchResult(docs[:r], scores[:r], counts[:r], hits[:r])
+
+    def search_staged(self, stream=None):
+        """Kernels of the staged batch + the exchange, on `stream` (a cudaStream_t as int, None = the engine's own)."""
+        if _lib.load().dgpu_sharded_search_staged(self._ptr, C.c_void_p(stream) if stream else None) != 0:
+            raise DiagonError(_lib.last_error())
+
+    def close(self):
+        if self._ptr:
+            _lib.load().dgpu_sharded_searcher_free(self._ptr)
+            self._ptr = None

@@ -166,6 +166,8 @@ struct dgpu_engine {
     bool split_any = false;
     bool plan_pool_global = false;
     DevBuf<uint64_t> d_pool;
+    DevBuf<uint64_t> d_packed, d_gathered;   // sharded search: this rank's (k + 2)-word records, and every rank's
+    uint64_t collectives = 0;                // NCCL calls issued (one per exchanged batch)
     PinnedArena h_stage, h_results;
     struct TableEntry {
         uint64_t key;   // term id << 32 | idf bits
@@ -306,6 +308,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     e->d_run_docs.release(); e->d_run_scores.release(); e->d_run_cmax.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
     e->d_witems.release(); e->d_part_off.release(); e->d_pool.release();
+    e->d_packed.release(); e->d_gathered.release();
     e->h_stage.release(); e->h_results.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1250,3 +1253,5 @@ int dgpu_engine_merge_parts(dgpu_engine* e, const uint64_t* part_keys, const int
 }
 
 }  // extern "C"
+
+#include "collective.cuh"

@@ -154,15 +154,20 @@ void compile_lines(IndexSearcher& s, const std::vector<LineSpan>& lines, size_t 
 }
 
 int run_compiled(IndexSearcher& s, const CompiledBatch& batch, int32_t k, int32_t* out_docs, float* out_scores,
-                 int32_t* out_counts, int64_t* out_total_hits) {
+                 int32_t* out_counts, int64_t* out_total_hits, dgpu_comm* comm = nullptr) {
     const size_t n = batch.queries.size();
     std::vector<uint64_t> keys(n * static_cast<size_t>(k));
     std::vector<int32_t> counts(n);
     dgpu_results res{keys.data(), counts.data(), out_total_hits};
     dgpu_query_batch view = batch.view();
     auto guard = s.getIndexReader().lock_engines();
-    if (n && !s.getIndexReader().engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
-    if (n && dgpu_engine_search(s.getIndexReader().engine(), &view, k, &res) != 0)
+    dgpu_engine* e = s.getIndexReader().engine();
+    if (n && !e) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
+    if (n && comm) {   // sharded: every rank runs the same batch; the exchange is collective
+        if (dgpu_engine_stage_batch(e, &view, k) != 0 || dgpu_engine_search_staged(e, nullptr) != 0 ||
+            dgpu_engine_exchange_topk(e, comm, nullptr) != 0 || dgpu_engine_fetch_results(e, &res) != 0)
+            throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
+    } else if (n && dgpu_engine_search(e, &view, k, &res) != 0)
         throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
     unpack(keys, counts, static_cast<int32_t>(n), k, out_docs, out_scores);
     std::memcpy(out_counts, counts.data(), n * sizeof(int32_t));
@@ -201,7 +206,7 @@ int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, 
 // parses, compiles and stages chunk i + 1 on the other engine. Results are those of the unchunked call (queries are
 // independent; only the sharing of decoded terms between queries shrinks to a chunk).
 int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int chunks, int32_t k, int32_t* out_docs,
-                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits) {
+                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits, dgpu_comm* comm = nullptr) {
     if (k <= 0) throw std::invalid_argument("numHits must be > 0");
     static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
@@ -244,7 +249,8 @@ int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int
             fetch(slot);   // the chunk before last ran on this engine: its results leave before its buffers are reused
             const double tc = now_ms();
             dgpu_query_batch view = batch.view();
-            if (dgpu_engine_stage_batch(eng[slot], &view, k) != 0 || dgpu_engine_search_staged(eng[slot], nullptr) != 0)
+            if (dgpu_engine_stage_batch(eng[slot], &view, k) != 0 || dgpu_engine_search_staged(eng[slot], nullptr) != 0 ||
+                (comm && dgpu_engine_exchange_topk(eng[slot], comm, nullptr) != 0))   // sharded: the ranks' top k, one all-gather
                 throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
             fly[slot] = Inflight{q0, true};
             if (trace)
@@ -673,29 +679,123 @@ int dgpu_search_batch(DiagonIndexSearcher searcher, const DiagonQuery* queries, 
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
 
+static int search_text(IndexSearcher& s, dgpu_comm* comm, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
+                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
+    auto tp = std::chrono::steady_clock::now();
+    const auto lines = split_lines(text, text_len);
+    if (static_cast<int64_t>(lines.size()) > max_queries) { set_error("more queries than max_queries"); return -1; }
+    if (dgpu_engine* e = s.getIndexReader().engine()) {
+        int32_t pl[2];
+        dgpu_engine_pipeline(e, pl);
+        if (pl[0] > 1 && lines.size() >= static_cast<size_t>(pl[1]) && lines.size() >= static_cast<size_t>(pl[0]) &&
+            s.getIndexReader().shadow_engine())
+            return run_text_pipelined(s, lines, pl[0], k, out_docs, out_scores, out_counts, out_total_hits, comm);
+    }
+    if (k <= 0) throw std::invalid_argument("numHits must be > 0");
+    CompiledBatch batch;
+    compile_lines(s, lines, 0, lines.size(), batch);
+    if (std::getenv("DGPU_TRACE"))
+        std::fprintf(stderr, "[dgpu trace] parse + compile %.3f ms\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count());
+    return run_compiled(s, batch, k, out_docs, out_scores, out_counts, out_total_hits, comm);
+}
+
 int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
                            float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
     if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
     try {
-        auto tp = std::chrono::steady_clock::now();
-        const auto lines = split_lines(text, text_len);
-        if (static_cast<int64_t>(lines.size()) > max_queries) { set_error("more queries than max_queries"); return -1; }
-        IndexSearcher& s = *as_searcher(searcher);
-        if (dgpu_engine* e = s.getIndexReader().engine()) {
-            int32_t pl[2];
-            dgpu_engine_pipeline(e, pl);
-            if (pl[0] > 1 && lines.size() >= static_cast<size_t>(pl[1]) && lines.size() >= static_cast<size_t>(pl[0]) &&
-                s.getIndexReader().shadow_engine())
-                return run_text_pipelined(s, lines, pl[0], k, out_docs, out_scores, out_counts, out_total_hits);
-        }
-        if (k <= 0) throw std::invalid_argument("numHits must be > 0");
-        CompiledBatch batch;
-        compile_lines(s, lines, 0, lines.size(), batch);
-        if (std::getenv("DGPU_TRACE"))
-            std::fprintf(stderr, "[dgpu trace] parse + compile %.3f ms\n",
-                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count());
-        return run_compiled(s, batch, k, out_docs, out_scores, out_counts, out_total_hits);
+        return search_text(*as_searcher(searcher), nullptr, text, text_len, k, out_docs, out_scores, out_counts, out_total_hits,
+                           max_queries);
     } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+// ------------------------------------------------------------------ segment-sharded search (one rank per GPU)
+namespace {
+struct ShardedSearcher {
+    IndexSearcher searcher;
+    dgpu_comm* comm = nullptr;
+    explicit ShardedSearcher(IndexReader& r) : searcher(r) {}
+};
+ShardedSearcher* as_sharded(DgpuShardedSearcher p) { return static_cast<ShardedSearcher*>(p); }
+}  // namespace
+
+int dgpu_sharded_unique_id(uint8_t* out_id) {
+    if (!out_id) { set_error("Invalid id buffer"); return -1; }
+    if (dgpu_comm_unique_id(out_id) != 0) { set_error(dgpu_engine_last_error()); return -1; }
+    return 0;
+}
+
+DgpuShardedSearcher dgpu_sharded_searcher_create(DiagonIndexReader reader, const uint8_t* id, int32_t rank, int32_t world) {
+    if (!reader || !id) { set_error("Invalid reader or id"); return nullptr; }
+    try {
+        IndexReader* rd = as_reader(reader);
+        if (!rd->engine()) { set_error("host-only reader: no GPU engine, and there is no CPU fallback"); return nullptr; }
+        auto ss = std::make_unique<ShardedSearcher>(*rd);
+        if (dgpu_comm_create(id, rank, world, dgpu_engine_device(rd->engine()), &ss->comm) != 0) {
+            set_error(dgpu_engine_last_error());
+            return nullptr;
+        }
+        HostIndex& ix = rd->index();
+        if (ix.stats_need_exchange && world > 1) {
+            // idf and avgdl come from statistics over ALL leaves (TermQuery.cpp:195-247): sum the shards' docFreq per
+            // term and (sumTotalTermFreq, maxDoc) per field, so that every rank scores with the same numbers
+            auto guard = rd->lock_engines();
+            std::vector<int64_t> buf(ix.term_doc_freq);
+            for (size_t f = 0; f < ix.fields.size(); ++f) {
+                int64_t s = 0, m = 0;
+                for (size_t i = 0; i < ix.segments.size(); ++i) {
+                    if (!ix.segments[i].is_local) continue;
+                    const auto& fs = ix.field_stats[i][f];
+                    if (fs.has_terms && fs.sum_total_term_freq > 0) s += fs.sum_total_term_freq;
+                    m += ix.segments[i].max_doc;
+                }
+                buf.push_back(s);
+                buf.push_back(m);
+            }
+            if (dgpu_comm_allreduce_sum_i64(ss->comm, buf.data(), buf.size()) != 0) {
+                set_error(dgpu_engine_last_error());
+                dgpu_comm_destroy(ss->comm);
+                return nullptr;
+            }
+            const size_t nt = ix.term_doc_freq.size();
+            std::copy(buf.begin(), buf.begin() + static_cast<std::ptrdiff_t>(nt), ix.term_doc_freq.begin());
+            for (size_t f = 0; f < ix.fields.size(); ++f) ix.set_global_stats(static_cast<int>(f), buf[nt + 2 * f], buf[nt + 2 * f + 1]);
+            ix.stats_need_exchange = false;
+            if (dgpu_engine_set_ktab(rd->engine(), ix.image.ktab.data(), ix.image.n_fields) != 0) {
+                set_error(dgpu_engine_last_error());
+                dgpu_comm_destroy(ss->comm);
+                return nullptr;
+            }
+        }
+        return ss.release();
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+void dgpu_sharded_searcher_free(DgpuShardedSearcher s) {
+    if (!s) return;
+    dgpu_comm_destroy(as_sharded(s)->comm);
+    delete as_sharded(s);
+}
+
+DiagonIndexSearcher dgpu_sharded_searcher_local(DgpuShardedSearcher s) { return s ? &as_sharded(s)->searcher : nullptr; }
+
+int dgpu_sharded_search_batch_text(DgpuShardedSearcher s, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
+                                   float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
+    if (!s || !text) { set_error("Invalid searcher or text"); return -1; }
+    try {
+        return search_text(as_sharded(s)->searcher, as_sharded(s)->comm, text, text_len, k, out_docs, out_scores, out_counts,
+                           out_total_hits, max_queries);
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+int dgpu_sharded_search_staged(DgpuShardedSearcher s, void* stream) {
+    if (!s) { set_error("Invalid searcher"); return -1; }
+    dgpu_engine* e = as_sharded(s)->searcher.getIndexReader().engine();
+    if (dgpu_engine_search_staged(e, stream) != 0 || dgpu_engine_exchange_topk(e, as_sharded(s)->comm, stream) != 0) {
+        set_error(dgpu_engine_last_error());
+        return -1;
+    }
+    return 0;
 }
 
 int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats) {

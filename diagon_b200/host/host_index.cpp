@@ -601,6 +601,7 @@ std::shared_ptr<HostIndex> build_synthetic(const synth::CorpusSpec& spec, int se
         ix.field_stats.emplace_back(1);
     }
     ix.max_doc_total = spec.num_docs;
+    ix.stats_need_exchange = seg_lo != 0 || seg_hi != static_cast<int>(spec.num_segments);
     ix.image.doc_lo = doc_lo;
     ix.image.doc_hi = doc_hi;
 

@@ -74,6 +74,10 @@ public:
     std::vector<int64_t> term_doc_freq;        // GLOBAL docFreq (sum over all leaves)
     std::vector<int64_t> term_total_term_freq;
     int64_t max_doc_total = 0;                 // IndexReader::maxDoc() over all leaves
+    // A shard that only knows its own documents (a synthetic corpus generated per rank): docFreq and the field totals
+    // are local until the ranks have summed them (dgpu_sharded_searcher_create). Shards opened from an index directory
+    // or built through dgpu_builder_* read the statistics of every segment themselves.
+    bool stats_need_exchange = false;
     IndexImage image;                          // local postings, device layout
 
     int field_id(const std::string& name) const;

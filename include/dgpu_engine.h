@@ -154,6 +154,26 @@ int dgpu_engine_merge_parts(dgpu_engine* e, const uint64_t* part_keys, const int
                             const int64_t* part_hits, int32_t n_parts, uint32_t n_queries, int32_t k,
                             uint64_t* out_keys, int32_t* out_counts, int64_t* out_hits, void* stream);
 
+/* Segment-sharded search: one rank per GPU, each holding a contiguous run of segments. NCCL is
+ * bound at run time (dlopen libnccl.so.2); without it these calls fail with a message, everything else works.
+ *   dgpu_comm_unique_id   rank 0 makes the id, the caller ships its 128 bytes to the other ranks by any means
+ *   dgpu_comm_create      ncclCommInitRank on `device`
+ *   dgpu_comm_allreduce_sum_i64   start-up exchange of index statistics (docFreq per term, field totals: TermQuery.cpp:195-247
+ *                         needs them over ALL leaves), host array in and out
+ *   dgpu_engine_exchange_topk     after dgpu_engine_search_staged: packs this rank's top k + hit count per query, ONE
+ *                         ncclAllGather, merge by the collector's order (TopScoreDocCollector.cpp:205-231); the merged
+ *                         results replace the local ones in the engine's result buffers (fetch / device_results as usual).
+ *                         All ranks must call it for the same batches in the same order. */
+#define DGPU_COMM_ID_BYTES 128
+typedef struct dgpu_comm dgpu_comm;
+int dgpu_comm_unique_id(uint8_t out[DGPU_COMM_ID_BYTES]);
+int dgpu_comm_create(const uint8_t id[DGPU_COMM_ID_BYTES], int rank, int world, int device, dgpu_comm** out);
+void dgpu_comm_destroy(dgpu_comm* c);
+int dgpu_comm_rank(const dgpu_comm* c);
+int dgpu_comm_world(const dgpu_comm* c);
+int dgpu_comm_allreduce_sum_i64(dgpu_comm* c, int64_t* host_inout, size_t n);
+int dgpu_engine_exchange_topk(dgpu_engine* e, dgpu_comm* c, void* stream);
+
 /* Bookkeeping for the roofline: kernel launches issued by this engine since creation, and the
  * device time (ms) of the last dgpu_engine_search / search_staged call measured with CUDA events
  * on the launching stream. */

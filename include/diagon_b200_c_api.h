@@ -175,6 +175,27 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
  * out_stats: [0] queries, [1] algorithmic posting bytes of the batch, [2] postings of the batch. */
 int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats);
 
+/* Segment-sharded search, one rank (process) per GPU (the reference loops over the leaves and shares
+ * one collector: IndexSearcher.cpp:76-110). Every rank opens ITS run of segments (dgpu_open_index / dgpu_open_synthetic
+ * with seg_lo, seg_hi, or dgpu_builder_add_segment(..., is_local)); rank 0 makes a 128-byte id with dgpu_sharded_unique_id
+ * and the caller ships it to the other ranks (MPI, a file, torch.distributed: plumbing). dgpu_sharded_searcher_create joins
+ * the NCCL communicator (NCCL is bound at run time, dlopen libnccl.so.2) and, for shards that only know their own
+ * documents, sums docFreq and the field totals over the ranks so that idf / avgdl are the global ones everywhere
+ * (TermQuery.cpp:195-247). dgpu_sharded_search_batch_text is dgpu_search_batch_text over all shards: every rank passes
+ * the SAME batch, scores it on its documents, ONE ncclAllGather per (chunk of a) batch moves k keys + count + hits per
+ * query, each rank merges by the collector's order and returns the same merged results. Calls are collective: all ranks,
+ * same order. dgpu_sharded_searcher_local is the rank's ordinary searcher (staging, options, statistics);
+ * dgpu_sharded_search_staged = dgpu_engine_search_staged + the exchange on `stream` (results stay on the device). */
+typedef void* DgpuShardedSearcher;
+int dgpu_sharded_unique_id(uint8_t* out_id /* [128] */);
+DgpuShardedSearcher dgpu_sharded_searcher_create(DiagonIndexReader local_shard, const uint8_t* id /* [128] */, int32_t rank,
+                                                 int32_t world);
+void dgpu_sharded_searcher_free(DgpuShardedSearcher s);
+DiagonIndexSearcher dgpu_sharded_searcher_local(DgpuShardedSearcher s);
+int dgpu_sharded_search_batch_text(DgpuShardedSearcher s, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
+                                   float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries);
+int dgpu_sharded_search_staged(DgpuShardedSearcher s, void* stream);
+
 /* Sharded indexes: the host work of a batch can be divided between the ranks. dgpu_compile_batch_text parses and
  * compiles a slice of a batch into a relocatable blob WITHOUT touching the device (returns the bytes needed; writes
  * them when `capacity` suffices; every descriptor depends on global statistics only, so any rank may compile any
