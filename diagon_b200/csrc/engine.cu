@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
@@ -455,6 +456,23 @@ int dgpu_engine_upload(dgpu_engine* e, const dgpu_index_image* im) {
     e->owned.push_back(dcols);
     if (!cols.empty()) CU(cudaMemcpy(dcols, cols.data(), cols.size() * sizeof(int64_t*), cudaMemcpyHostToDevice));
     e->ix.dv = static_cast<const int64_t* const*>(dcols);
+    // a column whose values all fit 32 bits is kept a second time as int32: range filters gather it at random, one
+    // value per collected doc (NumericRangeQuery.cpp:129-181 compares int64; the bounds are clamped, the test is the same)
+    std::vector<const int32_t*> cols32(im->n_dv, nullptr);
+    const size_t n_docs = static_cast<size_t>(im->doc_hi - im->doc_lo);
+    for (uint32_t c = 0; c < im->n_dv; ++c) {
+        bool fits = true;
+        for (size_t d = 0; d < n_docs && fits; ++d) fits = im->dv[c][d] >= INT32_MIN && im->dv[c][d] <= INT32_MAX;
+        if (!fits) continue;
+        std::vector<int32_t> narrow(n_docs);
+        for (size_t d = 0; d < n_docs; ++d) narrow[d] = static_cast<int32_t>(im->dv[c][d]);
+        if (upload_array(e, narrow.data(), n_docs, &cols32[c])) return -1;
+    }
+    void* dcols32 = nullptr;
+    CU(cudaMalloc(&dcols32, std::max<size_t>(cols32.size(), 1) * sizeof(int32_t*)));
+    e->owned.push_back(dcols32);
+    if (!cols32.empty()) CU(cudaMemcpy(dcols32, cols32.data(), cols32.size() * sizeof(int32_t*), cudaMemcpyHostToDevice));
+    e->ix.dv32 = static_cast<const int32_t* const*>(dcols32);
     e->ix.doc_lo = im->doc_lo;
     e->ix.doc_hi = im->doc_hi;
     return 0;

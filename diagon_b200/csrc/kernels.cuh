@@ -27,6 +27,7 @@ struct DeviceIndex {
     const uint8_t* data;
     const float* ktab;
     const int64_t* const* dv;
+    const int32_t* const* dv32;   // the same column as 32-bit values when every value fits (else null): half the gather footprint
     uint32_t doc_lo, doc_hi;
 };
 

@@ -127,11 +127,20 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         const uint32_t nf = FILTER ? qd.filter_end - qd.filter_begin : 0u;
         const dgpu_qfilter* qf = P.filters + qd.filter_begin;
         const int64_t* dv0 = nullptr;   // first range filter of the query: column, bounds
+        const int32_t* dv0n = nullptr;  // ... the column as 32-bit values when it has that form: bounds clamped to int32
         int64_t lo0 = 0, hi0 = 0;
+        int32_t lo0n = 0, hi0n = -1;
         if (FILTER && nf) {
             dv0 = ix.dv[qf[0].column] - ix.doc_lo;
             lo0 = qf[0].lo;
             hi0 = qf[0].hi;
+            if (ix.dv32[qf[0].column]) {
+                dv0n = ix.dv32[qf[0].column] - ix.doc_lo;
+                if (lo0 <= INT32_MAX && hi0 >= INT32_MIN) {   // else no 32-bit value is inside: lo0n > hi0n stays
+                    lo0n = static_cast<int32_t>(max(lo0, static_cast<int64_t>(INT32_MIN)));
+                    hi0n = static_cast<int32_t>(min(hi0, static_cast<int64_t>(INT32_MAX)));
+                }
+            }
         }
         const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
         DGPU_ASSERT(nt <= 32u);
@@ -223,8 +232,14 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         };
         // every range filter of the query on one doc
         auto passes = [&](uint32_t doc) -> bool {
-            const int64_t v0 = dv0[doc];
-            bool ok = v0 >= lo0 && v0 <= hi0;
+            bool ok;
+            if (dv0n) {
+                const int32_t v0 = __ldg(dv0n + doc);
+                ok = v0 >= lo0n && v0 <= hi0n;
+            } else {
+                const int64_t v0 = dv0[doc];
+                ok = v0 >= lo0 && v0 <= hi0;
+            }
             for (uint32_t f = 1; f < nf && ok; ++f) {
                 const int64_t v = ix.dv[qf[f].column][doc - ix.doc_lo];
                 ok = v >= qf[f].lo && v <= qf[f].hi;

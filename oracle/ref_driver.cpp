@@ -9,6 +9,9 @@
 //            results to a binary file, optional multi-threaded timing (one reader+searcher per thread,
 //            because the reference's searcher is not thread-safe: IndexSearcher.h:290)
 //   kat    : known answers of util::StreamVByte / util::BitPacking for pinning oracle/bm25_oracle.c
+//   spec   : the numbers of a named synthetic corpus as JSON (docs, vocab, segments)
+//   queries: a named synthetic query log in the text form below (so that the reference arm of bench.py needs nothing
+//            of the product, not even its query generator's Python binding)
 //
 // Query file: one query per line
 //   TERM <field> <term>
@@ -39,6 +42,7 @@
 
 #include "synth_corpus.h"
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -313,6 +317,10 @@ int cmd_search(const Args& a) {
     if (threads < 1) threads = 1;
     std::vector<Result> results(lines.size());
     std::vector<double> perThreadSec(static_cast<size_t>(threads), 0.0);
+    std::vector<std::atomic<size_t>> cursors(static_cast<size_t>(warmup + repeat));
+    std::vector<std::atomic<int>> arrived(static_cast<size_t>(warmup + repeat));
+    for (auto& c : cursors) c.store(0);
+    for (auto& c : arrived) c.store(0);
     std::string dirPath = a.get("dir");
 
     auto worker = [&](int t) {
@@ -321,11 +329,14 @@ int cmd_search(const Args& a) {
         search::IndexSearcherConfig cfg;
         cfg.enable_block_max_wand = wand;
         search::IndexSearcher searcher(*reader, cfg);
-        size_t lo = lines.size() * static_cast<size_t>(t) / static_cast<size_t>(threads);
-        size_t hi = lines.size() * static_cast<size_t>(t + 1) / static_cast<size_t>(threads);
         for (int rep = -warmup; rep < repeat; ++rep) {
+            // the threads start a repetition together and pull queries from one counter: nobody idles while another
+            // thread still holds the expensive queries of a static slice
+            std::atomic<size_t>& next = cursors[static_cast<size_t>(rep + warmup)];
+            ++arrived[static_cast<size_t>(rep + warmup)];
+            while (arrived[static_cast<size_t>(rep + warmup)].load() < threads) std::this_thread::yield();
             auto t0 = std::chrono::steady_clock::now();
-            for (size_t q = lo; q < hi; ++q) {
+            for (size_t q = next.fetch_add(1); q < lines.size(); q = next.fetch_add(1)) {
                 auto query = parse_query(lines[q]);  // rebuilt each time, like reuters_benchmark.cpp:321-356
                 search::TopDocs td = searcher.search(*query, k);
                 if (rep == repeat - 1) {
@@ -340,6 +351,17 @@ int cmd_search(const Args& a) {
                 perThreadSec[static_cast<size_t>(t)] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
     };
+    if (threads > 1 && !lines.empty()) {
+        // one search on this thread first: whatever the reference initialises lazily on first use is set up before the
+        // workers start together (its searcher makes no promise about concurrent first use)
+        auto dir = store::MMapDirectory::open(dirPath);
+        auto reader = index::DirectoryReader::open(*dir);
+        search::IndexSearcherConfig cfg;
+        cfg.enable_block_max_wand = wand;
+        search::IndexSearcher searcher(*reader, cfg);
+        auto query = parse_query(lines[0]);
+        (void)searcher.search(*query, k);
+    }
     auto w0 = std::chrono::steady_clock::now();
     if (threads == 1) {
         worker(0);
@@ -372,6 +394,32 @@ int cmd_search(const Args& a) {
                 "\"search_seconds\": %.6f, \"wall_seconds\": %.6f, \"qps\": %.3f}\n",
                 lines.size(), repeat, threads, wand ? 1 : 0, k, slowest, wall,
                 slowest > 0 ? static_cast<double>(lines.size()) * repeat / slowest : 0.0);
+    return 0;
+}
+
+// ------------------------------------------------------------------ spec / queries
+int cmd_spec(const Args& a) {
+    auto spec = corpus_from_args(a);
+    std::printf("{\"num_docs\": %u, \"vocab\": %u, \"num_segments\": %u, \"with_price\": %d}\n", spec.num_docs, spec.vocab,
+                spec.num_segments, spec.with_price ? 1 : 0);
+    return 0;
+}
+
+int cmd_queries(const Args& a) {
+    dgpu::synth::QueryLogSpec qs = dgpu::synth::named_query_log(a.get("log"), static_cast<uint32_t>(a.integer("vocab", 0)),
+                                                                static_cast<uint32_t>(a.integer("n", 0)));
+    if (qs.num_queries == 0) throw std::runtime_error("unknown query log " + a.get("log"));
+    dgpu::synth::QueryLog log = dgpu::synth::make_query_log(qs);
+    const std::string kind = a.get("kind");
+    std::ofstream o(a.get("out"), std::ios::binary);
+    for (uint32_t q = 0; q < log.size(); ++q) {
+        o << kind;
+        if (qs.with_range) o << ' ' << log.range_lo[q] << ' ' << log.range_hi[q];
+        const uint32_t* r = log.query(q);
+        for (uint32_t t = 0; t < log.terms_per_query; ++t) o << ' ' << dgpu::synth::term_text(r[t]);
+        o << '\n';
+    }
+    std::printf("{\"queries\": %u}\n", log.size());
     return 0;
 }
 
@@ -448,7 +496,7 @@ int cmd_kat(const Args& a) {
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        std::fprintf(stderr, "usage: ref_driver index|export|search|kat --key value ...\n");
+        std::fprintf(stderr, "usage: ref_driver index|export|search|kat|spec|queries --key value ...\n");
         return 64;
     }
     std::string cmd = argv[1];
@@ -457,6 +505,8 @@ int main(int argc, char** argv) {
         if (cmd == "index") return cmd_index(a);
         if (cmd == "export") return cmd_export(a);
         if (cmd == "search") return cmd_search(a);
+        if (cmd == "spec") return cmd_spec(a);
+        if (cmd == "queries") return cmd_queries(a);
         if (cmd == "kat") return cmd_kat(a);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "ref_driver %s failed: %s\n", cmd.c_str(), e.what());
