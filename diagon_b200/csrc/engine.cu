@@ -198,6 +198,7 @@ struct dgpu_engine {
     uint32_t batch_filters = 0;                  // range filters of the staged batch
     int lane_ring_entries = 2176;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
     int union_window_docs = 32768;  // docs per window (one bit each in shared memory) of union_topk_kernel
+    uint64_t run_entry_limit = 0xFFFFFFFFull - 4096;   // entries the decode scratch of one batch may hold (32-bit positions)
     int union_max_overlap = 15;     // lane_merge = 3: a query whose expected later sightings exceed this percentage of its
                                     // postings (dense terms on a small index) is merged in registers by staged_merge_topk_kernel
     int pipeline_chunks = 3;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
@@ -398,6 +399,11 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->union_window_docs = static_cast<int>(value);
         return 0;
     }
+    if (!std::strcmp(name, "run_entry_limit")) {   // (tests: makes a batch "too large" without a 100 M-doc index)
+        if (value < 1024 || value > static_cast<int64_t>(0xFFFFFFFFull - 4096)) return fail("run_entry_limit must be in [1024, 2^32 - 4096]");
+        e->run_entry_limit = static_cast<uint64_t>(value);
+        return 0;
+    }
     if (!std::strcmp(name, "union_max_overlap")) {
         if (value < 0 || value > 100000) return fail("union_max_overlap (percent) must be in [0, 100000]");
         e->union_max_overlap = static_cast<int>(value);
@@ -495,6 +501,7 @@ int dgpu_engine_sync_options(dgpu_engine* dst, const dgpu_engine* src) {
     dst->lane_ring_entries = src->lane_ring_entries;
     dst->union_window_docs = src->union_window_docs;
     dst->union_max_overlap = src->union_max_overlap;
+    dst->run_entry_limit = src->run_entry_limit;
     dst->lane_ctas_per_sm = src->lane_ctas_per_sm;
     dst->pool_smem_cap = src->pool_smem_cap;
     dst->pipeline_chunks = src->pipeline_chunks;
@@ -746,7 +753,8 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
                 break;
             }
         }
-        if (run_entries > 0xFFFFFFFFull - 4096) return fail("batch decodes to more than 2^32 postings; split the batch");
+        if (run_entries > e->run_entry_limit)
+            return fail("batch decodes to more than %llu postings; split the batch", static_cast<unsigned long long>(e->run_entry_limit));
         run.base = dterms[slot].out_base;
     }
     lap("terms");

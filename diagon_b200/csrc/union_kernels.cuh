@@ -230,22 +230,24 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                 n_cand += __popc(sm);
             }
         };
-        // every range filter of the query on one doc
-        auto passes = [&](uint32_t doc) -> bool {
-            bool ok;
+        // the range filters of the query on one doc: the first one (the only one, as a rule), the others
+        auto passes_first = [&](uint32_t doc) -> bool {
             if (dv0n) {
                 const int32_t v0 = __ldg(dv0n + doc);
-                ok = v0 >= lo0n && v0 <= hi0n;
-            } else {
-                const int64_t v0 = dv0[doc];
-                ok = v0 >= lo0 && v0 <= hi0;
+                return v0 >= lo0n && v0 <= hi0n;
             }
+            const int64_t v0 = dv0[doc];
+            return v0 >= lo0 && v0 <= hi0;
+        };
+        auto passes_rest = [&](uint32_t doc) -> bool {
+            bool ok = true;
             for (uint32_t f = 1; f < nf && ok; ++f) {
                 const int64_t v = ix.dv[qf[f].column][doc - ix.doc_lo];
                 ok = v >= qf[f].lo && v <= qf[f].hi;
             }
             return ok;
         };
+        auto passes = [&](uint32_t doc) -> bool { return passes_first(doc) && passes_rest(doc); };
 
         for (;;) {
             // ---- window: W docs from the smallest next doc of any clause
@@ -337,12 +339,33 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) lt[j] = (o[j] & b[j]) != 0u;
                             if (FILTER && single_ok) {
+                                // first sightings: a hit if the doc passes the filters. The four gathers of a lane are issued
+                                // together (a value per collected doc, at random: the latency is what costs)
+                                bool nw[4];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    bool nw = in[j] && !lt[j];
-                                    if (nf && nw) nw = passes(dv[j]);
-                                    hits += nw ? 1u : 0u;
+                                for (int j = 0; j < 4; ++j) nw[j] = in[j] && !lt[j];
+                                if (nf) {
+                                    if (dv0n) {
+                                        int32_t v[4];
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) v[j] = nw[j] ? __ldg(dv0n + dv[j]) : 0;
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) nw[j] = nw[j] && v[j] >= lo0n && v[j] <= hi0n;
+                                    } else {
+                                        int64_t v[4];
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) v[j] = nw[j] ? __ldg(dv0 + dv[j]) : 0;
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) nw[j] = nw[j] && v[j] >= lo0 && v[j] <= hi0;
+                                    }
+                                    if (nf > 1) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+                                            if (nw[j]) nw[j] = passes_rest(dv[j]);
+                                    }
                                 }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) hits += nw[j] ? 1u : 0u;
                             }
                             if (any_later) {
                                 // can a doc seen again here be collected? second sighting: this chunk's maximum plus the largest

@@ -700,12 +700,35 @@ static int search_text(IndexSearcher& s, dgpu_comm* comm, const char* text, int6
     return run_compiled(s, batch, k, out_docs, out_scores, out_counts, out_total_hits, comm);
 }
 
+// A batch whose distinct terms decode to more than the engine's scratch can index or the GPU can hold (a 100 M-doc index
+// on one GPU: the engine says "split the batch") is run as two halves, recursively. Not for sharded searches: there the
+// ranks would have to agree on the cut.
+static int search_text_splitting(IndexSearcher& s, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
+                                 float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
+    try {
+        return search_text(s, nullptr, text, text_len, k, out_docs, out_scores, out_counts, out_total_hits, max_queries);
+    } catch (const std::runtime_error& e) {
+        const auto lines = split_lines(text, text_len);
+        if (std::strstr(e.what(), "split the batch") == nullptr || lines.size() < 2) throw;
+        const size_t half = lines.size() / 2;
+        const char* mid = lines[half].first;
+        const int a = search_text_splitting(s, text, mid - text, k, out_docs, out_scores, out_counts, out_total_hits,
+                                            static_cast<int32_t>(half));
+        if (a < 0) return a;
+        const size_t o = static_cast<size_t>(a);
+        const int b = search_text_splitting(s, mid, text + text_len - mid, k, out_docs + o * static_cast<size_t>(k),
+                                            out_scores + o * static_cast<size_t>(k), out_counts + o, out_total_hits + o,
+                                            max_queries - a);
+        return b < 0 ? b : a + b;
+    }
+}
+
 int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
                            float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
     if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }
     try {
-        return search_text(*as_searcher(searcher), nullptr, text, text_len, k, out_docs, out_scores, out_counts, out_total_hits,
-                           max_queries);
+        return search_text_splitting(*as_searcher(searcher), text, text_len, k, out_docs, out_scores, out_counts, out_total_hits,
+                                     max_queries);
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
 

@@ -453,6 +453,31 @@ def test_union_kernel_edge_shapes(readers, g1_dump, window):
             r.set_option(opt, v)
 
 
+def test_oversized_batch_is_split_automatically(readers, golden_dir):
+    """A batch whose distinct terms decode to more postings than the engine's scratch can index is cut in halves by the
+    library (dgpu_search_batch_text), recursively, with the results of the one-call batch. The limit is lowered here so
+    that the golden query file is "too large" several times over; pipelined and not."""
+    r = readers["g1"]
+    s = dg.IndexSearcher(r)
+    text = open(os.path.join(golden_dir, "g1_queries.txt"), "rb").read()
+    want = s.search_batch_text(text, 10)
+    try:
+        for limit, chunks in ((140000, 1), (100000, 1), (100000, 3)):
+            r.set_option("run_entry_limit", limit)
+            r.set_option("pipeline_chunks", chunks)
+            r.set_option("pipeline_min", 1 if chunks > 1 else 2048)
+            got = s.search_batch_text(text, 10)
+            assert np.array_equal(got.docs, want.docs) and np.array_equal(got.scores, want.scores)
+            assert np.array_equal(got.total_hits, want.total_hits) and np.array_equal(got.counts, want.counts)
+        r.set_option("run_entry_limit", 1024)   # not even one query fits: the error comes through
+        with pytest.raises(dg.DiagonError):
+            s.search_batch_text(text, 10)
+    finally:
+        r.set_option("run_entry_limit", 0xFFFFFFFF - 4096)
+        r.set_option("pipeline_chunks", 3)
+        r.set_option("pipeline_min", 2048)
+
+
 def test_staging_compiled_slices_equals_one_call(readers, golden_dir):
     """dgpu_compile_batch_text on slices + dgpu_stage_compiled (how the ranks of a sharded index divide the host work)
     gives the same results as dgpu_search_batch_text on the whole batch."""
