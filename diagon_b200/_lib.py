@@ -112,6 +112,7 @@ PROTOTYPES = {
     "dgpu_sharded_searcher_local": (C.c_void_p, [C.c_void_p]),
     "dgpu_sharded_search_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "dgpu_sharded_search_staged": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dgpu_shm_exchange_selftest": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "dgpu_stage_compiled": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     "dgpu_create_long_range_query": (C.c_void_p, [C.c_char_p, C.c_int64, C.c_int64, C.c_bool, C.c_bool]),
     "dgpu_parse_query": (C.c_void_p, [C.c_char_p]),

@@ -699,8 +699,13 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     // ---- pass 2: the distinct (term, idf, field) of the batch -> runs in the scratch. The first use of a key claims a
     // slot; the same term with another idf / field (a boosted clause) gets a slot of its own. Open addressing over a
     // table that stays in the host's L2, stamped with an epoch instead of being cleared.
-    size_t tcap = 1024;
+    // The table is cut into kParts sub-tables by the top bits of the key's hash; each part is deduplicated by one host
+    // thread (first use of a key in batch order claims the next local slot), then the parts' slots and runs are numbered
+    // one after the other.
+    constexpr uint32_t kParts = 16;
+    size_t tcap = 1024 * kParts;
     while (tcap < 2 * static_cast<size_t>(b->n_terms)) tcap <<= 1;
+    const size_t sub = tcap / kParts;
     if (e->h_table.size() != tcap) {
         e->h_table.assign(tcap, dgpu_engine::TableEntry{0, 0, 0, 0});
         e->epoch = 0;
@@ -709,54 +714,86 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         std::fill(e->h_table.begin(), e->h_table.end(), dgpu_engine::TableEntry{0, 0, 0, 0});
         e->epoch = 1;
     }
-    std::vector<DTerm> dterms;
-    std::vector<DItem> items;
-    dterms.reserve(b->n_terms / 2 + 16);
-    items.reserve(b->n_terms + 16);
-    uint64_t run_entries = kRunPad;  // [0, kRunPad) is the empty run (terms absent on this GPU)
-    // the probes are cache misses into a table of a few MB: hash every key first, then walk with the slot of the key
-    // 16 steps ahead already on its way
-    std::vector<uint32_t> slot_of(b->n_terms);
+    std::vector<uint32_t> slot_of(b->n_terms);     // where the probe of term t starts (index into its sub-table)
+    std::vector<uint8_t> part_of(b->n_terms);
+    std::vector<uint32_t> local_slot(b->n_terms);  // the distinct term of t, numbered inside its part
     dgpu::parallel_for(b->n_terms, n_threads, [&](size_t lo, size_t hi, int) {
         for (size_t t = lo; t < hi; ++t) {
             const dgpu_qterm& qt = b->terms[t];
             uint32_t idf_bits;
             std::memcpy(&idf_bits, &qt.idf, 4);
             const uint64_t key = (static_cast<uint64_t>(qt.term_id) << 32) | idf_bits;
-            slot_of[t] = static_cast<uint32_t>((key * 0x9E3779B97F4A7C15ull) >> 20) & static_cast<uint32_t>(tcap - 1);
+            const uint64_t h = key * 0x9E3779B97F4A7C15ull;
+            part_of[t] = static_cast<uint8_t>(h >> 60);
+            slot_of[t] = static_cast<uint32_t>((h >> 20) & (sub - 1));
         }
     });
-    constexpr uint32_t kAhead = 16;
-    for (uint32_t t = 0; t < b->n_terms; ++t) {
-        if (t + kAhead < b->n_terms) __builtin_prefetch(&e->h_table[slot_of[t + kAhead]], 1, 1);
-        QTermRun& run = qruns[t];
-        if (run.len == 0) continue;   // absent here, or no postings
-        const dgpu_qterm& qt = b->terms[t];
-        uint32_t idf_bits;
-        std::memcpy(&idf_bits, &qt.idf, 4);
-        const uint64_t key = (static_cast<uint64_t>(qt.term_id) << 32) | idf_bits;
-        size_t h = slot_of[t];
-        uint32_t slot = 0xFFFFFFFFu;
-        for (;; h = (h + 1) & (tcap - 1)) {
-            dgpu_engine::TableEntry& te = e->h_table[h];
-            if (te.epoch != e->epoch) {   // free: claim
-                slot = static_cast<uint32_t>(dterms.size());
-                te = dgpu_engine::TableEntry{key, slot, qt.field, e->epoch};
-                const uint32_t nb = run.len / DGPU_BLOCK_POSTINGS;
-                dterms.push_back(DTerm{qt.term_id, qt.idf, qt.field, static_cast<uint32_t>(run_entries), run.pad, nb});
-                for (uint32_t rel = 0; rel < nb; rel += kItemBlocks) items.push_back(DItem{slot, rel});
-                run_entries += (static_cast<uint64_t>(nb) + kPadBlocks) * DGPU_BLOCK_POSTINGS;
-                break;
-            }
-            if (te.key == key && te.field == qt.field) {
-                slot = te.slot;
-                break;
+    static_assert(kParts == 16, "part_of takes the top four bits of the hash");
+    struct Part {
+        std::vector<DTerm> dterms;      // out_base relative to the part's first entry
+        uint64_t entries = 0;
+    };
+    std::vector<Part> parts(kParts);
+    dgpu::parallel_for(kParts, n_threads, [&](size_t p_lo, size_t p_hi, int) {
+        constexpr uint32_t kAhead = 16;   // the probes are cache misses: the slot of a key a few steps ahead is on its way
+        for (size_t p = p_lo; p < p_hi; ++p) {
+            Part& part = parts[p];
+            dgpu_engine::TableEntry* tab = e->h_table.data() + p * sub;
+            part.dterms.reserve(b->n_terms / (2 * kParts) + 16);
+            for (uint32_t t = 0; t < b->n_terms; ++t) {
+                if (t + kAhead < b->n_terms && part_of[t + kAhead] == p) __builtin_prefetch(&tab[slot_of[t + kAhead]], 1, 1);
+                if (part_of[t] != p) continue;
+                const QTermRun& run = qruns[t];
+                if (run.len == 0) continue;   // absent here, or no postings
+                const dgpu_qterm& qt = b->terms[t];
+                uint32_t idf_bits;
+                std::memcpy(&idf_bits, &qt.idf, 4);
+                const uint64_t key = (static_cast<uint64_t>(qt.term_id) << 32) | idf_bits;
+                for (size_t h = slot_of[t];; h = (h + 1) & (sub - 1)) {
+                    dgpu_engine::TableEntry& te = tab[h];
+                    if (te.epoch != e->epoch) {   // free: claim
+                        const uint32_t slot = static_cast<uint32_t>(part.dterms.size());
+                        te = dgpu_engine::TableEntry{key, slot, qt.field, e->epoch};
+                        const uint32_t nb = run.len / DGPU_BLOCK_POSTINGS;
+                        part.dterms.push_back(DTerm{qt.term_id, qt.idf, qt.field, static_cast<uint32_t>(part.entries), run.pad, nb});
+                        part.entries += (static_cast<uint64_t>(nb) + kPadBlocks) * DGPU_BLOCK_POSTINGS;
+                        local_slot[t] = slot;
+                        break;
+                    }
+                    if (te.key == key && te.field == qt.field) {
+                        local_slot[t] = te.slot;
+                        break;
+                    }
+                }
             }
         }
-        if (run_entries > e->run_entry_limit)
-            return fail("batch decodes to more than %llu postings; split the batch", static_cast<unsigned long long>(e->run_entry_limit));
-        run.base = dterms[slot].out_base;
+    });
+    uint64_t run_entries = kRunPad;  // [0, kRunPad) is the empty run (terms absent on this GPU)
+    uint32_t part_slot0[kParts];
+    size_t n_dt = 0;
+    for (uint32_t p = 0; p < kParts; ++p) {
+        part_slot0[p] = static_cast<uint32_t>(n_dt);
+        n_dt += parts[p].dterms.size();
     }
+    std::vector<DTerm> dterms(n_dt);
+    std::vector<DItem> items;
+    items.reserve(n_dt + n_dt / 8 + 16);
+    for (uint32_t p = 0; p < kParts; ++p) {
+        if (run_entries + parts[p].entries > e->run_entry_limit)
+            return fail("batch decodes to more than %llu postings; split the batch", static_cast<unsigned long long>(e->run_entry_limit));
+        for (size_t i = 0; i < parts[p].dterms.size(); ++i) {
+            DTerm dt = parts[p].dterms[i];
+            dt.out_base += static_cast<uint32_t>(run_entries);
+            const uint32_t slot = part_slot0[p] + static_cast<uint32_t>(i);
+            dterms[slot] = dt;
+            for (uint32_t rel = 0; rel < dt.n_blocks; rel += kItemBlocks) items.push_back(DItem{slot, rel});
+        }
+        run_entries += parts[p].entries;
+    }
+    dgpu::parallel_for(b->n_terms, n_threads, [&](size_t lo, size_t hi, int) {
+        for (size_t t = lo; t < hi; ++t)
+            if (qruns[t].len != 0) qruns[t].base = dterms[part_slot0[part_of[t]] + local_slot[t]].out_base;
+    });
     lap("terms");
     e->max_terms = max_terms;
     e->lane_max_terms = lane_max_terms;
@@ -841,7 +878,25 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             keys[i].hi = (cls << 62) | ((127 - cost_class) << 40) | (static_cast<uint64_t>(heavy_term[q]) << 8);
             keys[i].lo = (static_cast<uint64_t>(witems[i].doc_lo) << 32) | i;
         }
-        std::sort(keys.begin(), keys.end());
+        if (n_items < 4096) {
+            std::sort(keys.begin(), keys.end());
+        } else {   // eight slices sorted on the host threads, then merged pairwise
+            constexpr size_t kSlices = 8;
+            dgpu::parallel_for(kSlices, 0, [&](size_t s_lo, size_t s_hi, int) {
+                for (size_t s = s_lo; s < s_hi; ++s)
+                    std::sort(keys.begin() + static_cast<std::ptrdiff_t>(n_items * s / kSlices),
+                              keys.begin() + static_cast<std::ptrdiff_t>(n_items * (s + 1) / kSlices));
+            });
+            for (size_t width = 1; width < kSlices; width *= 2)
+                dgpu::parallel_for(kSlices / (2 * width), 0, [&](size_t m_lo, size_t m_hi, int) {
+                    for (size_t m = m_lo; m < m_hi; ++m) {
+                        const size_t a = 2 * width * m;
+                        std::inplace_merge(keys.begin() + static_cast<std::ptrdiff_t>(n_items * a / kSlices),
+                                           keys.begin() + static_cast<std::ptrdiff_t>(n_items * (a + width) / kSlices),
+                                           keys.begin() + static_cast<std::ptrdiff_t>(n_items * (a + 2 * width) / kSlices));
+                    }
+                });
+        }
         for (uint32_t i = 0; i < n_items; ++i) order[i] = static_cast<uint32_t>(keys[i].lo);
         e->n_and_items = n_and;
         e->n_lane_items = n_lane;

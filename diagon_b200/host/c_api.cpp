@@ -3,6 +3,7 @@
 #include "../../include/diagon_b200_c_api.h"
 
 #include "search.h"
+#include "shm_exchange.h"
 
 #include <bit>
 #include <cstdlib>
@@ -153,6 +154,99 @@ void compile_lines(IndexSearcher& s, const std::vector<LineSpan>& lines, size_t 
     }
 }
 
+// Compiled descriptors as one relocatable blob ("DGPB": counts, queries, terms, filters; slices local to the blob).
+void to_blob(const CompiledBatch& batch, std::vector<uint8_t>& out) {
+    const uint32_t hdr[4] = {0x42504744u, static_cast<uint32_t>(batch.queries.size()), static_cast<uint32_t>(batch.terms.size()),
+                             static_cast<uint32_t>(batch.filters.size())};
+    const size_t nq = batch.queries.size() * sizeof(dgpu_query), nt = batch.terms.size() * sizeof(dgpu_qterm),
+                 nf = batch.filters.size() * sizeof(dgpu_qfilter);
+    out.resize(sizeof hdr + nq + nt + nf);
+    uint8_t* p = out.data();
+    std::memcpy(p, hdr, sizeof hdr); p += sizeof hdr;
+    if (nq) std::memcpy(p, batch.queries.data(), nq);
+    p += nq;
+    if (nt) std::memcpy(p, batch.terms.data(), nt);
+    p += nt;
+    if (nf) std::memcpy(p, batch.filters.data(), nf);
+}
+
+// Appends a blob to a batch (offsets relocated). Throws on a damaged blob.
+void append_blob(CompiledBatch& batch, const uint8_t* blob, uint64_t size) {
+    uint32_t hdr[4];
+    if (size < sizeof hdr) throw std::runtime_error("compiled batch: truncated blob");
+    std::memcpy(hdr, blob, sizeof hdr);
+    const size_t nq = hdr[1] * sizeof(dgpu_query), nt = hdr[2] * sizeof(dgpu_qterm), nf = hdr[3] * sizeof(dgpu_qfilter);
+    if (hdr[0] != 0x42504744u || size < sizeof hdr + nq + nt + nf) throw std::runtime_error("compiled batch: bad blob");
+    const uint8_t* p = blob + sizeof hdr;
+    const uint32_t toff = static_cast<uint32_t>(batch.terms.size()), foff = static_cast<uint32_t>(batch.filters.size());
+    const size_t q0 = batch.queries.size();
+    batch.queries.resize(q0 + hdr[1]);
+    if (nq) std::memcpy(batch.queries.data() + q0, p, nq);
+    p += nq;
+    for (size_t q = q0; q < batch.queries.size(); ++q) {
+        dgpu_query& d = batch.queries[q];
+        if (d.term_begin > d.term_end || d.term_end > hdr[2] || d.filter_begin > d.filter_end || d.filter_end > hdr[3])
+            throw std::runtime_error("compiled batch: bad slice");
+        d.term_begin += toff; d.term_end += toff;
+        d.filter_begin += foff; d.filter_end += foff;
+    }
+    batch.terms.resize(toff + hdr[2]);
+    if (nt) std::memcpy(batch.terms.data() + toff, p, nt);
+    p += nt;
+    batch.filters.resize(foff + hdr[3]);
+    if (nf) std::memcpy(batch.filters.data() + foff, p, nf);
+}
+
+// What a sharded searcher needs besides its local searcher: the communicator of the ONE exchange step and (optional)
+// the shared-memory channel through which the ranks of a box divide the compile work.
+struct ShardContext {
+    dgpu_comm* comm = nullptr;
+    ShmExchange* xch = nullptr;
+    uint64_t* round = nullptr;   // rounds of `xch` used so far (same on every rank)
+};
+
+// compile_lines for a sharded search: every rank compiles 1/world of the lines and the ranks swap the compiled slices
+// through shared memory. Falls back to compiling everything locally when there is no channel or a slice does not fit it
+// (every rank sees the same flag, so they all take the same path).
+void compile_lines_shared(IndexSearcher& s, const ShardContext* sc, const std::vector<LineSpan>& lines, size_t lo, size_t hi,
+                          CompiledBatch& out) {
+    if (!sc || !sc->xch) {
+        compile_lines(s, lines, lo, hi, out);
+        return;
+    }
+    const size_t n = hi - lo, W = static_cast<size_t>(sc->xch->world()), r = static_cast<size_t>(sc->xch->rank());
+    CompiledBatch mine;
+    std::vector<uint8_t> blob;
+    uint64_t publish = 0;
+    std::exception_ptr err;
+    try {
+        compile_lines(s, lines, lo + n * r / W, lo + n * (r + 1) / W, mine);
+        to_blob(mine, blob);
+        publish = blob.size();
+    } catch (...) {
+        err = std::current_exception();
+        publish = ShmExchange::kFailed;
+    }
+    bool too_large = false, failed = false;
+    CompiledBatch all;
+    const bool ok = sc->xch->exchange(++*sc->round, blob.data(), publish, [&](int, const uint8_t* p, uint64_t size) {
+        if (size == ShmExchange::kTooLarge) too_large = true;
+        else if (size == ShmExchange::kFailed) failed = true;
+        else if (!too_large && !failed) append_blob(all, p, size);
+    });
+    if (err) std::rethrow_exception(err);
+    if (!ok) throw std::runtime_error("sharded search: the ranks' compiled slices did not arrive (shared-memory exchange timed out)");
+    if (failed) throw std::runtime_error("sharded search: another rank failed to compile its slice of the batch");
+    if (too_large) {
+        compile_lines(s, lines, lo, hi, out);
+        return;
+    }
+    std::vector<CompiledBatch> one;
+    one.push_back(std::move(all));
+    concat(one, out);
+    out.algorithmic_bytes += mine.algorithmic_bytes;   // (statistics only: this rank's slice)
+}
+
 int run_compiled(IndexSearcher& s, const CompiledBatch& batch, int32_t k, int32_t* out_docs, float* out_scores,
                  int32_t* out_counts, int64_t* out_total_hits, dgpu_comm* comm = nullptr) {
     const size_t n = batch.queries.size();
@@ -206,7 +300,7 @@ int run_batch(IndexSearcher& s, const std::vector<const Query*>& qs, int32_t k, 
 // parses, compiles and stages chunk i + 1 on the other engine. Results are those of the unchunked call (queries are
 // independent; only the sharing of decoded terms between queries shrinks to a chunk).
 int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int chunks, int32_t k, int32_t* out_docs,
-                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits, dgpu_comm* comm = nullptr) {
+                       float* out_scores, int32_t* out_counts, int64_t* out_total_hits, const ShardContext* sc = nullptr) {
     if (k <= 0) throw std::invalid_argument("numHits must be > 0");
     static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
@@ -244,13 +338,13 @@ int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int
             auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
             const double ta = now_ms();
             CompiledBatch batch;
-            compile_lines(s, lines, q0, q1, batch);
+            compile_lines_shared(s, sc, lines, q0, q1, batch);
             const double tb = now_ms();
             fetch(slot);   // the chunk before last ran on this engine: its results leave before its buffers are reused
             const double tc = now_ms();
             dgpu_query_batch view = batch.view();
             if (dgpu_engine_stage_batch(eng[slot], &view, k) != 0 || dgpu_engine_search_staged(eng[slot], nullptr) != 0 ||
-                (comm && dgpu_engine_exchange_topk(eng[slot], comm, nullptr) != 0))   // sharded: the ranks' top k, one all-gather
+                (sc && dgpu_engine_exchange_topk(eng[slot], sc->comm, nullptr) != 0))   // sharded: the ranks' top k, one all-gather
                 throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
             fly[slot] = Inflight{q0, true};
             if (trace)
@@ -679,7 +773,7 @@ int dgpu_search_batch(DiagonIndexSearcher searcher, const DiagonQuery* queries, 
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
 
-static int search_text(IndexSearcher& s, dgpu_comm* comm, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
+static int search_text(IndexSearcher& s, const ShardContext* sc, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
                        float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
     auto tp = std::chrono::steady_clock::now();
     const auto lines = split_lines(text, text_len);
@@ -689,15 +783,15 @@ static int search_text(IndexSearcher& s, dgpu_comm* comm, const char* text, int6
         dgpu_engine_pipeline(e, pl);
         if (pl[0] > 1 && lines.size() >= static_cast<size_t>(pl[1]) && lines.size() >= static_cast<size_t>(pl[0]) &&
             s.getIndexReader().shadow_engine())
-            return run_text_pipelined(s, lines, pl[0], k, out_docs, out_scores, out_counts, out_total_hits, comm);
+            return run_text_pipelined(s, lines, pl[0], k, out_docs, out_scores, out_counts, out_total_hits, sc);
     }
     if (k <= 0) throw std::invalid_argument("numHits must be > 0");
     CompiledBatch batch;
-    compile_lines(s, lines, 0, lines.size(), batch);
+    compile_lines_shared(s, sc, lines, 0, lines.size(), batch);
     if (std::getenv("DGPU_TRACE"))
         std::fprintf(stderr, "[dgpu trace] parse + compile %.3f ms\n",
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count());
-    return run_compiled(s, batch, k, out_docs, out_scores, out_counts, out_total_hits, comm);
+    return run_compiled(s, batch, k, out_docs, out_scores, out_counts, out_total_hits, sc ? sc->comm : nullptr);
 }
 
 // A batch whose distinct terms decode to more than the engine's scratch can index or the GPU can hold (a 100 M-doc index
@@ -737,6 +831,8 @@ namespace {
 struct ShardedSearcher {
     IndexSearcher searcher;
     dgpu_comm* comm = nullptr;
+    std::unique_ptr<ShmExchange> xch;   // null: every rank compiles the whole batch (ranks on different boxes, no /dev/shm)
+    uint64_t round = 0;
     explicit ShardedSearcher(IndexReader& r) : searcher(r) {}
 };
 ShardedSearcher* as_sharded(DgpuShardedSearcher p) { return static_cast<ShardedSearcher*>(p); }
@@ -790,8 +886,32 @@ DgpuShardedSearcher dgpu_sharded_searcher_create(DiagonIndexReader reader, const
                 return nullptr;
             }
         }
+        // the ranks of one box divide the compile work of every batch through shared memory (DGPU_SHARD_COMPILE=0: off)
+        const char* sw = std::getenv("DGPU_SHARD_COMPILE");
+        if (!(sw && sw[0] == '0')) ss->xch = ShmExchange::create(id, rank, world);
         return ss.release();
     } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+// Self-test of the shared-memory channel (no GPU): `rounds` exchanges of patterned slices of varying size between the
+// `world` processes that call it with the same id. 0 = every slice of every round arrived intact.
+int dgpu_shm_exchange_selftest(const uint8_t* id, int32_t rank, int32_t world, int32_t rounds) {
+    if (!id) { set_error("Invalid id"); return -1; }
+    auto x = ShmExchange::create(id, rank, world);
+    if (!x) { set_error("shared memory channel could not be set up"); return -1; }
+    for (int32_t round = 1; round <= rounds; ++round) {
+        auto size_of = [&](int r) { return static_cast<size_t>(1000 + 37 * r + 4099 * ((round * 7 + r) % 11)); };
+        std::vector<uint8_t> mine(size_of(rank));
+        for (size_t i = 0; i < mine.size(); ++i) mine[i] = static_cast<uint8_t>(i * 31 + rank * 7 + round);
+        bool good = true;
+        const bool ok = x->exchange(static_cast<uint64_t>(round), mine.data(), mine.size(), [&](int r, const uint8_t* p, uint64_t n) {
+            if (n != size_of(r)) { good = false; return; }
+            for (size_t i = 0; i < n; ++i)
+                if (p[i] != static_cast<uint8_t>(i * 31 + r * 7 + round)) { good = false; return; }
+        });
+        if (!ok || !good) { set_error("shared memory exchange: slice missing or damaged"); return -1; }
+    }
+    return 0;
 }
 
 void dgpu_sharded_searcher_free(DgpuShardedSearcher s) {
@@ -806,8 +926,9 @@ int dgpu_sharded_search_batch_text(DgpuShardedSearcher s, const char* text, int6
                                    float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries) {
     if (!s || !text) { set_error("Invalid searcher or text"); return -1; }
     try {
-        return search_text(as_sharded(s)->searcher, as_sharded(s)->comm, text, text_len, k, out_docs, out_scores, out_counts,
-                           out_total_hits, max_queries);
+        ShardedSearcher* ss = as_sharded(s);
+        const ShardContext sc{ss->comm, ss->xch.get(), &ss->round};
+        return search_text(ss->searcher, &sc, text, text_len, k, out_docs, out_scores, out_counts, out_total_hits, max_queries);
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
 
@@ -856,18 +977,10 @@ int64_t dgpu_compile_batch_text(DiagonIndexSearcher searcher, const char* text, 
         const auto lines = split_lines(text, text_len);
         CompiledBatch batch;
         compile_lines(*as_searcher(searcher), lines, 0, lines.size(), batch);
-        const uint32_t hdr[4] = {0x42504744u /* "DGPB" */, static_cast<uint32_t>(batch.queries.size()),
-                                 static_cast<uint32_t>(batch.terms.size()), static_cast<uint32_t>(batch.filters.size())};
-        const size_t nq = batch.queries.size() * sizeof(dgpu_query), nt = batch.terms.size() * sizeof(dgpu_qterm),
-                     nf = batch.filters.size() * sizeof(dgpu_qfilter);
-        const int64_t need = static_cast<int64_t>(sizeof hdr + nq + nt + nf);
-        if (out && capacity >= need) {
-            uint8_t* p = out;
-            std::memcpy(p, hdr, sizeof hdr); p += sizeof hdr;
-            std::memcpy(p, batch.queries.data(), nq); p += nq;
-            std::memcpy(p, batch.terms.data(), nt); p += nt;
-            std::memcpy(p, batch.filters.data(), nf);
-        }
+        std::vector<uint8_t> blob;
+        to_blob(batch, blob);
+        const int64_t need = static_cast<int64_t>(blob.size());
+        if (out && capacity >= need) std::memcpy(out, blob.data(), blob.size());
         return need;
     } catch (const std::exception& e) { set_error(e); return -1; }
 }
@@ -877,34 +990,7 @@ int dgpu_stage_compiled(DiagonIndexSearcher searcher, const uint8_t* const* blob
     if (!searcher || !blobs || !sizes) { set_error("Invalid arguments"); return -1; }
     try {
         CompiledBatch batch;
-        for (int32_t i = 0; i < n_blobs; ++i) {
-            uint32_t hdr[4];
-            if (sizes[i] < static_cast<int64_t>(sizeof hdr)) { set_error("compiled batch: truncated blob"); return -1; }
-            std::memcpy(hdr, blobs[i], sizeof hdr);
-            const size_t nq = hdr[1] * sizeof(dgpu_query), nt = hdr[2] * sizeof(dgpu_qterm), nf = hdr[3] * sizeof(dgpu_qfilter);
-            if (hdr[0] != 0x42504744u || sizes[i] < static_cast<int64_t>(sizeof hdr + nq + nt + nf)) {
-                set_error("compiled batch: bad blob");
-                return -1;
-            }
-            const uint8_t* p = blobs[i] + sizeof hdr;
-            const uint32_t toff = static_cast<uint32_t>(batch.terms.size()), foff = static_cast<uint32_t>(batch.filters.size());
-            const size_t q0 = batch.queries.size();
-            batch.queries.resize(q0 + hdr[1]);
-            std::memcpy(batch.queries.data() + q0, p, nq); p += nq;
-            for (size_t q = q0; q < batch.queries.size(); ++q) {
-                dgpu_query& d = batch.queries[q];
-                if (d.term_begin > d.term_end || d.term_end > hdr[2] || d.filter_begin > d.filter_end || d.filter_end > hdr[3]) {
-                    set_error("compiled batch: bad slice");
-                    return -1;
-                }
-                d.term_begin += toff; d.term_end += toff;
-                d.filter_begin += foff; d.filter_end += foff;
-            }
-            batch.terms.resize(toff + hdr[2]);
-            std::memcpy(batch.terms.data() + toff, p, nt); p += nt;
-            batch.filters.resize(foff + hdr[3]);
-            std::memcpy(batch.filters.data() + foff, p, nf);
-        }
+        for (int32_t i = 0; i < n_blobs; ++i) append_blob(batch, blobs[i], static_cast<uint64_t>(std::max<int64_t>(sizes[i], 0)));
         dgpu_query_batch view = batch.view();
         auto* rd = &as_searcher(searcher)->getIndexReader();
         if (!rd->engine()) { set_error("host-only reader: no GPU engine, and there is no CPU fallback"); return -1; }

@@ -195,6 +195,10 @@ DiagonIndexSearcher dgpu_sharded_searcher_local(DgpuShardedSearcher s);
 int dgpu_sharded_search_batch_text(DgpuShardedSearcher s, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
                                    float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries);
 int dgpu_sharded_search_staged(DgpuShardedSearcher s, void* stream);
+/* The ranks of one box also divide the parse + compile work of every batch: each compiles 1/world of the lines and the
+ * compiled descriptors are swapped through POSIX shared memory (host plumbing, no collective; DGPU_SHARD_COMPILE=0 turns
+ * it off and every rank compiles the whole batch). dgpu_shm_exchange_selftest exercises that channel without a GPU. */
+int dgpu_shm_exchange_selftest(const uint8_t* id /* [128] */, int32_t rank, int32_t world, int32_t rounds);
 
 /* Sharded indexes: the host work of a batch can be divided between the ranks. dgpu_compile_batch_text parses and
  * compiles a slice of a batch into a relocatable blob WITHOUT touching the device (returns the bytes needed; writes

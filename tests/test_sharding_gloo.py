@@ -143,3 +143,31 @@ def test_two_rank_statistics_exchange_and_topk_merge(tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+def _shm_worker(rank, world, uid, q):
+    from diagon_b200 import _lib
+    import ctypes as C
+
+    buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+    rc = _lib.load().dgpu_shm_exchange_selftest(C.addressof(buf), rank, world, 50)
+    q.put((rank, rc, _lib.last_error() if rc else ""))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_memory_compile_exchange(world):
+    """The channel through which the ranks of one box swap the compiled slices of a batch (diagon_b200/host/shm_exchange.h):
+    `world` processes, 50 rounds of patterned slices of varying size, double-buffered; every slice must arrive intact."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    uid = bytes((i * 37 + 11 * world) & 0xFF for i in range(128))
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shm_worker, args=(r, world, uid, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(r for r, _, _ in got) == list(range(world))
+    assert all(rc == 0 for _, rc, _ in got), got
