@@ -106,6 +106,7 @@ PROTOTYPES = {
     "dgpu_comm_world": (C.c_int, [C.c_void_p]),
     "dgpu_comm_allreduce_sum_i64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "dgpu_engine_exchange_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dgpu_search_after": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float]),
     "dgpu_sharded_unique_id": (C.c_int, [C.c_void_p]),
     "dgpu_sharded_searcher_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "dgpu_sharded_searcher_free": (None, [C.c_void_p]),

@@ -417,6 +417,25 @@ class IndexSearcher:
         finally:
             lib.diagon_free_top_docs(td)
 
+    def search_after(self, after: ScoreDoc, query: Query, num_hits: int) -> TopDocs:
+        """TopScoreDocCollector::create(numHits, after) + IndexSearcher::search(query, collector)."""
+        lib = _lib.load()
+        td = lib.dgpu_search_after(self._ptr, query._handle(), num_hits, after.doc, after.score)
+        if not td:
+            msg = _lib.last_error()
+            if "numHits" in msg or "not supported" in msg:
+                raise ValueError(msg)
+            raise DiagonError(msg)
+        try:
+            n = lib.diagon_top_docs_score_docs_length(td)
+            sds = []
+            for i in range(n):
+                sd = lib.diagon_top_docs_score_doc_at(td, i)
+                sds.append(ScoreDoc(lib.diagon_score_doc_get_doc(sd), lib.diagon_score_doc_get_score(sd)))
+            return TopDocs(TotalHits(lib.diagon_top_docs_total_hits(td)), sds, lib.diagon_top_docs_max_score(td))
+        finally:
+            lib.diagon_free_top_docs(td)
+
     def count(self, query: Query) -> int:
         c = _lib.load().diagon_count(self._ptr, query._handle())
         if c < 0:

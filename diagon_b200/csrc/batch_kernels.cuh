@@ -616,7 +616,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
                     const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
                     const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
                     // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
-                    const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+                    const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u && doc >= qd.after_plus1;
                     if (NEED_CNT || nf) hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
                     const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
                     if (pm) {
@@ -774,7 +774,7 @@ intersect_topk_kernel(DeviceIndex ix, AccumParams P) {
             const uint32_t sb = __float_as_uint(score);
             const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
             const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - d);
-            const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+            const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u && d >= qd.after_plus1;
             hits += __popc(__ballot_sync(0xFFFFFFFFu, match));
             const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
             if (pm) {
@@ -961,7 +961,7 @@ lane_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
             const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - m);
             // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
-            const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+            const bool push = match && key > thresh && (sb & 0x7F800000u) != 0x7F800000u && m >= qd.after_plus1;
             const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
             if (pm) {
                 if (n_cand + 32u > P.cand_cap) prune();
@@ -1280,7 +1280,7 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
                 const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
                 // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
-                const bool push = maybe && key > thresh && (sb & 0x7F800000u) != 0x7F800000u;
+                const bool push = maybe && key > thresh && (sb & 0x7F800000u) != 0x7F800000u && doc >= qd.after_plus1;
                 if (n_cand + 32u > P.cand_cap) prune();
                 const bool still = push && key > thresh;   // the prune may have raised the threshold
                 const uint32_t sm = __ballot_sync(0xFFFFFFFFu, still);

@@ -331,7 +331,7 @@ search_kernel(DeviceIndex ix, SearchParams P) {
                     const uint32_t sb = __float_as_uint(score);
                     const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
                     // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:171-174)
-                    if (ord >= thresh_hi && (sb & 0x7F800000u) != 0x7F800000u) {
+                    if (ord >= thresh_hi && (sb & 0x7F800000u) != 0x7F800000u && doc >= qd.after_plus1) {
                         const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
                         if (key > thresh) {
                             const uint32_t pos = atomicAdd(&s_cand, 1u);

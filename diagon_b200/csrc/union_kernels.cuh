@@ -59,6 +59,7 @@ __host__ __device__ inline size_t union_warp_smem_bytes(uint32_t window_docs, ui
     size_t b = window_docs / 8;                                  // seen bitmap
     b += sizeof(uint32_t) * kUnionFilterWords;                   // hashed filter of the docs seen twice
     b += sizeof(uint32_t) * 32;                                  // one word per lane for the atomics of entries outside the window
+    b += 16;                                                     // the item's searchAfter bound (read on the collect path only)
     b += 2 * sizeof(uint32_t) * kUnionRecords;                   // records: doc, meta
     b += cap_smem ? sizeof(uint64_t) * cap_smem                  // candidate pool in shared memory, or
                   : sizeof(uint32_t) * 256;                      // the digit histogram of warp_select_topk
@@ -98,6 +99,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
     const uint32_t idle_s = static_cast<uint32_t>(__cvta_generic_to_shared(sp)) + 4u * lane;
     reinterpret_cast<uint32_t*>(sp)[lane] = 0u;
     sp += sizeof(uint32_t) * 32;
+    volatile uint32_t* after_p = reinterpret_cast<volatile uint32_t*>(sp);
+    sp += 16;
     uint32_t* rec_doc = reinterpret_cast<uint32_t*>(sp);
     uint32_t* rec_meta = rec_doc + kUnionRecords;
     sp += 2 * sizeof(uint32_t) * kUnionRecords;
@@ -143,6 +146,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
             }
         }
         const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
+        if (lane == 0) *after_p = qd.after_plus1;
+        __syncwarp();
         DGPU_ASSERT(nt <= 32u);
         const bool mine = static_cast<uint32_t>(lane) < nt;
 
@@ -215,7 +220,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         auto collect = [&](uint32_t doc, float score, bool match) {
             // quick test on the score alone: a superset of "key > thresh" (ties and -0.0f are settled by the key
             // compare below; a NaN score fails it, and NaN is never collected)
-            const bool maybe = match && score >= thresh_f;
+            const bool maybe = match && score >= thresh_f && doc >= *after_p;   // (searchAfter: a filter on the doc id)
             const uint32_t pm = __ballot_sync(0xFFFFFFFFu, maybe);
             if (pm) {
                 const uint32_t sb = __float_as_uint(score);

@@ -429,6 +429,18 @@ DiagonTopDocs diagon_search(DiagonIndexSearcher searcher, DiagonQuery query, int
     } catch (const std::exception& e) { set_error(e); return nullptr; }
 }
 
+// Pagination as the reference spells it: TopScoreDocCollector::create(numHits, after) + IndexSearcher::search(query, collector)
+// (TopScoreDocCollector.h:69, IndexSearcher.h:255; the filter: TopScoreDocCollector.cpp:176-187). The reference's C bridge
+// has no entry point for it; this is what one would look like.
+DiagonTopDocs dgpu_search_after(DiagonIndexSearcher searcher, DiagonQuery query, int32_t num_hits, int32_t after_doc, float after_score) {
+    if (!searcher || !query) { set_error("Invalid searcher or query"); return nullptr; }
+    try {
+        auto collector = TopScoreDocCollector::create(num_hits, ScoreDoc(after_doc, after_score));
+        as_searcher(searcher)->search(*as_query(query), collector.get());
+        return new TopDocs(collector->topDocs());
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
 int diagon_count(DiagonIndexSearcher searcher, DiagonQuery query) {
     if (!searcher || !query) { set_error("Invalid searcher or query"); return -1; }
     try {
@@ -954,13 +966,57 @@ int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_
         auto guard = rd->lock_engines();
         if (dgpu_engine_stage_batch(rd->engine(), &view, k) != 0) { set_error(dgpu_engine_last_error()); return -1; }
         if (out_stats) {
-            out_stats[0] = static_cast<int64_t>(batch.queries.size());
-            out_stats[1] = static_cast<int64_t>(batch.algorithmic_bytes);
-            int64_t postings = 0;
+            // Algorithmic bytes: every block of every term of a disjunction; of a pure conjunction
+            // only the blocks that can hold a candidate - those of the shortest list, and of the other lists the blocks
+            // whose [first, last] doc range meets a block of the shortest list. A block costs its payload + its 16-byte
+            // skip row. Postings are counted over the same blocks.
             auto& im = rd->index().image;
-            for (auto& t : batch.terms)
-                for (uint32_t b = im.term_block_start[t.term_id]; b < im.term_block_start[t.term_id + 1]; ++b)
-                    postings += (im.block_meta[b] & 0xFF) + 1;
+            std::vector<int64_t> q_bytes(batch.queries.size(), 0), q_postings(batch.queries.size(), 0);
+            parallel_for(batch.queries.size(), batch.queries.size() < 256 ? 1 : 0, [&](size_t q_lo, size_t q_hi, int) {
+                auto block_bytes = [&](uint32_t b) { return 16ll * (im.block_data_off[b + 1] - im.block_data_off[b]) + 16ll; };
+                for (size_t q = q_lo; q < q_hi; ++q) {
+                    const dgpu_query& d = batch.queries[q];
+                    const uint32_t nt = d.term_end - d.term_begin;
+                    bool conj = nt >= 2 && d.n_must == nt;
+                    for (uint32_t t = d.term_begin; conj && t < d.term_end; ++t) conj = batch.terms[t].role == DGPU_ROLE_MUST;
+                    uint32_t lead = d.term_begin;
+                    if (conj)
+                        for (uint32_t t = d.term_begin; t < d.term_end; ++t) {
+                            auto nb = [&](uint32_t x) { return im.term_block_start[batch.terms[x].term_id + 1] - im.term_block_start[batch.terms[x].term_id]; };
+                            if (nb(t) < nb(lead)) lead = t;
+                        }
+                    int64_t bytes = 0, postings = 0;
+                    for (uint32_t t = d.term_begin; t < d.term_end; ++t) {
+                        const uint32_t b0 = im.term_block_start[batch.terms[t].term_id], b1 = im.term_block_start[batch.terms[t].term_id + 1];
+                        if (!conj || t == lead) {
+                            for (uint32_t b = b0; b < b1; ++b) {
+                                bytes += block_bytes(b);
+                                postings += (im.block_meta[b] & 0xFF) + 1;
+                            }
+                            continue;
+                        }
+                        // both block lists ascend: walk them together
+                        uint32_t l = im.term_block_start[batch.terms[lead].term_id];
+                        const uint32_t l1 = im.term_block_start[batch.terms[lead].term_id + 1];
+                        for (uint32_t b = b0; b < b1; ++b) {
+                            while (l < l1 && im.block_last_doc[l] < im.block_first_doc[b]) ++l;
+                            if (l < l1 && im.block_first_doc[l] <= im.block_last_doc[b]) {
+                                bytes += block_bytes(b);
+                                postings += (im.block_meta[b] & 0xFF) + 1;
+                            }
+                        }
+                    }
+                    q_bytes[q] = bytes;
+                    q_postings[q] = postings;
+                }
+            });
+            int64_t bytes = 0, postings = 0;
+            for (size_t q = 0; q < batch.queries.size(); ++q) {
+                bytes += q_bytes[q];
+                postings += q_postings[q];
+            }
+            out_stats[0] = static_cast<int64_t>(batch.queries.size());
+            out_stats[1] = bytes;
             out_stats[2] = postings;
         }
         return static_cast<int>(batch.queries.size());

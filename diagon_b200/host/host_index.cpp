@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <sstream>
 #include <stdexcept>
 #include <thread>
 
@@ -303,7 +304,7 @@ void assemble_image(HostIndex& ix, uint32_t n_terms, int threads,
             docs.clear();
             freqs.clear();
             const int8_t* norms = fetch(static_cast<uint32_t>(t), docs, freqs);
-            encode_postings(docs.data(), freqs.data(), docs.size(), norms, im.doc_lo, enc[t]);
+            encode_postings(docs.data(), freqs.data(), docs.size(), norms, im.doc_lo, im.doc_hi, enc[t]);
             enc[t].data.shrink_to_fit();
         }
     });
@@ -408,6 +409,12 @@ void IndexBuilder::add_term(int seg, const std::string& field, const uint8_t* te
     if (docs && doc_freq > 0) {
         if (!ix.segments.at(static_cast<size_t>(seg)).is_local)
             throw std::invalid_argument("postings given for a remote segment");
+        // a damaged source must end in an error, not in a posting outside its segment or a doc listed twice
+        const int32_t seg_docs = ix.segments[static_cast<size_t>(seg)].max_doc;
+        for (int32_t i = 0; i < doc_freq; ++i) {
+            if (docs[i] < 0 || docs[i] >= seg_docs) throw std::invalid_argument("posting outside its segment (doc >= maxDoc)");
+            if (i && docs[i] <= docs[i - 1]) throw std::invalid_argument("postings of a term are not in strictly ascending doc order");
+        }
         Impl::Run r;
         r.seg = seg;
         r.docs.assign(docs, docs + doc_freq);
@@ -426,8 +433,12 @@ void IndexBuilder::add_numeric_doc_values(int seg, const std::string& name, cons
         id = static_cast<int>(ix.dv_names.size() - 1);
         for (auto& d : impl_->dv) d.resize(ix.dv_names.size());
     }
+    if (!values) return;   // a remote segment: the column is registered (same ids on every rank), its values live elsewhere
     int32_t n = ix.segments.at(static_cast<size_t>(seg)).max_doc;
-    impl_->dv[static_cast<size_t>(seg)][static_cast<size_t>(id)].assign(values, values + n);
+    auto& col = impl_->dv[static_cast<size_t>(seg)][static_cast<size_t>(id)];
+    col.assign(values, values + n);
+    for (int64_t& v : col)
+        if (v == HostIndex::kDvMissing) v = HostIndex::kDvMissing + 1;   // (the reserved value itself cannot be stored: see HostIndex::kDvMissing)
 }
 
 std::shared_ptr<HostIndex> IndexBuilder::finish(int threads) {
@@ -458,10 +469,12 @@ std::shared_ptr<HostIndex> IndexBuilder::finish(int threads) {
                         impl_->norms[s][f].data(), impl_->norms[s][f].size());
         }
     }
-    // doc values over the local range (missing => 0, NumericDocValuesReader.cpp:104-118)
+    // doc values over the local range. A doc without a value inside a segment that has the column reads 0
+    // (NumericDocValuesReader.cpp:104-118); a segment WITHOUT the column gives a range query no scorer at all
+    // (NumericRangeQuery.cpp:225-228): its docs hold the reserved value no compiled range contains
     ix.image.dv.assign(ix.dv_names.size(), {});
     for (size_t d = 0; d < ix.dv_names.size(); ++d) {
-        ix.image.dv[d].assign(hi - lo, 0);
+        ix.image.dv[d].assign(hi - lo, HostIndex::kDvMissing);
         for (size_t s = 0; s < ix.segments.size(); ++s) {
             if (!ix.segments[s].is_local || impl_->dv[s].size() <= d || impl_->dv[s][d].empty()) continue;
             std::memcpy(ix.image.dv[d].data() + (static_cast<uint32_t>(ix.segments[s].doc_base) - lo),
@@ -874,12 +887,26 @@ uint64_t HostIndex::image_hash() const {
     return h;
 }
 
+// Hash of the file body (everything after magic, version and the hash itself): FNV-1a over 64-bit words, so that a
+// gigabyte image is checked in a fraction of a second. EVERY byte the loader parses is covered: dictionary, statistics,
+// segment table, names as well as the uploaded arrays.
+static uint64_t body_hash(const uint8_t* p, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x100000001b3ull;
+        h ^= h >> 29;
+    }
+    for (; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+
 void HostIndex::save_image(const std::string& path) const {
-    std::ofstream out(path, std::ios::binary | std::ios::trunc);
-    if (!out) throw std::runtime_error("cannot write " + path);
-    out.write(kImageMagic, 8);
-    img_put_pod<uint32_t>(out, 1u);   // version
-    img_put_pod<uint64_t>(out, image_hash());
+    std::ofstream file(path, std::ios::binary | std::ios::trunc);
+    if (!file) throw std::runtime_error("cannot write " + path);
+    std::ostringstream out(std::ios::binary);
     img_put_pod<uint32_t>(out, static_cast<uint32_t>(fields.size()));
     for (const auto& f : fields) img_put_str(out, f);
     img_put_pod<uint32_t>(out, static_cast<uint32_t>(dv_names.size()));
@@ -915,8 +942,13 @@ void HostIndex::save_image(const std::string& path) const {
     img_put_vec(out, image.ktab);
     img_put_pod<uint32_t>(out, static_cast<uint32_t>(image.dv.size()));
     for (const auto& c : image.dv) img_put_vec(out, c);
-    out.flush();
-    if (!out) throw std::runtime_error("short write to " + path);
+    const std::string body = out.str();
+    file.write(kImageMagic, 8);
+    img_put_pod<uint32_t>(file, 2u);   // version
+    img_put_pod<uint64_t>(file, body_hash(reinterpret_cast<const uint8_t*>(body.data()), body.size()));
+    file.write(body.data(), static_cast<std::streamsize>(body.size()));
+    file.flush();
+    if (!file) throw std::runtime_error("short write to " + path);
 }
 
 std::shared_ptr<HostIndex> HostIndex::load_image(const std::string& path) {
@@ -932,8 +964,9 @@ std::shared_ptr<HostIndex> HostIndex::load_image(const std::string& path) {
     const uint8_t* end = p + buf.size();
     if (std::memcmp(p, kImageMagic, 8) != 0) bad_image("not a DGPUIMG1 file");
     p += 8;
-    if (img_get_pod<uint32_t>(p, end) != 1u) bad_image("unsupported version");
+    if (img_get_pod<uint32_t>(p, end) != 2u) bad_image("unsupported version");
     const uint64_t want_hash = img_get_pod<uint64_t>(p, end);
+    if (body_hash(p, static_cast<size_t>(end - p)) != want_hash) bad_image("content hash mismatch");
     auto ix = std::make_shared<HostIndex>();
     const uint32_t nf = img_get_pod<uint32_t>(p, end);
     if (nf > 65535) bad_image("field count");
@@ -1000,7 +1033,10 @@ std::shared_ptr<HostIndex> HostIndex::load_image(const std::string& path) {
     for (const auto& c : im.dv)
         if (c.size() != static_cast<size_t>(im.doc_hi - im.doc_lo)) bad_image("doc-values column length");
     if (!ix->global_sum_ttf_override_.empty() && ix->global_sum_ttf_override_.size() != nf) bad_image("statistics overrides");
-    if (ix->image_hash() != want_hash) bad_image("content hash mismatch");
+    if (im.term_bytes.size() != n_terms) bad_image("encoded sizes disagree with the dictionary");
+    for (size_t t = 0; t < n_terms; ++t)
+        if (ix->dict.term_field(static_cast<uint32_t>(t)) >= nf) bad_image("dictionary names an unknown field");
+    ix->stats_changed();
     return ix;
 }
 

@@ -15,6 +15,7 @@
 #include "synth_corpus.h"
 
 #include <atomic>
+#include <limits>
 #include <cstdint>
 #include <mutex>
 #include <iosfwd>
@@ -82,6 +83,11 @@ public:
 
     int field_id(const std::string& name) const;
     int dv_id(const std::string& name) const;
+    // The value the docs of a local segment WITHOUT a doc-values column hold in the dense device column: no compiled
+    // range contains it (query compilation raises a lower bound of INT64_MIN by one), so such docs never pass a filter -
+    // the reference gives the range clause no scorer there (NumericRangeQuery.cpp:225-228). A stored value of exactly
+    // INT64_MIN is kept as INT64_MIN + 1, which no range tells apart from it once the bound is raised.
+    static constexpr int64_t kDvMissing = std::numeric_limits<int64_t>::min();
 
     // Statistics exactly as TermWeight::createScorer derives them (TermQuery.cpp:184-260).
     float avg_field_length(int field) const;

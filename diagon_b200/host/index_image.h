@@ -41,9 +41,15 @@ inline uint32_t svb_len(uint32_t v) { return v < (1u << 8) ? 1 : v < (1u << 16) 
 // norms: indexed by (global doc - doc_lo); nullptr => the field has no norms, norm = 1
 // (TermQuery.cpp:78). Throws when a norm byte is outside [0,127] — the reference's encoder
 // (DocumentsWriterPerThread.cpp:465-481) cannot produce one and the 128-entry k table relies on it.
+// Doc ids must lie in [doc_lo, doc_hi) and ascend strictly: a duplicate or a doc outside the shard would break what the
+// kernels rely on (distinct docs per list, every doc inside the window arithmetic) and is refused here.
 inline void encode_postings(const uint32_t* docs, const uint32_t* freqs, size_t n, const int8_t* norms,
-                            uint32_t doc_lo, EncodedList& out) {
+                            uint32_t doc_lo, uint32_t doc_hi, EncodedList& out) {
     out.clear();
+    for (size_t i = 0; i < n; ++i) {
+        if (docs[i] < doc_lo || docs[i] >= doc_hi) throw std::runtime_error("posting outside the doc range of its index");
+        if (i && docs[i] <= docs[i - 1]) throw std::runtime_error("postings of a term are not in strictly ascending doc order");
+    }
     uint32_t dv[DGPU_BLOCK_POSTINGS], fv[DGPU_BLOCK_POSTINGS];
     for (size_t base = 0; base < n; base += DGPU_BLOCK_POSTINGS) {
         uint32_t cnt = static_cast<uint32_t>(n - base < DGPU_BLOCK_POSTINGS ? n - base : DGPU_BLOCK_POSTINGS);

@@ -124,6 +124,7 @@ struct Compiler {
             if (f.hi == std::numeric_limits<int64_t>::min()) empty = true; else f.hi -= 1;
         }
         if (empty) { f.lo = 1; f.hi = 0; }
+        if (f.lo == HostIndex::kDvMissing) f.lo += 1;   // the value of "this segment has no such column" is outside every range
         out.filters.push_back(f);
         return true;
     }
@@ -343,7 +344,7 @@ bool IndexSearcher::compile_text_line(const char* p, const char* end, CompiledBa
             } else {
                 dgpu_qfilter f{};
                 f.column = dv;
-                f.lo = lo;
+                f.lo = lo == HostIndex::kDvMissing ? lo + 1 : lo;   // (as Compiler::add_range)
                 f.hi = hi;
                 out.filters.push_back(f);
             }
@@ -384,11 +385,15 @@ bool IndexSearcher::compile_text_line(const char* p, const char* end, CompiledBa
 }
 
 // ------------------------------------------------------------------ search
-std::vector<TopDocs> IndexSearcher::search(const std::vector<const Query*>& queries, int numHits) {
+std::vector<TopDocs> IndexSearcher::search(const std::vector<const Query*>& queries, int numHits, const std::vector<int>* after_docs) {
     if (numHits <= 0) throw std::invalid_argument("numHits must be > 0");  // TopScoreDocCollector.cpp:49-51
     if (numHits > DGPU_MAX_K) throw std::invalid_argument("numHits exceeds DGPU_MAX_K");
+    if (after_docs && after_docs->size() != queries.size()) throw std::invalid_argument("one `after` doc per query");
     CompiledBatch batch;
     for (const Query* q : queries) compile(*q, batch);
+    if (after_docs)   // TopScoreDocCollector.cpp:176-187: docs up to and including after.doc are not collected
+        for (size_t q = 0; q < queries.size(); ++q)
+            if ((*after_docs)[q] >= 0) batch.queries[q].after_plus1 = static_cast<uint32_t>((*after_docs)[q]) + 1u;
     auto guard = reader_.lock_engines();
     size_t n = queries.size();
     std::vector<uint64_t> keys(n * static_cast<size_t>(numHits));
@@ -423,6 +428,20 @@ TopDocs IndexSearcher::search(const Query& query, int numHits) {
 
 TopDocs IndexSearcher::search(const Query& query, int numHits, int /*totalHitsThreshold*/) {
     return search(query, numHits);  // always exact
+}
+
+void IndexSearcher::search(const Query& query, Collector* collector) {
+    auto* top = dynamic_cast<TopScoreDocCollector*>(collector);
+    if (!top) throw std::invalid_argument("only TopScoreDocCollector is supported by the GPU engine (no CPU fallback for per-hit collectors)");
+    std::vector<const Query*> one{&query};
+    std::vector<int> after{top->hasAfter() ? top->after().doc : -1};
+    top->setResult(std::move(search(one, top->numHits(), &after)[0]));
+}
+
+TopDocs IndexSearcher::searchAfter(const ScoreDoc& after, const Query& query, int numHits) {
+    auto c = TopScoreDocCollector::create(numHits, after);
+    search(query, c.get());
+    return c->topDocs();
 }
 
 int IndexSearcher::count(const Query& query) { return static_cast<int>(search(query, 1).totalHits.value); }

@@ -57,6 +57,50 @@ struct TopDocs {
     }
 };
 
+// ---- Collector.h:37-55 / TopScoreDocCollector.h:40-179. The engine collects on the GPU, so the only Collector
+// IndexSearcher::search(query, collector) accepts is TopScoreDocCollector (a collector with a per-hit callback would need
+// every hit streamed back to the host: unsupported, there is no CPU path). `create(numHits, after)` is the reference's
+// pagination: its leaf collector drops every doc whose id is not above after.doc before it looks at the queue
+// (TopScoreDocCollector.cpp:176-187), and counts it as a hit all the same (:165-168).
+class Collector {
+public:
+    virtual ~Collector() = default;
+};
+
+class TopScoreDocCollector : public Collector {
+public:
+    static std::unique_ptr<TopScoreDocCollector> create(int numHits) {
+        return std::unique_ptr<TopScoreDocCollector>(new TopScoreDocCollector(numHits, false, ScoreDoc()));
+    }
+    static std::unique_ptr<TopScoreDocCollector> create(int numHits, int /*totalHitsThreshold*/) { return create(numHits); }  // always exact
+    static std::unique_ptr<TopScoreDocCollector> create(int numHits, const ScoreDoc& after) {
+        return std::unique_ptr<TopScoreDocCollector>(new TopScoreDocCollector(numHits, true, after));
+    }
+    TopDocs topDocs() { return topDocs(0, numHits_); }
+    TopDocs topDocs(int start, int howMany) {   // TopScoreDocCollector.cpp:63-101
+        if (start < 0 || howMany < 0) throw std::invalid_argument("start and howMany must be >= 0");
+        std::vector<ScoreDoc> docs;
+        if (start < static_cast<int>(result_.scoreDocs.size())) {
+            const int end = std::min(start + howMany, static_cast<int>(result_.scoreDocs.size()));
+            docs.assign(result_.scoreDocs.begin() + start, result_.scoreDocs.begin() + end);
+        }
+        return TopDocs(result_.totalHits, std::move(docs));
+    }
+    int numHits() const { return numHits_; }
+    bool hasAfter() const { return hasAfter_; }
+    const ScoreDoc& after() const { return after_; }
+    void setResult(TopDocs r) { result_ = std::move(r); }
+
+private:
+    TopScoreDocCollector(int numHits, bool hasAfter, const ScoreDoc& after) : numHits_(numHits), hasAfter_(hasAfter), after_(after) {
+        if (numHits <= 0) throw std::invalid_argument("numHits must be > 0");   // TopScoreDocCollector.cpp:49-51
+    }
+    int numHits_;
+    bool hasAfter_;
+    ScoreDoc after_;
+    TopDocs result_;
+};
+
 // ---- BooleanClause.h:20-50
 enum class Occur : uint8_t { MUST = 0, SHOULD = 1, MUST_NOT = 2, FILTER = 3 };
 
@@ -227,8 +271,13 @@ public:
     // (TopScoreDocCollector.cpp:49-51) and for unsupported query shapes.
     TopDocs search(const Query& query, int numHits);
     TopDocs search(const Query& query, int numHits, int totalHitsThreshold);
-    // Batched form: one engine call for all queries.
-    std::vector<TopDocs> search(const std::vector<const Query*>& queries, int numHits);
+    // IndexSearcher.h:255. Only TopScoreDocCollector (with or without `after`); results through collector->topDocs().
+    void search(const Query& query, Collector* collector);
+    // IndexSearcher::searchAfter of Lucene, spelled with the reference's collector: the best numHits docs among those the
+    // collector created with `after` lets through; totalHits counts every hit.
+    TopDocs searchAfter(const ScoreDoc& after, const Query& query, int numHits);
+    // Batched form: one engine call for all queries. after_docs (optional, one per query, -1 = none): searchAfter.
+    std::vector<TopDocs> search(const std::vector<const Query*>& queries, int numHits, const std::vector<int>* after_docs = nullptr);
     // IndexSearcher.cpp:113-141
     int count(const Query& query);
 

@@ -556,7 +556,10 @@ bool read_norms(SegmentFiles& files, int32_t field_number, int32_t max_doc, std:
 }
 
 // NumericDocValuesReader.cpp:25-58, :104-118: dense big-endian int64 per doc.
-void read_numeric_doc_values(SegmentFiles& files, int32_t max_doc, std::map<std::string, std::vector<int64_t>>& out) {
+// names_only: the columns of a segment that lives on another GPU (its values are not read, but the column ids must be
+// the same on every rank: a compiled filter names a column by id)
+void read_numeric_doc_values(SegmentFiles& files, int32_t max_doc, std::map<std::string, std::vector<int64_t>>& out,
+                             bool names_only = false) {
     In meta, data;
     if (!files.open(".dvm", meta, ".dvm") || !files.open(".dvd", data, ".dvd")) return;
     if (meta.str() != "DiagonDocValues") corrupt("bad .dvm header");
@@ -570,6 +573,10 @@ void read_numeric_doc_values(SegmentFiles& files, int32_t max_doc, std::map<std:
         meta.vlong();  // length
         meta.be64();   // min
         meta.be64();   // max
+        if (names_only) {
+            out[name];
+            continue;
+        }
         std::vector<int64_t> v(static_cast<size_t>(std::max<int64_t>(num_docs, max_doc)), 0);
         data.seek(off);
         for (uint32_t d = 0; d < num_docs; ++d) v[d] = static_cast<int64_t>(data.be64());
@@ -629,10 +636,10 @@ std::shared_ptr<HostIndex> load_index_directory(const std::string& dir, int seg_
                 if (seen != num_terms) corrupt("term count of field " + field + " in " + s.name + " disagrees with its .tip header");
             }
         }
-        if (local) {
+        {
             std::map<std::string, std::vector<int64_t>> dvs;
-            read_numeric_doc_values(files, s.max_doc, dvs);
-            for (auto& kv : dvs) b.add_numeric_doc_values(seg, kv.first, kv.second.data());
+            read_numeric_doc_values(files, s.max_doc, dvs, !local);
+            for (auto& kv : dvs) b.add_numeric_doc_values(seg, kv.first, local ? kv.second.data() : nullptr);
         }
     }
     return b.finish(threads);

@@ -67,6 +67,8 @@ typedef struct {
     uint16_t min_should_match;     /* SHOULD terms that must match (>= 1 when only SHOULD terms) */
     uint8_t n_must;                /* number of DGPU_ROLE_MUST terms (all must match) */
     uint8_t flags;                 /* reserved */
+    uint32_t after_plus1;          /* searchAfter: only docs >= this are collected (0 = every doc); hits count all docs
+                                      (TopScoreDocCollector.cpp:154-187: the collector's pagination filter is on the doc id) */
 } dgpu_query;
 
 #define DGPU_ROLE_SHOULD 0

@@ -175,6 +175,12 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
  * out_stats: [0] queries, [1] algorithmic posting bytes of the batch, [2] postings of the batch. */
 int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats);
 
+/* Pagination (the reference: TopScoreDocCollector::create(numHits, after) + IndexSearcher::search(query, collector),
+ * TopScoreDocCollector.h:69, IndexSearcher.h:255): the best num_hits docs among those whose id is above after_doc - the
+ * reference's leaf collector filters on the doc id (TopScoreDocCollector.cpp:176-187) - with totalHits counting every hit.
+ * The reference's C bridge has no entry point for it. Free the result with diagon_free_top_docs. */
+DiagonTopDocs dgpu_search_after(DiagonIndexSearcher searcher, DiagonQuery query, int32_t num_hits, int32_t after_doc, float after_score);
+
 /* Segment-sharded search, one rank (process) per GPU (the reference loops over the leaves and shares
  * one collector: IndexSearcher.cpp:76-110). Every rank opens ITS run of segments (dgpu_open_index / dgpu_open_synthetic
  * with seg_lo, seg_hi, or dgpu_builder_add_segment(..., is_local)); rank 0 makes a 128-byte id with dgpu_sharded_unique_id

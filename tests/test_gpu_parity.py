@@ -453,6 +453,70 @@ def test_union_kernel_edge_shapes(readers, g1_dump, window):
             r.set_option(opt, v)
 
 
+def test_search_after_pagination(readers, g1_dump):
+    """searchAfter as the reference's collector defines it (TopScoreDocCollector.cpp:154-187): every hit is counted, docs
+    whose id is not above after.doc are never collected, the rest compete as usual. The expectation is built from the
+    oracle's full ranking of the same query (all hits), filtered by that rule - for every kernel a query can be routed to."""
+    ox = orc.OracleIndex(g1_dump)
+    r = readers["g1"]
+    lines = ["OR body 0 t0000003 t0000020 t0000150", "TERM body t0000005", "AND body t0000001 t0000002",
+             "OR body 2 t0000001 t0000002 t0000003 t0000004", "ORF body price 100000 600000 t0000002 t0000007",
+             "ANDNOT body 1 t0000002 t0000001", "OR body 0 " + " ".join("t%07d" % i for i in range(1, 41))]
+    try:
+        for opts in (dict(), dict(union_max_overlap=100000), dict(lane_merge=1), dict(lane_merge=0), dict(kernel=2)):
+            for o, v in {**_DEFAULTS, "kernel": 3, **opts}.items():
+                r.set_option(o, v)
+            s = dg.IndexSearcher(r)
+            for line in lines:
+                q = api.parse_line(line)
+                hits, full, _ = ox.search(q, 4096)
+                assert hits <= 4096
+                for k in (5, 50):
+                    for after_doc in (-1, 0, 17, 1000, 3000, 4420, 10 ** 6):
+                        want = [(d, sc) for d, sc in full if d > after_doc][:k]
+                        td = s.search_after(api.ScoreDoc(after_doc, 1.0), q, k)
+                        got = [(x.doc, np.float32(x.score)) for x in td.scoreDocs]
+                        assert td.totalHits.value == hits, (line, after_doc)
+                        assert [d for d, _ in got] == [d for d, _ in want], (opts, line[:40], k, after_doc)
+                        assert all(a[1] == np.float32(b[1]) for a, b in zip(got, want))
+    finally:
+        for o, v in {**_DEFAULTS, "kernel": 3}.items():
+            r.set_option(o, v)
+
+
+def test_segment_without_the_filter_column_matches_nothing(g1_dump):
+    """A range clause has no scorer in a segment that lacks the doc-values column (NumericRangeQuery.cpp:225-228), so no doc
+    of that segment passes the filter - even when the range holds 0, the value the reference's reader reports for a
+    missing doc inside a segment that does have the column. The golden corpus with the column taken out of its middle
+    segment, against the oracle on the same dump."""
+    import copy
+
+    from diagon_b200.dumpfile import build_reader_from_dump
+
+    dump = copy.deepcopy(g1_dump)
+    assert len(dump.segments) == 3 and "price" in dump.segments[1].dv
+    del dump.segments[1].dv["price"]
+    ox = orc.OracleIndex(dump)
+    reader = build_reader_from_dump(dump, 0)
+    try:
+        searcher = dg.IndexSearcher(reader)
+        lines = ["ORF body price 0 400000 t0000001 t0000002 t0000003",
+                 "ORF body price -5 5 t0000001 t0000002",
+                 "ORF body price -9223372036854775808 9223372036854775807 t0000001 t0000004",
+                 "ANDF body price 0 999999999 t0000001 t0000002",
+                 "ORF body price 100000 300000 t0000005 t0000010 t0000012"]
+        for k in (10, 100):
+            res = searcher.search_batch_text(("\n".join(lines) + "\n").encode(), k)
+            for q, line in enumerate(lines):
+                h, sd, _ = ox.search(api.parse_line(line), k)
+                got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
+                assert_same_topdocs(int(res.total_hits[q]), got, h, sd, line[:60])
+                lo, hi = dump.segments[1].doc_base, dump.segments[1].doc_base + dump.segments[1].max_doc
+                assert not [d for d, _ in got if lo <= d < hi], "a doc of the segment without the column passed the filter"
+    finally:
+        reader.close()
+
+
 def test_oversized_batch_is_split_automatically(readers, golden_dir):
     """A batch whose distinct terms decode to more postings than the engine's scratch can index is cut in halves by the
     library (dgpu_search_batch_text), recursively, with the results of the one-call batch. The limit is lowered here so

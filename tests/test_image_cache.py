@@ -89,11 +89,13 @@ def test_damaged_images_are_refused(g1_raw, tmp_path):
     refused(blob[:16], "corrupt index image")
     refused(b"XGPUIMG1" + blob[8:], "not a DGPUIMG1 file")
     refused(blob[: len(blob) // 2], "corrupt index image")
-    refused(blob + b"\0", "trailing bytes")
-    for pos in (len(blob) // 3, len(blob) - 9):   # payload bytes: structure still parses, the content hash does not match
+    refused(blob + b"\0", "corrupt index image")
+    # one flipped bit anywhere in the body - names, segment table, statistics, dictionary, postings, k tables - changes the
+    # content hash (the whole body is hashed, not only what is uploaded)
+    for pos in [20, 40, 64, 100, 200, 400, 1000, len(blob) // 7, len(blob) // 5, len(blob) // 3, len(blob) // 2, len(blob) - 9]:
         flipped = bytearray(blob)
         flipped[pos] ^= 0x40
-        refused(bytes(flipped), "corrupt index image")
+        refused(bytes(flipped), "content hash mismatch")
     with pytest.raises(api.DiagonError):
         dg.IndexReader.from_image(str(tmp_path / "missing.img"), -1)
 
