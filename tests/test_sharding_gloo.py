@@ -112,8 +112,8 @@ def _worker(rank, world, port, tmp):
         def unpack(b):
             magic, nq, nt, nf = np.frombuffer(b[:16].tobytes(), dtype=np.uint32)
             assert magic == 0x42504744
-            q = np.frombuffer(b[16:16 + 20 * nq].tobytes(), dtype=np.uint32).reshape(nq, 5).copy()
-            t = b[16 + 20 * nq: 16 + 20 * nq + 12 * nt].tobytes()
+            q = np.frombuffer(b[16:16 + 24 * nq].tobytes(), dtype=np.uint32).reshape(nq, 6).copy()   # sizeof(dgpu_query) == 24
+            t = b[16 + 24 * nq: 16 + 24 * nq + 12 * nt].tobytes()
             return q, t, nt, nf
 
         want_q, want_t, _, _ = unpack(ws.compile_batch_text(("\n".join(lines) + "\n").encode()))
