@@ -469,10 +469,10 @@ def test_search_after_pagination(readers, g1_dump):
             s = dg.IndexSearcher(r)
             for line in lines:
                 q = api.parse_line(line)
-                hits, full, _ = ox.search(q, 4096)
-                assert hits <= 4096
+                hits, full, _ = ox.search(q, g1_dump.max_doc)
+                assert hits == len(full)
                 for k in (5, 50):
-                    for after_doc in (-1, 0, 17, 1000, 3000, 4420, 10 ** 6):
+                    for after_doc in (-1, 0, 17, 1000, 3000, 4420, g1_dump.max_doc - 2, 10 ** 6):
                         want = [(d, sc) for d, sc in full if d > after_doc][:k]
                         td = s.search_after(api.ScoreDoc(after_doc, 1.0), q, k)
                         got = [(x.doc, np.float32(x.score)) for x in td.scoreDocs]
