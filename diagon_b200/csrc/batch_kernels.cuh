@@ -1007,7 +1007,7 @@ lane_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t staged_warp_smem_bytes(uint32_t ring_entries, uint32_t cap_smem, int T) {
     size_t b = sizeof(uint2) * (static_cast<size_t>(ring_entries) + 1);   // rings + the shared end-of-run entry
-    b += (sizeof(uint32_t) * static_cast<size_t>(T) + 7) & ~static_cast<size_t>(7);   // cursor exchange
+    b += (sizeof(uint32_t) * (static_cast<size_t>(T) + 1) + 7) & ~static_cast<size_t>(7);   // cursor exchange + the searchAfter bound
     b += cap_smem ? sizeof(uint64_t) * cap_smem                           // candidate pool in shared memory, or
                   : sizeof(uint32_t) * 256;                               // the digit histogram of warp_select_topk (pool in global memory)
     return (b + 15) & ~static_cast<size_t>(15);
@@ -1114,9 +1114,10 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
     uint2* ring = reinterpret_cast<uint2*>(sp);
     uint32_t* xch = reinterpret_cast<uint32_t*>(sp + sizeof(uint2) * (B + 1));
     uint64_t* cand = BIGK ? P.pool + static_cast<size_t>(blockIdx.x) * P.cand_cap
-                          : reinterpret_cast<uint64_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * T + 7) & ~7u));
+                          : reinterpret_cast<uint64_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * (T + 1) + 7) & ~7u));
     // with the pool in global memory, its place in shared memory holds the digit histogram of warp_select_topk
-    uint32_t* hist = reinterpret_cast<uint32_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * T + 7) & ~7u));
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sp + sizeof(uint2) * (B + 1) + ((sizeof(uint32_t) * (T + 1) + 7) & ~7u));
+    volatile uint32_t* after_p = xch + T;   // the item's searchAfter bound
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint2* __restrict__ runs = P.runs;
     if (lane == 0) ring[B] = make_uint2(kDocEnd, 0u);   // what the unused term slots of a query read
@@ -1154,6 +1155,8 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
             pend[d] = false;
         }
         const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
+        if (lane == 0) *after_p = qd.after_plus1;
+        __syncwarp();
         DGPU_ASSERT(nt <= static_cast<uint32_t>(T));
         const bool mine = static_cast<uint32_t>(lane) < nt;
 
@@ -1280,7 +1283,9 @@ staged_merge_topk_kernel(DeviceIndex ix, AccumParams P) {
                 const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
                 const uint64_t key = (static_cast<uint64_t>(ord) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - doc);
                 // NaN / Inf are counted as hits but never collected (TopScoreDocCollector.cpp:165-174)
-                const bool push = maybe && key > thresh && (sb & 0x7F800000u) != 0x7F800000u && doc >= qd.after_plus1;
+                // (searchAfter bound: kept in shared memory and read here, on the rare path - a register held through the
+                // merge loop costs the T = 20 instantiation a warp per SM)
+                const bool push = maybe && key > thresh && (sb & 0x7F800000u) != 0x7F800000u && doc >= *after_p;
                 if (n_cand + 32u > P.cand_cap) prune();
                 const bool still = push && key > thresh;   // the prune may have raised the threshold
                 const uint32_t sm = __ballot_sync(0xFFFFFFFFu, still);

@@ -188,7 +188,10 @@ struct dgpu_engine {
     int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
     int warps_per_sm = 20;   // independent scoring warps per SM (each owns 1/n of the shared memory)
     int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
-    int part_factor = 1;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
+    int batch_share_permille = 1000;   // the staged batch is this share of the work the GPU has in flight (a chunk of a pipelined
+                                       // call: its neighbours run beside it, so it is cut into parts as the whole call would be)
+    int part_factor = 0;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
+                             // (0 = by kernel: 1 for batches of union_topk items - 32 warps per SM already -, 2 otherwise)
     int decode_ctas_per_sm = 64; // grid of decode_score_kernel (grid-stride over the decode work items)
     int intersect = 1;       // pure-MUST queries of 2..32 terms go to intersect_topk_kernel (0: counted in the windows)
     int lane_merge = 3;      // queries of <= 32 terms: 3 = union_topk_kernel, 1 = staged_merge_topk_kernel, 2 = lane_merge_topk_kernel (<= 16 terms), 0 = accumulated in windows
@@ -369,8 +372,13 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
         e->force_splits = static_cast<int>(value);
         return 0;
     }
+    if (!std::strcmp(name, "batch_share_permille")) {
+        if (value < 1 || value > 1000) return fail("batch_share_permille must be in [1, 1000]");
+        e->batch_share_permille = static_cast<int>(value);
+        return 0;
+    }
     if (!std::strcmp(name, "part_factor")) {
-        if (value < 1 || value > 64) return fail("part_factor must be in [1, 64]");
+        if (value < 0 || value > 64) return fail("part_factor must be in [0, 64]");
         e->part_factor = static_cast<int>(value);
         return 0;
     }
@@ -820,9 +828,12 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         // warps that will pull items: union_topk_kernel runs 32 one-warp CTAs per SM, the others plan_ctas x plan_wpc
         uint32_t n_union_q = 0;
         for (uint32_t q = 0; q < b->n_queries; ++q) n_union_q += is_and[q] == 2 ? 1u : 0u;
+        const bool mostly_union = 2 * n_union_q > b->n_queries;
         const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) *
-                                 (2 * n_union_q > b->n_queries ? 32u : static_cast<uint32_t>(e->plan_ctas * e->plan_wpc));
-        const uint64_t target = std::max<uint64_t>(64, total_cost / (n_warps * static_cast<uint64_t>(e->part_factor)) + 1);   // posting blocks per item
+                                 (mostly_union ? 32u : static_cast<uint32_t>(e->plan_ctas * e->plan_wpc));
+        const uint64_t part_factor = e->part_factor ? static_cast<uint64_t>(e->part_factor) : (mostly_union ? 1u : 2u);
+        const uint64_t in_flight = total_cost * 1000u / static_cast<uint64_t>(e->batch_share_permille);
+        const uint64_t target = std::max<uint64_t>(64, in_flight / (n_warps * part_factor) + 1);   // posting blocks per item
         // every part keeps its own top-k and the merge compares all pairs of parts: large k gets fewer parts
         const uint32_t cap_parts = e->max_parts ? static_cast<uint32_t>(e->max_parts)
                                                 : std::max(2u, std::min(64u, 4096u / static_cast<uint32_t>(k)));

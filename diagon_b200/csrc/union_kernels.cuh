@@ -311,6 +311,16 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                     }
                     const bool single_ok = !NEED_CNT || ((single_mask >> u) & 1u);
                     const uint32_t meta_u = static_cast<uint32_t>(u) << 25;
+                    // mode 2, 32-bit column: the filter values of a chunk's docs are gathered one iteration ahead (a value per
+                    // posting, at random: the latency is what costs), for the entries inside the window only
+                    const bool ahead = FILTER && single_ok && nf && dv0n;
+                    int32_t fv[4] = {0, 0, 0, 0};
+                    auto gather_ahead = [&](const uint4& dd) {
+                        const uint32_t x[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) fv[j] = (x[j] - ws < wlen) ? __ldg(dv0n + x[j]) : 0;
+                    };
+                    if (FILTER && ahead) gather_ahead(d);
                     for (;;) {
                         DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk <= P.run_total);
                         // sorted run: the chunk's last entry tells whether the clause goes on inside this window
@@ -351,11 +361,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                 for (int j = 0; j < 4; ++j) nw[j] = in[j] && !lt[j];
                                 if (nf) {
                                     if (dv0n) {
-                                        int32_t v[4];
 #pragma unroll
-                                        for (int j = 0; j < 4; ++j) v[j] = nw[j] ? __ldg(dv0n + dv[j]) : 0;
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) nw[j] = nw[j] && v[j] >= lo0n && v[j] <= hi0n;
+                                        for (int j = 0; j < 4; ++j) nw[j] = nw[j] && fv[j] >= lo0n && fv[j] <= hi0n;
                                     } else {
                                         int64_t v[4];
 #pragma unroll
@@ -438,6 +445,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         c += kUnionChunk;
                         d = dn;
                         cm = cmn;
+                        if (FILTER && ahead) gather_ahead(d);
                         if (full) break;
                     }
                 }

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <filesystem>
 #include <limits>
@@ -328,9 +329,17 @@ int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int
             throw std::runtime_error(std::string("dgpu search: ") + dgpu_engine_last_error());
     };
     try {
-        // the first chunk is half a share: its host work is the only one the GPU waits for
-        const size_t shares = 2 * static_cast<size_t>(chunks) - 1;
-        auto cut = [&](int c) { return c <= 0 ? static_cast<size_t>(0) : n * (2 * static_cast<size_t>(c) - 1) / shares; };
+        // chunk sizes double: the first chunk's host work is the only one the GPU waits for, and the host prepares a
+        // chunk about three times faster than the GPU scores it (measured on C2: 3 chunks of 1/7, 2/7, 4/7 beat equal
+        // chunks and a half-size first chunk by 4 %)
+        std::vector<size_t> cuts(static_cast<size_t>(chunks) + 1, 0);
+        {
+            const double tot = std::ldexp(1.0, chunks) - 1.0;
+            for (int c = 1; c < chunks; ++c)
+                cuts[static_cast<size_t>(c)] = static_cast<size_t>(static_cast<double>(n) * (std::ldexp(1.0, c) - 1.0) / tot);
+        }
+        cuts[static_cast<size_t>(chunks)] = n;
+        auto cut = [&](int c) { return cuts[static_cast<size_t>(std::max(0, c))]; };
         for (int c = 0; c < chunks; ++c) {
             const size_t q0 = cut(c), q1 = c + 1 == chunks ? n : cut(c + 1);
             if (q1 == q0) continue;
