@@ -169,6 +169,7 @@ struct RunArrays {
     uint32_t* docs;
     float* scores;
     float* cmax;   // [entry / 64]
+    float* bmax;   // [entry / 128]: the larger of a block's two chunk maxima
 };
 
 template <bool AOS, bool SOA>
@@ -268,11 +269,14 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
 #pragma unroll
                 for (int o = 8; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
                 if ((lane & 15) == 0) out.cmax[e0 >> 6] = mx;
+                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
+                if (lane == 0) out.bmax[e0 >> 7] = mx;
                 if (rel + 1 == nb) {
 #pragma unroll
                     for (int pb = 1; pb <= kPadBlocks; ++pb) {
                         *reinterpret_cast<uint4*>(out.docs + e0 + pb * DGPU_BLOCK_POSTINGS) = make_uint4(kDocEnd, kDocEnd, kDocEnd, kDocEnd);
                         if ((lane & 15) == 0) out.cmax[(e0 >> 6) + 2 * pb] = __uint_as_float(0xFF800000u);
+                        if (lane == 0) out.bmax[(e0 >> 7) + pb] = __uint_as_float(0xFF800000u);
                     }
                 }
             }
@@ -302,6 +306,7 @@ struct AccumParams {
     const uint32_t* run_docs;   // the same runs as three arrays (union_topk_kernel): doc ids,
     const float* run_scores;    //   scores,
     const float* run_cmax;      //   maximum score of every 64 entries
+    const float* run_bmax;      //   ... of every 128 entries (one block)
     uint64_t run_total;         // entries allocated in `runs` (bounds checks)
     int k;
     uint32_t W;                 // docs per window (multiple of 32, <= 65536)

@@ -150,6 +150,7 @@ struct dgpu_engine {
     DevBuf<uint32_t> d_run_docs;        // the runs as three arrays (union_topk_kernel): doc ids,
     DevBuf<float> d_run_scores;         //   scores,
     DevBuf<float> d_run_cmax;           //   maximum score of every 64 entries
+    DevBuf<float> d_run_bmax;           //   ... of every 128 entries
     bool runs_aos = true, runs_soa = false;   // which layouts decode_score_kernel writes for the staged batch
     DevBuf<uint64_t> d_part_keys;
     DevBuf<int32_t> d_part_counts;
@@ -310,7 +311,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     e->d_queries.release(); e->d_terms.release(); e->d_filters.release(); e->d_order.release();
     e->d_counter.release(); e->d_keys.release(); e->d_counts.release(); e->d_hits.release();
     e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_runs.release();
-    e->d_run_docs.release(); e->d_run_scores.release(); e->d_run_cmax.release();
+    e->d_run_docs.release(); e->d_run_scores.release(); e->d_run_cmax.release(); e->d_run_bmax.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
     e->d_witems.release(); e->d_part_off.release(); e->d_pool.release();
     e->d_packed.release(); e->d_gathered.release();
@@ -947,6 +948,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             ce = e->d_run_docs.ensure(cap);
             if (ce == cudaSuccess) ce = e->d_run_scores.ensure(cap);
             if (ce == cudaSuccess) ce = e->d_run_cmax.ensure(cap / 64 + 64);
+            if (ce == cudaSuccess) ce = e->d_run_bmax.ensure(cap / 128 + 64);
         }
         if (ce != cudaSuccess)
             return fail("cannot allocate %zu MB of decode scratch (%s); split the batch", cap * 8 >> 20, cudaGetErrorString(ce));
@@ -1138,6 +1140,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.run_docs = e->d_run_docs.p;
     P.run_scores = e->d_run_scores.p;
     P.run_cmax = e->d_run_cmax.p;
+    P.run_bmax = e->d_run_bmax.p;
     P.run_total = e->runs_soa ? e->d_run_docs.cap : e->d_runs.cap;
     P.k = e->k;
     P.max_terms = (e->max_terms + 3u) & ~3u;
@@ -1162,7 +1165,7 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     CU(cudaEventRecord(e->ev0, stream));
     if (e->n_ditems) {
         const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * e->decode_ctas_per_sm));
-        const RunArrays out{e->d_runs.p, e->d_run_docs.p, e->d_run_scores.p, e->d_run_cmax.p};
+        const RunArrays out{e->d_runs.p, e->d_run_docs.p, e->d_run_scores.p, e->d_run_cmax.p, e->d_run_bmax.p};
         auto dk = e->runs_soa ? (e->runs_aos ? decode_score_kernel<true, true> : decode_score_kernel<false, true>)
                               : decode_score_kernel<true, false>;
         // on the engine's own stream the decode runs at high priority: when another engine's scoring kernel fills the GPU

@@ -110,6 +110,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
     const uint32_t* __restrict__ docs = P.run_docs;
     const float* __restrict__ scores = P.run_scores;
     const float* __restrict__ cmax = P.run_cmax;
+    const float* __restrict__ bmax = P.run_bmax;
 
     for (uint32_t i = lane; i < W / 128; i += 32) reinterpret_cast<uint4*>(seen)[i] = make_uint4(0u, 0u, 0u, 0u);
     filt[lane] = 0u;
@@ -145,8 +146,11 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                 }
             }
         }
-        const uint32_t lo = wi.doc_lo, hi = wi.doc_hi;
-        if (lane == 0) *after_p = qd.after_plus1;
+        const uint32_t lo = wi.doc_lo;
+        if (lane == 0) {   // read at window ends / on the collect path only: not worth a register each
+            after_p[0] = qd.after_plus1;
+            after_p[1] = wi.doc_hi;
+        }
         __syncwarp();
         DGPU_ASSERT(nt <= 32u);
         const bool mine = static_cast<uint32_t>(lane) < nt;
@@ -257,10 +261,11 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         for (;;) {
             // ---- window: W docs from the smallest next doc of any clause
             const uint32_t ws = opaque(__reduce_min_sync(0xFFFFFFFFu, nd));
+            const uint32_t hi = after_p[1];
             const bool last = ws >= hi;
-            const uint32_t we = opaque(last ? ws : ((hi - ws > W) ? ws + W : hi));
-            const uint32_t wlen = opaque(we - ws);
-            const uint32_t act0 = __ballot_sync(0xFFFFFFFFu, nd < we);   // clauses with entries inside the window (none if last)
+            // the stream tests docs against (ws, wlen) only: `doc - ws < wlen` (a chunk's last entry is never below ws)
+            const uint32_t wlen = opaque(last ? 0u : min(hi - ws, W));
+            const uint32_t act0 = __ballot_sync(0xFFFFFFFFu, nd - ws < wlen);   // clauses with entries inside the window (none if last)
             const uint32_t wpos = pos;
             if (n_rec == 0) {
                 base = pos;
@@ -280,8 +285,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
             // the docs of a chunk (this lane's four) and the larger of its two chunk maxima
             auto load_chunk = [&](uint32_t at, uint4& dd, float& mx) {
                 dd = __ldg(reinterpret_cast<const uint4*>(docs + at) + lane);
-                const float2 m2 = __ldg(reinterpret_cast<const float2*>(cmax + (at >> 6)));
-                mx = fmaxf(m2.x, m2.y);
+                mx = __ldg(bmax + (at >> 7));   // (nothing computed on it here: the load stays in flight)
             };
 
             for (;;) {
@@ -324,7 +328,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                     for (;;) {
                         DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk <= P.run_total);
                         // sorted run: the chunk's last entry tells whether the clause goes on inside this window
-                        const bool more = __shfl_sync(0xFFFFFFFFu, d.w, 31) < we;
+                        const bool more = __shfl_sync(0xFFFFFFFFu, d.w, 31) - ws < wlen;
                         uint4 dn = make_uint4(0u, 0u, 0u, 0u);
                         float cmn = 0.0f;
                         if (more) {
@@ -417,6 +421,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         if (!more) {
                             // the clause's next window starts at the first entry >= we: the entries below are a prefix
                             uint32_t below = kUnionChunk;
+                            const uint32_t we = ws + wlen;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) below -= __popc(__ballot_sync(0xFFFFFFFFu, dv[j] >= we));
                             DGPU_ASSERT(below < kUnionChunk);
