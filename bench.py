@@ -8,8 +8,11 @@ top-10, MS-MARCO-passage-shaped corpus of 8,841,823 docs in 8 segments). Prints 
 
   value     whole-job queries/s with the batch already staged on the device (kernels only; for N > 1 also the
             NCCL all-gather of the local top-k and the device merge), CUDA events, max over ranks
-  e2e       the same through the reference-facing C ABI with HOST buffers: query text in host memory ->
-            dgpu_search_batch_text (parse, dictionary lookups, weights, H2D, kernels, D2H) -> host arrays
+  e2e       the same through the reference-facing C ABI with HOST buffers, every step: query text in host memory ->
+            parse, dictionary lookups, weights, H2D, kernels, D2H -> host arrays. N == 1: a stream of batches through
+            dgpu_submit_batch_text / dgpu_collect_batch with two batches in flight (the reference arm is a throughput
+            run too: 16 threads pulling queries); `one_call_at_a_time` inside it is dgpu_search_batch_text called
+            K times in a row. N > 1: dgpu_sharded_search_batch_text on every rank
   roofline  algorithmic posting bytes of the batch / device time of the search kernel, against the measured
             HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, its own IndexSearcher, stock config) timed on this box's host cores on
@@ -439,6 +442,28 @@ def main():
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = nq * args.steps / float(e2e_t[0])
+    e2e_sync = None
+    if sharded is None:
+        # a stream of batches: batch i + 1 is submitted (host work, H2D, launches) before batch i is collected (wait, D2H,
+        # unpack), so the host work of one overlaps the kernels of the other and every batch runs whole. Every step still
+        # carries its own text in and its own results out; the timed region holds `steps` submits and `steps` collects,
+        # the pipeline's fill and drain included.
+        e2e_sync = {"value": e2e_value, "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps,
+                    "call": "dgpu_search_batch_text, one call at a time (the batch is cut into 3 chunks inside the call)"}
+        outs = [searcher._alloc(nq, k) for _ in range(2)]
+        for timed in (False, True):
+            n_steps = args.steps if timed else n_warm
+            barrier()
+            t1 = time.perf_counter()
+            prev = searcher.submit_batch_text(text, k)
+            for i in range(1, n_steps):
+                cur = searcher.submit_batch_text(text, k)
+                res = prev.collect(outs[(i - 1) & 1])
+                prev = cur
+            res = prev.collect(outs[(n_steps - 1) & 1])
+            t2 = time.perf_counter()
+        e2e_t = torch.tensor([t2 - t1], dtype=torch.float64, device="cuda")
+        e2e_value = nq * args.steps / float(e2e_t[0])
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel: accumulate_topk_kernel (batched path) or search_kernel (fused path)
@@ -501,12 +526,13 @@ def main():
                        "kernel_path": "batched" if batched else "fused-windows"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "call": ("dgpu_search_batch_text (host text -> host results; the batch is cut into chunks, chunk i + 1 is parsed, "
-                             "compiled and staged on another engine while the kernels of chunk i run)" if world == 1 else
+                    "call": ("dgpu_submit_batch_text + dgpu_collect_batch, two batches in flight (host text -> host results: batch "
+                             "i + 1 is parsed, compiled, staged and launched before batch i is collected)" if world == 1 else
                              "dgpu_sharded_search_batch_text on every rank (host text -> merged host results: parse + compile, "
                              "H2D, kernels on the rank's shard, ONE ncclAllGather of k keys + count + hits per query and chunk, "
                              "device merge, D2H)"),
-                    "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
+                    "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps,
+                    **({"one_call_at_a_time": e2e_sync} if e2e_sync else {})},
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -4,7 +4,7 @@ The product is libdiagon_b200.so (CUDA engine + C++20 host layer, C ABI in inclu
 Python mirror of the reference's search API used by tests and bench.py; it contains no compute.
 """
 from .api import (  # noqa: F401
-    BatchResult, BooleanClause, BooleanQuery, DiagonError, IndexBuilder, IndexReader, IndexSearcher,
+    BatchResult, BatchTicket, BooleanClause, BooleanQuery, DiagonError, IndexBuilder, IndexReader, IndexSearcher,
     NumericRangeQuery, Occur, Query, ScoreDoc, ShardedSearcher, Term, TermQuery, TopDocs, TotalHits, and_query, named_corpus,
     or_query, parse_line, query_log_text, write_synthetic_dump,
 )

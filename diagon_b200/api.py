@@ -456,6 +456,13 @@ class IndexSearcher:
             raise DiagonError(_lib.last_error())
         return BatchResult(docs, scores, counts, hits)
 
+    def submit_batch_text(self, text: bytes, k: int) -> "BatchTicket":
+        """dgpu_submit_batch_text: host work + H2D + kernel launches, returns without waiting (up to 4 batches in flight)."""
+        t = _lib.load().dgpu_submit_batch_text(self._ptr, text, len(text), k)
+        if not t:
+            raise DiagonError(_lib.last_error())
+        return BatchTicket(self, t, k)
+
     def search_batch_text(self, text: bytes, k: int, max_queries: Optional[int] = None, out=None) -> BatchResult:
         if max_queries is None:
             max_queries = text.count(b"\n") + 1
@@ -533,6 +540,39 @@ def query_log_text(config: str, vocab: int, num_queries: int, kind: str) -> byte
 def write_synthetic_dump(spec, path: str):
     if _lib.load().dgpu_write_synthetic_dump(C.byref(spec), str(path).encode()) != 0:
         raise DiagonError(_lib.last_error())
+
+
+class BatchTicket:
+    """A batch submitted with IndexSearcher.submit_batch_text; collect() waits for it and returns its results."""
+
+    def __init__(self, searcher, ptr, k):
+        self._searcher, self._ptr, self._k = searcher, ptr, k
+
+    def __len__(self):
+        return int(_lib.load().dgpu_batch_ticket_queries(self._ptr)) if self._ptr else 0
+
+    def collect(self, out=None) -> BatchResult:
+        if not self._ptr:
+            raise DiagonError("ticket already collected")
+        n = len(self)
+        docs, scores, counts, hits = out if out is not None else self._searcher._alloc(max(n, 1), self._k)
+        ptr, self._ptr = self._ptr, None   # the call frees the ticket, also when it fails
+        r = _lib.load().dgpu_collect_batch(ptr, docs.ctypes.data, scores.ctypes.data, counts.ctypes.data, hits.ctypes.data,
+                                           len(counts))
+        if r < 0:
+            raise DiagonError(_lib.last_error())
+        return BatchResult(docs[:r], scores[:r], counts[:r], hits[:r])
+
+    def abandon(self):
+        if self._ptr:
+            _lib.load().dgpu_batch_ticket_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.abandon()
+        except Exception:
+            pass
 
 
 class ShardedSearcher:

@@ -256,6 +256,7 @@ int run_compiled(IndexSearcher& s, const CompiledBatch& batch, int32_t k, int32_
     dgpu_results res{keys.data(), counts.data(), out_total_hits};
     dgpu_query_batch view = batch.view();
     auto guard = s.getIndexReader().lock_engines();
+    s.getIndexReader().require_idle();
     dgpu_engine* e = s.getIndexReader().engine();
     if (n && !e) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
     if (n && comm) {   // sharded: every rank runs the same batch; the exchange is collective
@@ -307,6 +308,7 @@ int run_text_pipelined(IndexSearcher& s, const std::vector<LineSpan>& lines, int
     const auto t0 = std::chrono::steady_clock::now();
     IndexReader& rd = s.getIndexReader();
     auto guard = rd.lock_engines();
+    rd.require_idle();
     // the chunks rotate over up to four engines that share the device index: a chunk is staged while the kernels of the
     // chunks before it run, and an engine's buffers are not reused before its last chunk has been fetched
     dgpu_engine* eng[1 + IndexReader::kMaxShadows] = {rd.engine(), nullptr, nullptr, nullptr};
@@ -845,6 +847,98 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
         return search_text_splitting(*as_searcher(searcher), text, text_len, k, out_docs, out_scores, out_counts, out_total_hits,
                                      max_queries);
     } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+// ------------------------------------------------------------------ submit / collect: several batches in flight
+// dgpu_search_batch_text returns when the results are in host memory, so the host work of the next batch (parse, compile,
+// stage: ~5 ms per 10 K queries) cannot overlap the kernels of this one unless the batch is cut into chunks - and chunks
+// cost device efficiency (their doc-range parts are finer, their distinct terms are decoded per chunk). A caller with a
+// stream of batches submits batch i + 1 before it collects batch i: every batch runs whole on an engine of its own
+// (up to 1 + kMaxShadows in flight), the GPU always has the next batch queued.
+struct BatchTicket {
+    IndexSearcher* searcher = nullptr;
+    dgpu_engine* engine = nullptr;
+    int slot = -1;
+    size_t n = 0;
+    int32_t k = 0;
+};
+
+DgpuBatchTicket dgpu_submit_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k) {
+    if (!searcher || !text) { set_error("Invalid searcher or text"); return nullptr; }
+    try {
+        if (k <= 0) throw std::invalid_argument("numHits must be > 0");
+        IndexSearcher& s = *as_searcher(searcher);
+        const auto lines = split_lines(text, text_len);
+        auto ticket = std::make_unique<BatchTicket>();
+        ticket->searcher = &s;
+        ticket->n = lines.size();
+        ticket->k = k;
+        if (lines.empty()) return ticket.release();
+        CompiledBatch batch;
+        compile_lines_shared(s, nullptr, lines, 0, lines.size(), batch);   // (host threads; no engine touched yet)
+        IndexReader& rd = s.getIndexReader();
+        auto guard = rd.lock_engines();
+        if (!rd.engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
+        ticket->slot = rd.acquire_engine_slot(&ticket->engine);
+        if (ticket->slot < 0) throw std::runtime_error("every engine of the reader holds a submitted batch: collect one first");
+        dgpu_query_batch view = batch.view();
+        if (dgpu_engine_stage_batch(ticket->engine, &view, k) != 0 || dgpu_engine_search_staged(ticket->engine, nullptr) != 0) {
+            const std::string msg = dgpu_engine_last_error();
+            dgpu_engine_wait(ticket->engine);
+            rd.release_engine_slot(ticket->slot);
+            throw std::runtime_error("dgpu search: " + msg);
+        }
+        return ticket.release();
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
+}
+
+int32_t dgpu_batch_ticket_queries(DgpuBatchTicket ticket) {
+    if (!ticket) { set_error("Invalid ticket"); return -1; }
+    return static_cast<int32_t>(static_cast<BatchTicket*>(ticket)->n);
+}
+
+// Waits for the batch, copies its results out and frees the ticket (also when it fails).
+int dgpu_collect_batch(DgpuBatchTicket ticket, int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
+                       int32_t max_queries) {
+    if (!ticket) { set_error("Invalid ticket"); return -1; }
+    std::unique_ptr<BatchTicket> t(static_cast<BatchTicket*>(ticket));
+    try {
+        if (t->n == 0) return 0;
+        IndexReader& rd = t->searcher->getIndexReader();
+        std::vector<uint64_t> keys;
+        std::vector<int32_t> counts;
+        {
+            auto guard = rd.lock_engines();
+            int rc = -1;
+            std::string msg;
+            if (static_cast<int64_t>(t->n) > max_queries) {
+                msg = "more queries than max_queries";
+                dgpu_engine_wait(t->engine);
+            } else {
+                keys.resize(t->n * static_cast<size_t>(t->k));
+                counts.resize(t->n);
+                dgpu_results res{keys.data(), counts.data(), out_total_hits};
+                rc = dgpu_engine_fetch_results(t->engine, &res);
+                if (rc != 0) msg = std::string("dgpu search: ") + dgpu_engine_last_error();
+            }
+            rd.release_engine_slot(t->slot);
+            if (rc != 0) throw std::runtime_error(msg);
+        }
+        unpack(keys, counts, static_cast<int32_t>(t->n), t->k, out_docs, out_scores);
+        std::memcpy(out_counts, counts.data(), t->n * sizeof(int32_t));
+        return static_cast<int>(t->n);
+    } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+// Abandons a submitted batch: waits for its kernels and gives the engine back.
+void dgpu_batch_ticket_free(DgpuBatchTicket ticket) {
+    if (!ticket) return;
+    std::unique_ptr<BatchTicket> t(static_cast<BatchTicket*>(ticket));
+    if (t->slot < 0) return;
+    IndexReader& rd = t->searcher->getIndexReader();
+    auto guard = rd.lock_engines();
+    dgpu_engine_wait(t->engine);
+    rd.release_engine_slot(t->slot);
 }
 
 // ------------------------------------------------------------------ segment-sharded search (one rank per GPU)

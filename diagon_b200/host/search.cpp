@@ -84,6 +84,18 @@ dgpu_engine* IndexReader::shadow_engine(int i) {
     return shadow_[i];
 }
 
+int IndexReader::acquire_engine_slot(dgpu_engine** out) {
+    for (int slot = 0; slot <= kMaxShadows; ++slot) {
+        if (in_flight_ & (1u << slot)) continue;
+        dgpu_engine* e = slot == 0 ? engine_ : shadow_engine(slot - 1);
+        if (!e) return -1;
+        in_flight_ |= 1u << slot;
+        *out = e;
+        return slot;
+    }
+    return -1;
+}
+
 // ------------------------------------------------------------------ compilation
 namespace {
 
@@ -395,6 +407,7 @@ std::vector<TopDocs> IndexSearcher::search(const std::vector<const Query*>& quer
         for (size_t q = 0; q < queries.size(); ++q)
             if ((*after_docs)[q] >= 0) batch.queries[q].after_plus1 = static_cast<uint32_t>((*after_docs)[q]) + 1u;
     auto guard = reader_.lock_engines();
+    reader_.require_idle();
     size_t n = queries.size();
     std::vector<uint64_t> keys(n * static_cast<size_t>(numHits));
     std::vector<int32_t> counts(n);

@@ -22,6 +22,7 @@
 #include <limits>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -226,8 +227,16 @@ public:
     // or fetches takes this lock, so concurrent callers of one reader / searcher are serialised instead of racing
     // (the reference builds its per-query state per call; throughput comes from the batch calls, not from threads).
     std::unique_lock<std::recursive_mutex> lock_engines() { return std::unique_lock<std::recursive_mutex>(engine_mutex_); }
+    // Batches submitted without waiting (dgpu_submit_batch_text) each hold one engine until they are collected. Slot 0 is
+    // engine(), slot i the (i - 1)-th shadow engine. Call with the engine lock held. A synchronous call needs all engines.
+    int acquire_engine_slot(dgpu_engine** out);   // -1: every engine holds a batch (or cannot be created)
+    void release_engine_slot(int slot) { in_flight_ &= ~(1u << slot); }
+    void require_idle() const {
+        if (in_flight_) throw std::runtime_error("batches submitted with dgpu_submit_batch_text are in flight: collect them first");
+    }
 
 private:
+    uint32_t in_flight_ = 0;
     std::recursive_mutex engine_mutex_;
     std::shared_ptr<HostIndex> index_;
     dgpu_engine* engine_ = nullptr;

@@ -171,6 +171,21 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
                            int32_t* out_docs, float* out_scores, int32_t* out_counts, int64_t* out_total_hits,
                            int32_t max_queries);
 
+/* Several batches in flight. dgpu_search_batch_text returns when the results are in host memory; a caller with a stream
+ * of batches submits batch i + 1 before it collects batch i, so the host work of one batch (parse, compile, stage)
+ * overlaps the kernels of the other and every batch runs whole (no chunks). dgpu_submit_batch_text does the host work on
+ * the calling thread, copies the descriptors to the device, launches the kernels on a free engine of the reader (up to 4
+ * batches in flight) and returns a ticket, NULL on error; dgpu_collect_batch waits, copies the results out (same layout
+ * as dgpu_search_batch_text) and frees the ticket, also when it fails; dgpu_batch_ticket_free abandons a batch. While
+ * tickets are outstanding the synchronous calls of the same reader fail ("collect them first"). Results are those of
+ * dgpu_search_batch_text. Single-GPU readers only. */
+typedef void* DgpuBatchTicket;
+DgpuBatchTicket dgpu_submit_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k);
+int32_t dgpu_batch_ticket_queries(DgpuBatchTicket ticket);
+int dgpu_collect_batch(DgpuBatchTicket ticket, int32_t* out_docs, float* out_scores, int32_t* out_counts,
+                       int64_t* out_total_hits, int32_t max_queries);
+void dgpu_batch_ticket_free(DgpuBatchTicket ticket);
+
 /* Compiles a text batch and keeps it staged on the device (for kernel-only timing and multi-GPU runs).
  * out_stats: [0] queries, [1] algorithmic posting bytes of the batch, [2] postings of the batch. */
 int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k, int64_t* out_stats);

@@ -542,6 +542,44 @@ def test_oversized_batch_is_split_automatically(readers, golden_dir):
         r.set_option("pipeline_min", 2048)
 
 
+def test_submitted_batches_in_flight_equal_the_synchronous_call(readers, golden_dir):
+    """dgpu_submit_batch_text / dgpu_collect_batch: up to four batches in flight, each on an engine of its own, collected in
+    any order, with the results of dgpu_search_batch_text; the synchronous calls refuse to run while tickets are out, a
+    fifth submit is refused, an abandoned ticket gives its engine back."""
+    r = readers["g1"]
+    s = dg.IndexSearcher(r)
+    lines = open(os.path.join(golden_dir, "g1_queries.txt"), "rb").read().strip().split(b"\n")
+    texts = [b"\n".join(lines[i::4]) + b"\n" for i in range(4)]
+    want = [s.search_batch_text(t, 10) for t in texts]
+    for order in ((0, 1, 2, 3), (3, 1, 0, 2)):
+        tickets = [s.submit_batch_text(t, 10) for t in texts]
+        assert [len(t) for t in tickets] == [len(w.counts) for w in want]
+        with pytest.raises(dg.DiagonError):
+            s.search_batch_text(texts[0], 10)             # the engines are taken
+        with pytest.raises(dg.DiagonError):
+            s.submit_batch_text(texts[0], 10)             # a fifth batch
+        for i in order:
+            got = tickets[i].collect()
+            assert np.array_equal(got.docs, want[i].docs) and np.array_equal(got.scores, want[i].scores), (order, i)
+            assert np.array_equal(got.total_hits, want[i].total_hits) and np.array_equal(got.counts, want[i].counts)
+        with pytest.raises(dg.DiagonError):
+            tickets[0].collect()                          # a ticket is collected once
+    # the steady state of a stream of batches: submit i + 1, collect i
+    prev = s.submit_batch_text(texts[0], 10)
+    for i in range(1, 9):
+        cur = s.submit_batch_text(texts[i % 4], 10)
+        got = prev.collect()
+        assert np.array_equal(got.docs, want[(i - 1) % 4].docs) and np.array_equal(got.scores, want[(i - 1) % 4].scores)
+        prev = cur
+    prev.abandon()
+    again = s.search_batch_text(texts[1], 10)             # all engines are free again
+    assert np.array_equal(again.docs, want[1].docs) and np.array_equal(again.total_hits, want[1].total_hits)
+    with pytest.raises(dg.DiagonError):
+        s.submit_batch_text(b"OR body 0 t0000001\n", 0)   # numHits must be > 0
+    empty = s.submit_batch_text(b"", 10)
+    assert len(empty) == 0 and len(empty.collect().counts) == 0
+
+
 def test_staging_compiled_slices_equals_one_call(readers, golden_dir):
     """dgpu_compile_batch_text on slices + dgpu_stage_compiled (how the ranks of a sharded index divide the host work)
     gives the same results as dgpu_search_batch_text on the whole batch."""
