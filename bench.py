@@ -442,28 +442,30 @@ def main():
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = nq * args.steps / float(e2e_t[0])
-    e2e_sync = None
-    if sharded is None:
-        # a stream of batches: batch i + 1 is submitted (host work, H2D, launches) before batch i is collected (wait, D2H,
-        # unpack), so the host work of one overlaps the kernels of the other and every batch runs whole. Every step still
-        # carries its own text in and its own results out; the timed region holds `steps` submits and `steps` collects,
-        # the pipeline's fill and drain included.
-        e2e_sync = {"value": e2e_value, "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps,
-                    "call": "dgpu_search_batch_text, one call at a time (the batch is cut into 3 chunks inside the call)"}
-        outs = [searcher._alloc(nq, k) for _ in range(2)]
-        for timed in (False, True):
-            n_steps = args.steps if timed else n_warm
-            barrier()
-            t1 = time.perf_counter()
-            prev = searcher.submit_batch_text(text, k)
-            for i in range(1, n_steps):
-                cur = searcher.submit_batch_text(text, k)
-                res = prev.collect(outs[(i - 1) & 1])
-                prev = cur
-            res = prev.collect(outs[(n_steps - 1) & 1])
-            t2 = time.perf_counter()
-        e2e_t = torch.tensor([t2 - t1], dtype=torch.float64, device="cuda")
-        e2e_value = nq * args.steps / float(e2e_t[0])
+    stream_of = searcher if sharded is None else sharded
+    # a stream of batches: batch i + 1 is submitted (host work, H2D, launches) before batch i is collected (wait, D2H,
+    # unpack), so the host work of one overlaps the kernels of the other and every batch runs whole. Every step still
+    # carries its own text in and its own results out; the timed region holds `steps` submits and `steps` collects,
+    # the pipeline's fill and drain included.
+    e2e_sync = {"value": e2e_value, "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps,
+                "call": ("dgpu_search_batch_text" if sharded is None else "dgpu_sharded_search_batch_text on every rank") +
+                        ", one call at a time (the batch is cut into 3 chunks inside the call)"}
+    outs = [searcher._alloc(nq, k) for _ in range(2)]
+    for timed in (False, True):
+        n_steps = args.steps if timed else n_warm
+        barrier()
+        t1 = time.perf_counter()
+        prev = stream_of.submit_batch_text(text, k)
+        for i in range(1, n_steps):
+            cur = stream_of.submit_batch_text(text, k)
+            res = prev.collect(outs[(i - 1) & 1])
+            prev = cur
+        res = prev.collect(outs[(n_steps - 1) & 1])
+        t2 = time.perf_counter()
+    e2e_t = torch.tensor([t2 - t1], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = nq * args.steps / float(e2e_t[0])
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel: accumulate_topk_kernel (batched path) or search_kernel (fused path)
@@ -528,9 +530,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": ("dgpu_submit_batch_text + dgpu_collect_batch, two batches in flight (host text -> host results: batch "
                              "i + 1 is parsed, compiled, staged and launched before batch i is collected)" if world == 1 else
-                             "dgpu_sharded_search_batch_text on every rank (host text -> merged host results: parse + compile, "
-                             "H2D, kernels on the rank's shard, ONE ncclAllGather of k keys + count + hits per query and chunk, "
-                             "device merge, D2H)"),
+                             "dgpu_sharded_submit_batch_text + dgpu_collect_batch on every rank, two batches in flight (host text -> "
+                             "merged host results: the ranks divide parse + compile, H2D, kernels on the rank's shard, ONE "
+                             "ncclAllGather of k keys + count + hits per query, device merge, D2H)"),
                     "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps,
                     **({"one_call_at_a_time": e2e_sync} if e2e_sync else {})},
             "roofline": roofline,

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "dgpu_search_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "dgpu_submit_batch_text": (C.c_void_p, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32]),
     "dgpu_batch_ticket_queries": (C.c_int32, [C.c_void_p]),
+    "dgpu_sharded_submit_batch_text": (C.c_void_p, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32]),
     "dgpu_collect_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "dgpu_batch_ticket_free": (None, [C.c_void_p]),
     "dgpu_stage_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p]),

@@ -599,6 +599,13 @@ class ShardedSearcher:
         self.local._ptr = _lib.load().dgpu_sharded_searcher_local(self._ptr)
         self.local._borrowed = True
 
+    def submit_batch_text(self, text: bytes, k: int) -> "BatchTicket":
+        """dgpu_sharded_submit_batch_text: a collective - every rank submits the same batches in the same order."""
+        t = _lib.load().dgpu_sharded_submit_batch_text(self._ptr, text, len(text), k)
+        if not t:
+            raise DiagonError(_lib.last_error())
+        return BatchTicket(self.local, t, k)
+
     def search_batch_text(self, text: bytes, k: int, max_queries: Optional[int] = None, out=None) -> BatchResult:
         if max_queries is None:
             max_queries = text.count(b"\n") + 1

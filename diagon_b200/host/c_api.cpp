@@ -863,32 +863,36 @@ struct BatchTicket {
     int32_t k = 0;
 };
 
+static DgpuBatchTicket submit_text(IndexSearcher& s, const ShardContext* sc, const char* text, int64_t text_len, int32_t k) {
+    if (k <= 0) throw std::invalid_argument("numHits must be > 0");
+    const auto lines = split_lines(text, text_len);
+    auto ticket = std::make_unique<BatchTicket>();
+    ticket->searcher = &s;
+    ticket->n = lines.size();
+    ticket->k = k;
+    if (lines.empty()) return ticket.release();
+    CompiledBatch batch;
+    compile_lines_shared(s, sc, lines, 0, lines.size(), batch);   // (host threads; sharded: the ranks divide the lines)
+    IndexReader& rd = s.getIndexReader();
+    auto guard = rd.lock_engines();
+    if (!rd.engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
+    ticket->slot = rd.acquire_engine_slot(&ticket->engine);
+    if (ticket->slot < 0) throw std::runtime_error("every engine of the reader holds a submitted batch: collect one first");
+    dgpu_query_batch view = batch.view();
+    if (dgpu_engine_stage_batch(ticket->engine, &view, k) != 0 || dgpu_engine_search_staged(ticket->engine, nullptr) != 0 ||
+        (sc && dgpu_engine_exchange_topk(ticket->engine, sc->comm, nullptr) != 0)) {   // sharded: the ranks' top k, one all-gather
+        const std::string msg = dgpu_engine_last_error();
+        dgpu_engine_wait(ticket->engine);
+        rd.release_engine_slot(ticket->slot);
+        throw std::runtime_error("dgpu search: " + msg);
+    }
+    return ticket.release();
+}
+
 DgpuBatchTicket dgpu_submit_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k) {
     if (!searcher || !text) { set_error("Invalid searcher or text"); return nullptr; }
     try {
-        if (k <= 0) throw std::invalid_argument("numHits must be > 0");
-        IndexSearcher& s = *as_searcher(searcher);
-        const auto lines = split_lines(text, text_len);
-        auto ticket = std::make_unique<BatchTicket>();
-        ticket->searcher = &s;
-        ticket->n = lines.size();
-        ticket->k = k;
-        if (lines.empty()) return ticket.release();
-        CompiledBatch batch;
-        compile_lines_shared(s, nullptr, lines, 0, lines.size(), batch);   // (host threads; no engine touched yet)
-        IndexReader& rd = s.getIndexReader();
-        auto guard = rd.lock_engines();
-        if (!rd.engine()) throw std::runtime_error("host-only reader: no GPU engine, and there is no CPU fallback");
-        ticket->slot = rd.acquire_engine_slot(&ticket->engine);
-        if (ticket->slot < 0) throw std::runtime_error("every engine of the reader holds a submitted batch: collect one first");
-        dgpu_query_batch view = batch.view();
-        if (dgpu_engine_stage_batch(ticket->engine, &view, k) != 0 || dgpu_engine_search_staged(ticket->engine, nullptr) != 0) {
-            const std::string msg = dgpu_engine_last_error();
-            dgpu_engine_wait(ticket->engine);
-            rd.release_engine_slot(ticket->slot);
-            throw std::runtime_error("dgpu search: " + msg);
-        }
-        return ticket.release();
+        return submit_text(*as_searcher(searcher), nullptr, text, text_len, k);
     } catch (const std::exception& e) { set_error(e); return nullptr; }
 }
 
@@ -1045,6 +1049,17 @@ int dgpu_sharded_search_batch_text(DgpuShardedSearcher s, const char* text, int6
         const ShardContext sc{ss->comm, ss->xch.get(), &ss->round};
         return search_text(ss->searcher, &sc, text, text_len, k, out_docs, out_scores, out_counts, out_total_hits, max_queries);
     } catch (const std::exception& e) { set_error(e); return -1; }
+}
+
+// dgpu_submit_batch_text over all shards: every rank submits the same batches in the same order (the all-gather of a batch
+// is enqueued behind its kernels at submit time) and collects them with dgpu_collect_batch.
+DgpuBatchTicket dgpu_sharded_submit_batch_text(DgpuShardedSearcher s, const char* text, int64_t text_len, int32_t k) {
+    if (!s || !text) { set_error("Invalid searcher or text"); return nullptr; }
+    try {
+        ShardedSearcher* ss = as_sharded(s);
+        const ShardContext sc{ss->comm, ss->xch.get(), &ss->round};
+        return submit_text(ss->searcher, &sc, text, text_len, k);
+    } catch (const std::exception& e) { set_error(e); return nullptr; }
 }
 
 int dgpu_sharded_search_staged(DgpuShardedSearcher s, void* stream) {

@@ -178,7 +178,7 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
  * batches in flight) and returns a ticket, NULL on error; dgpu_collect_batch waits, copies the results out (same layout
  * as dgpu_search_batch_text) and frees the ticket, also when it fails; dgpu_batch_ticket_free abandons a batch. While
  * tickets are outstanding the synchronous calls of the same reader fail ("collect them first"). Results are those of
- * dgpu_search_batch_text. Single-GPU readers only. */
+ * dgpu_search_batch_text. Sharded searchers: dgpu_sharded_submit_batch_text below. */
 typedef void* DgpuBatchTicket;
 DgpuBatchTicket dgpu_submit_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k);
 int32_t dgpu_batch_ticket_queries(DgpuBatchTicket ticket);
@@ -216,6 +216,9 @@ DiagonIndexSearcher dgpu_sharded_searcher_local(DgpuShardedSearcher s);
 int dgpu_sharded_search_batch_text(DgpuShardedSearcher s, const char* text, int64_t text_len, int32_t k, int32_t* out_docs,
                                    float* out_scores, int32_t* out_counts, int64_t* out_total_hits, int32_t max_queries);
 int dgpu_sharded_search_staged(DgpuShardedSearcher s, void* stream);
+/* dgpu_submit_batch_text over all shards: a collective - every rank submits the same batches in the same order and collects
+ * them with dgpu_collect_batch (each rank gets the merged results). */
+DgpuBatchTicket dgpu_sharded_submit_batch_text(DgpuShardedSearcher s, const char* text, int64_t text_len, int32_t k);
 /* The ranks of one box also divide the parse + compile work of every batch: each compiles 1/world of the lines and the
  * compiled descriptors are swapped through POSIX shared memory (host plumbing, no collective; DGPU_SHARD_COMPILE=0 turns
  * it off and every rank compiles the whole batch). dgpu_shm_exchange_selftest exercises that channel without a GPU. */

@@ -31,10 +31,17 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ss = dg.ShardedSearcher(reader, uid[0], rank, world)
         text = dg.query_log_text(shape, spec.vocab, n, kind)
-        for chunks in (1, 3):
-            reader.set_option("pipeline_chunks", chunks)
-            reader.set_option("pipeline_min", 1 if chunks > 1 else 1 << 30)
-            got = ss.search_batch_text(text, k)
+        for chunks in (1, 3, 0):   # 0: a stream of submitted batches, three in flight, the middle one is checked
+            if chunks:
+                reader.set_option("pipeline_chunks", chunks)
+                reader.set_option("pipeline_min", 1 if chunks > 1 else 1 << 30)
+                got = ss.search_batch_text(text, k)
+            else:
+                half = text[: text.index(b"\n", len(text) // 2) + 1]
+                tickets = [ss.submit_batch_text(half, k), ss.submit_batch_text(text, k), ss.submit_batch_text(half, k)]
+                tickets[0].collect()
+                got = tickets[1].collect()
+                tickets[2].collect()
             want = [None]
             if rank == 0:
                 whole = dg.IndexReader.synthetic(spec, local)
