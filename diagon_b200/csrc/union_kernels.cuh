@@ -49,8 +49,14 @@ constexpr int kUnionWarps = 1;                 // one warp per CTA: the bitmap s
 constexpr uint32_t kUnionChunk = 128;          // entries per iteration (lane l: entries 4l .. 4l + 3)
 constexpr uint32_t kMaxChunk = 64;             // entries per chunk maximum (decode_score_kernel: RunArrays::cmax)
 constexpr uint32_t kUnionRecords = 256;        // record list of a warp (doc; meta = stream rank << 25 | flags)
-constexpr uint32_t kUnionResolveAt = 64;       // records that make a window end resolve the list
-constexpr uint32_t kUnionMaxDefer = 16;        // windows a record may wait
+#ifndef DGPU_UNION_RESOLVE_AT
+#define DGPU_UNION_RESOLVE_AT 64
+#endif
+#ifndef DGPU_UNION_MAX_DEFER
+#define DGPU_UNION_MAX_DEFER 16
+#endif
+constexpr uint32_t kUnionResolveAt = DGPU_UNION_RESOLVE_AT;       // records that make a window end resolve the list
+constexpr uint32_t kUnionMaxDefer = DGPU_UNION_MAX_DEFER;        // windows a record may wait
 constexpr uint32_t kUnionFilterWords = 32;     // 1024 bits
 constexpr uint32_t kRecCandidate = 1u << 30;   // meta flag: recorded by the window-end pass, collects only if no other clause holds the doc
 constexpr float kBoundSlack = 1.0001f;         // the bound is summed in stream order, the score in clause order
