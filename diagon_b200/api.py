@@ -264,6 +264,27 @@ class IndexReader:
     def num_terms(self):
         return _lib.load().dgpu_reader_num_terms(self._ptr)
 
+    def term_id(self, field: str, term: bytes) -> int:
+        """Dense id of (field, term) in the reader's dictionary, -1 when the index does not hold the term."""
+        r = _lib.load().dgpu_reader_term_id(self._ptr, field.encode(), term, len(term))
+        if r < -1:
+            raise DiagonError(_lib.last_error())
+        return int(r)
+
+    def term_bytes(self, term_id: int):
+        """(field id, term bytes) of a dense term id."""
+        import ctypes as C
+        f = C.c_int32(0)
+        n = _lib.load().dgpu_reader_term_bytes(self._ptr, term_id, None, 0, C.byref(f))
+        if n < 0:
+            raise DiagonError(_lib.last_error())
+        buf = C.create_string_buffer(max(int(n), 1))
+        _lib.load().dgpu_reader_term_bytes(self._ptr, term_id, buf, n, C.byref(f))
+        return int(f.value), buf.raw[:n]
+
+    def dictionary_frozen(self) -> bool:
+        return _lib.load().dgpu_reader_dictionary_frozen(self._ptr) == 1
+
     def image_bytes(self):
         return _lib.load().dgpu_reader_image_bytes(self._ptr)
 

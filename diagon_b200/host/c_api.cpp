@@ -696,6 +696,28 @@ int64_t dgpu_reader_num_terms(DiagonIndexReader r) {
     if (!r) { set_error("Invalid reader"); return -1; }
     return as_reader(r)->index().dict.size();
 }
+// Dictionary access for tests and tools: the dense id of (field, term bytes), -1 when the index does not hold the term;
+// the term of an id (returns its length, copies at most cap bytes); whether lookups go through the perfect hash.
+int64_t dgpu_reader_term_id(DiagonIndexReader r, const char* field, const char* bytes, int64_t len) {
+    if (!r || !field || (!bytes && len) || len < 0) { set_error("Invalid arguments"); return -2; }
+    const HostIndex& ix = as_reader(r)->index();
+    const int f = ix.field_id(field);
+    if (f < 0) return -1;
+    const uint32_t id = ix.dict.find(static_cast<uint16_t>(f), reinterpret_cast<const uint8_t*>(bytes), static_cast<size_t>(len));
+    return id == TermDictionary::kNotFound ? -1 : static_cast<int64_t>(id);
+}
+int64_t dgpu_reader_term_bytes(DiagonIndexReader r, int64_t term_id, char* out, int64_t cap, int32_t* out_field) {
+    if (!r || term_id < 0 || term_id >= static_cast<int64_t>(as_reader(r)->index().dict.size())) { set_error("Invalid term id"); return -1; }
+    const HostIndex& ix = as_reader(r)->index();
+    const std::string t = ix.dict.term_bytes(static_cast<uint32_t>(term_id));
+    if (out && cap > 0) std::memcpy(out, t.data(), std::min<size_t>(t.size(), static_cast<size_t>(cap)));
+    if (out_field) *out_field = ix.dict.term_field(static_cast<uint32_t>(term_id));
+    return static_cast<int64_t>(t.size());
+}
+int dgpu_reader_dictionary_frozen(DiagonIndexReader r) {
+    if (!r) { set_error("Invalid reader"); return -1; }
+    return as_reader(r)->index().dict.frozen() ? 1 : 0;
+}
 int dgpu_reader_get_doc_freqs(DiagonIndexReader r, int64_t* out, int64_t n) {
     if (!r || !out) { set_error("Invalid arguments"); return -1; }
     auto& df = as_reader(r)->index().term_doc_freq;

@@ -3,8 +3,11 @@
 #include <ostream>
 
 #include <algorithm>
+#include <numeric>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -162,7 +165,102 @@ void TermDictionary::reserve(size_t n_terms) {
 
 void TermDictionary::grow() { reserve(std::max<size_t>(16, offsets_.size() * 2)); }
 
+uint64_t TermDictionary::pack8(const uint8_t* bytes, size_t len) {
+    uint64_t k = 0;
+    std::memcpy(&k, bytes, len);   // len <= 8; hosts are little-endian (the image format assumes it too)
+    return k;
+}
+
+uint32_t TermDictionary::slot_of(uint64_t h, uint32_t disp, uint32_t m) {
+    uint64_t z = (h ^ (static_cast<uint64_t>(disp) * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+    z ^= z >> 32;
+    return static_cast<uint32_t>(((z & 0xFFFFFFFFull) * m) >> 32);
+}
+
+// Hash-and-displace (Belazzougui, Botelho, Dietzfelbinger: "Hash, displace, and compress", ESA 2009, without the
+// compression step): terms are thrown into n / 4 buckets by the high half of their hash; buckets are placed largest
+// first, each trying displacements 0, 1, 2, ... until slot_of(h, d) sends all its terms to free slots.
+void TermDictionary::freeze() {
+    if (frozen_) return;
+    static const bool off = std::getenv("DGPU_DICT_NO_FREEZE") != nullptr;   // A/B switch: keep the open-addressing table
+    if (off) return;
+    const size_t n = offsets_.size();
+    const auto t_start = std::chrono::steady_clock::now();
+    disp_.clear();
+    ph_.clear();
+    if (n == 0 || n > 0x7FFFFFFFu) return;
+    const uint32_t nb = static_cast<uint32_t>(std::max<size_t>(1, n / 4));
+    std::vector<uint64_t> hs(n);
+    parallel_for(n, n < 65536 ? 1 : 0, [&](size_t b, size_t e, int) {
+        for (size_t id = b; id < e; ++id) hs[id] = hash(fields_[id], pool_.data() + offsets_[id], lengths_[id]);
+    });
+    auto bucket_of = [&](uint64_t h) { return static_cast<uint32_t>(((h >> 32) * nb) >> 32); };
+    std::vector<uint32_t> start(static_cast<size_t>(nb) + 1, 0), members(n);
+    for (size_t id = 0; id < n; ++id) ++start[bucket_of(hs[id]) + 1];
+    for (uint32_t b = 0; b < nb; ++b) start[b + 1] += start[b];
+    {
+        std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+        for (size_t id = 0; id < n; ++id) members[fill[bucket_of(hs[id])]++] = static_cast<uint32_t>(id);
+    }
+    std::vector<uint32_t> order(nb);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return start[a + 1] - start[a] > start[c + 1] - start[c]; });
+    for (uint32_t m = static_cast<uint32_t>(n + n / 4 + 1);; m += m / 8 + 1) {   // (a retry with more room: not seen in practice)
+        std::vector<uint32_t> disp(nb, 0);
+        std::vector<uint8_t> taken(m, 0);
+        std::vector<uint32_t> where;
+        bool ok = true;
+        for (uint32_t b : order) {
+            const uint32_t lo = start[b], hi = start[b + 1];
+            if (lo == hi) continue;
+            uint32_t d = 0;
+            for (;; ++d) {
+                if (d > (1u << 22)) { ok = false; break; }   // two terms with one 64-bit hash, or no room
+                where.clear();
+                bool fits = true;
+                for (uint32_t i = lo; i < hi && fits; ++i) {
+                    const uint32_t s = slot_of(hs[members[i]], d, m);
+                    fits = !taken[s] && std::find(where.begin(), where.end(), s) == where.end();
+                    where.push_back(s);
+                }
+                if (fits) break;
+            }
+            if (!ok) break;
+            disp[b] = d;
+            for (uint32_t s : where) taken[s] = 1;
+        }
+        if (!ok) {
+            if (m > 4 * n + 64) return;   // give up: find() keeps using the open-addressing table
+            continue;
+        }
+        ph_.assign(m, Slot{0, kNotFound, 0, 0});
+        for (size_t id = 0; id < n; ++id) {
+            Slot& sl = ph_[slot_of(hs[id], disp[bucket_of(hs[id])], m)];
+            const uint32_t len = lengths_[id];
+            sl.id = static_cast<uint32_t>(id);
+            sl.field = fields_[id];
+            sl.len = static_cast<uint16_t>(std::min<uint32_t>(len, 0xFFFFu));
+            sl.key = len <= 8 ? pack8(pool_.data() + offsets_[id], len) : offsets_[id];
+        }
+        disp_.swap(disp);
+        frozen_ = true;
+        if (std::getenv("DGPU_TRACE"))
+            std::fprintf(stderr, "[dgpu trace] dictionary frozen: %zu terms, %u buckets, %u slots, %.1f ms\n", n, nb, m,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+        return;
+    }
+}
+
 uint32_t TermDictionary::find(uint16_t field, const uint8_t* bytes, size_t len) const {
+    if (frozen_) {
+        const uint64_t h = hash(field, bytes, len);
+        const uint32_t nb = static_cast<uint32_t>(disp_.size());
+        const Slot& sl = ph_[slot_of(h, disp_[static_cast<uint32_t>(((h >> 32) * nb) >> 32)], static_cast<uint32_t>(ph_.size()))];
+        if (sl.id == kNotFound || sl.field != field) return kNotFound;
+        if (len <= 8) return (sl.len == len && sl.key == pack8(bytes, len)) ? sl.id : kNotFound;
+        if (sl.len != std::min<size_t>(len, 0xFFFFu) || lengths_[sl.id] != len) return kNotFound;
+        return std::memcmp(pool_.data() + sl.key, bytes, len) == 0 ? sl.id : kNotFound;
+    }
     if (slots_.empty()) return kNotFound;
     size_t m = slots_.size() - 1, s = hash(field, bytes, len) & m;
     while (uint32_t v = slots_[s]) {
@@ -177,6 +275,7 @@ uint32_t TermDictionary::find(uint16_t field, const uint8_t* bytes, size_t len) 
 uint32_t TermDictionary::find_or_add(uint16_t field, const uint8_t* bytes, size_t len) {
     uint32_t id = find(field, bytes, len);
     if (id != kNotFound) return id;
+    frozen_ = false;   // the term set changes: lookups go through the open-addressing table until the next freeze()
     if ((offsets_.size() + 1) * 2 > slots_.size()) grow();
     id = static_cast<uint32_t>(offsets_.size());
     offsets_.push_back(pool_.size());
@@ -270,6 +369,7 @@ void HostIndex::set_global_stats(int field, int64_t sum_total_term_freq, int64_t
 // (BM25Similarity.h:141-153); the translation unit is compiled with -ffp-contract=off.
 void HostIndex::finalize_tables() {
     stats_changed();
+    dict.freeze();   // the term set is complete: lookups go through the perfect hash from here on
     image.n_fields = static_cast<uint32_t>(fields.size());
     image.ktab.assign(static_cast<size_t>(image.n_fields) * DGPU_KTAB_SIZE, 0.0f);
     const float k1 = 1.2f, b = 0.75f;
@@ -849,6 +949,9 @@ void TermDictionary::write_to(std::ostream& out) const {
     img_put_vec(out, lengths_);
     img_put_vec(out, fields_);
     img_put_vec(out, pool_);
+    // the perfect hash, so that reopening builds nothing (empty when the dictionary is not frozen)
+    img_put_vec(out, frozen_ ? disp_ : std::vector<uint32_t>());
+    img_put_vec(out, frozen_ ? ph_ : std::vector<Slot>());
 }
 
 void TermDictionary::read_from(const uint8_t*& p, const uint8_t* end) {
@@ -864,6 +967,25 @@ void TermDictionary::read_from(const uint8_t*& p, const uint8_t* end) {
         if (offsets_[i] > pool_.size() || lengths_[i] > pool_.size() - offsets_[i]) bad_image("dictionary term out of range");
     for (uint32_t sl : slots_)
         if (sl > n) bad_image("dictionary slot out of range");
+    img_get_vec(p, end, disp_);
+    img_get_vec(p, end, ph_);
+    frozen_ = false;
+    if (!ph_.empty()) {
+        if (disp_.empty() || ph_.size() < n || ph_.size() > 0xFFFFFFFFull) bad_image("perfect hash sizes");
+        size_t used = 0;
+        for (const Slot& sl : ph_) {
+            if (sl.id == kNotFound) continue;
+            ++used;
+            if (sl.id >= n || sl.field != fields_[sl.id] || sl.len != std::min<uint32_t>(lengths_[sl.id], 0xFFFFu))
+                bad_image("perfect hash slot disagrees with the term arrays");
+            if (lengths_[sl.id] > 8 ? sl.key != offsets_[sl.id] : sl.key != pack8(pool_.data() + offsets_[sl.id], lengths_[sl.id]))
+                bad_image("perfect hash key disagrees with the term pool");
+        }
+        if (used != n) bad_image("perfect hash does not hold every term");
+        frozen_ = true;
+    } else if (!disp_.empty()) {
+        bad_image("perfect hash sizes");
+    }
 }
 
 uint64_t HostIndex::image_hash() const {
@@ -944,7 +1066,7 @@ void HostIndex::save_image(const std::string& path) const {
     for (const auto& c : image.dv) img_put_vec(out, c);
     const std::string body = out.str();
     file.write(kImageMagic, 8);
-    img_put_pod<uint32_t>(file, 2u);   // version
+    img_put_pod<uint32_t>(file, 3u);   // version (3: the dictionary's perfect hash is part of the image)
     img_put_pod<uint64_t>(file, body_hash(reinterpret_cast<const uint8_t*>(body.data()), body.size()));
     file.write(body.data(), static_cast<std::streamsize>(body.size()));
     file.flush();
@@ -964,7 +1086,7 @@ std::shared_ptr<HostIndex> HostIndex::load_image(const std::string& path) {
     const uint8_t* end = p + buf.size();
     if (std::memcmp(p, kImageMagic, 8) != 0) bad_image("not a DGPUIMG1 file");
     p += 8;
-    if (img_get_pod<uint32_t>(p, end) != 2u) bad_image("unsupported version");
+    if (img_get_pod<uint32_t>(p, end) != 3u) bad_image("unsupported version");
     const uint64_t want_hash = img_get_pod<uint64_t>(p, end);
     if (body_hash(p, static_cast<size_t>(end - p)) != want_hash) bad_image("content hash mismatch");
     auto ix = std::make_shared<HostIndex>();
@@ -997,6 +1119,7 @@ std::shared_ptr<HostIndex> HostIndex::load_image(const std::string& path) {
     img_get_vec(p, end, ix->term_total_term_freq);
     img_get_vec(p, end, ix->global_sum_ttf_override_);
     ix->dict.read_from(p, end);
+    ix->dict.freeze();   // (an image written before its dictionary was frozen)
     IndexImage& im = ix->image;
     img_get_vec(p, end, im.term_block_start);
     img_get_vec(p, end, im.block_first_doc);

@@ -40,12 +40,22 @@ struct SegmentMeta {
     bool is_local = true;
 };
 
-// Open-addressing term dictionary: (field id, term bytes) -> dense term id.
+// Term dictionary: (field id, term bytes) -> dense term id. It replaces the per-leaf seekExact of the reference
+// (TermQuery.cpp:231-247 -> BlockTreeTermsReader.cpp:582-683: a trie walk, a block load and a binary search per term,
+// leaf and query) by one lookup over all leaves. While an index is built it is an open-addressing table; freeze() then
+// builds a PERFECT HASH over the finished term set (hash-and-displace: a displacement per bucket of ~4 terms sends every
+// term to a slot of its own in a table at 80 % load), and a lookup is two memory touches - the bucket's displacement
+// (2 bits per term, cache-resident) and ONE 16-byte slot that holds the id and, for terms of up to 8 bytes, the term
+// itself, so that the compare needs no third touch.
 class TermDictionary {
 public:
     static constexpr uint32_t kNotFound = 0xFFFFFFFFu;
     uint32_t find(uint16_t field, const uint8_t* bytes, size_t len) const;
-    uint32_t find_or_add(uint16_t field, const uint8_t* bytes, size_t len);
+    uint32_t find_or_add(uint16_t field, const uint8_t* bytes, size_t len);   // (thaws the perfect hash)
+    // Builds the perfect hash (no-op when it is current). Not thread-safe against concurrent find(): called where the
+    // term set is complete (HostIndex::finalize_tables, load_image), before any search.
+    void freeze();
+    bool frozen() const { return frozen_; }
     uint32_t size() const { return static_cast<uint32_t>(offsets_.size()); }
     void reserve(size_t n_terms);
     std::string term_bytes(uint32_t id) const;
@@ -62,6 +72,19 @@ private:
     std::vector<uint32_t> lengths_;
     std::vector<uint16_t> fields_;
     std::vector<uint8_t> pool_;
+    // the frozen form
+    struct Slot {
+        uint64_t key;     // the term's bytes (little-endian, zero-padded) when len <= 8, else its offset in pool_
+        uint32_t id;      // kNotFound: empty
+        uint16_t field;
+        uint16_t len;     // 0xFFFF: longer than 65534 bytes, the length is in lengths_[id]
+    };
+    static_assert(sizeof(Slot) == 16, "one slot, one 16-byte touch");
+    static uint64_t pack8(const uint8_t* bytes, size_t len);
+    static uint32_t slot_of(uint64_t h, uint32_t disp, uint32_t m);
+    std::vector<uint32_t> disp_;   // per bucket
+    std::vector<Slot> ph_;
+    bool frozen_ = false;
 };
 
 class HostIndex {

@@ -145,6 +145,13 @@ DiagonIndexReader dgpu_open_synthetic(const dgpu_corpus_spec* spec, int device, 
 
 /* Statistics plumbing for sharded indexes (all ranks must agree on idf/avgdl). */
 int64_t dgpu_reader_num_terms(DiagonIndexReader reader);
+/* The term dictionary (one lookup over all leaves in place of TermsEnum::seekExact per leaf, TermQuery.cpp:231-247): a
+ * perfect hash over the finished term set (host_index.h). dgpu_reader_term_id: dense id of (field, term bytes), -1 when the
+ * index does not hold the term; dgpu_reader_term_bytes: the term of an id (returns its length, copies at most cap bytes);
+ * dgpu_reader_dictionary_frozen: 1 when lookups go through the perfect hash. */
+int64_t dgpu_reader_term_id(DiagonIndexReader reader, const char* field, const char* bytes, int64_t len);
+int64_t dgpu_reader_term_bytes(DiagonIndexReader reader, int64_t term_id, char* out, int64_t cap, int32_t* out_field);
+int dgpu_reader_dictionary_frozen(DiagonIndexReader reader);
 int dgpu_reader_get_doc_freqs(DiagonIndexReader reader, int64_t* out, int64_t n);           /* global df per term id */
 int dgpu_reader_set_doc_freqs(DiagonIndexReader reader, const int64_t* df, int64_t n);
 int dgpu_reader_get_field_totals(DiagonIndexReader reader, const char* field, int64_t* sum_total_term_freq, int64_t* max_doc);

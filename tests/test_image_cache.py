@@ -119,3 +119,59 @@ def test_search_through_a_reopened_image(g1_raw, golden_dir, tmp_path, k):
             assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, f"query {q}")
     finally:
         reader.close()
+
+
+def test_term_dictionary_is_a_perfect_hash(g1_raw, tmp_path):
+    """one lookup over all leaves in place of seekExact per leaf. After an index is built (and after
+    an image is reopened) lookups go through the perfect hash: every term of the index maps to its own id, terms the index
+    does not hold - same length, one byte changed, longer than 8 bytes, empty, in another field - map to nothing."""
+    a = dg.IndexReader.from_dump(g1_raw, -1)
+    path = str(tmp_path / "g1.img")
+    a.save_image(path)
+    b = dg.IndexReader.from_image(path, -1)
+    try:
+        for r in (a, b):
+            assert r.dictionary_frozen()
+            n = r.num_terms()
+            assert n >= 1000
+            seen = set()
+            for tid in range(n):
+                f, t = r.term_bytes(tid)
+                assert f == 0 and (f, t) not in seen
+                seen.add((f, t))
+                assert r.term_id("body", t) == tid
+                if tid % 7 == 0:   # near misses
+                    assert r.term_id("title", t) == -1
+                    flipped = bytes([t[0] ^ 0x80]) + t[1:]   # (the corpus' terms are ASCII)
+                    assert r.term_id("body", flipped) == -1
+                    assert r.term_id("body", t + b"x" * 9) == -1
+            assert r.term_id("body", b"") == -1
+            assert r.term_id("body", b"no-such-term-anywhere") == -1
+    finally:
+        a.close()
+        b.close()
+
+
+def test_long_terms_and_late_additions_in_the_dictionary():
+    """Terms of more than 8 bytes are compared in the term pool, shorter ones inside the slot; a reader built from several
+    segments sees the union of their terms."""
+    b = dg.IndexBuilder()
+    terms = [b"a", b"ab", b"abcdefgh", b"abcdefghi", b"abcdefgh" * 40, b"\x00", b"\x00\x00", b"zz"] + [b"w%05d" % i for i in range(3000)]
+    for seg in range(2):
+        s = b.add_segment(8, 8 * seg)
+        norms = np.full(8, 100, dtype=np.int8)
+        mine = terms[seg::2] + [b"shared"]
+        b.set_field_stats(s, "body", 4 * len(mine), 2 * len(mine), 8, norms)
+        for t in mine:
+            b.add_term(s, "body", t, np.array([1, 5], dtype=np.int32), np.array([1, 3], dtype=np.int32))
+    r = b.finish(-1)
+    try:
+        assert r.dictionary_frozen() and r.num_terms() == len(terms) + 1
+        ids = {t: r.term_id("body", t) for t in terms + [b"shared"]}
+        assert sorted(ids.values()) == list(range(len(terms) + 1))
+        for t, tid in ids.items():
+            assert r.term_bytes(tid) == (0, t)
+        for t in (b"abcdefg", b"abcdefghj", b"abcdefgh" * 39, b"abcdefgh" * 40 + b"!", b"\x00\x00\x00", b"w", b"w0300", b"w030000"):
+            assert r.term_id("body", t) == -1, t
+    finally:
+        r.close()
