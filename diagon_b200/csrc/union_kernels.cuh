@@ -103,6 +103,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
     sp += sizeof(uint32_t) * kUnionFilterWords;
     // a lane whose entry lies outside the window ORs 0 into a word of its own: no branch around the atomic
     const uint32_t idle_s = static_cast<uint32_t>(__cvta_generic_to_shared(sp)) + 4u * lane;
+    // ... as word indexes from the start of the bitmap (the filter and the idle words follow it)
+    const uint32_t filt_w = W / 32u, idle_w = W / 32u + kUnionFilterWords + static_cast<uint32_t>(lane);
     reinterpret_cast<uint32_t*>(sp)[lane] = 0u;
     sp += sizeof(uint32_t) * 32;
     volatile uint32_t* after_p = reinterpret_cast<volatile uint32_t*>(sp);
@@ -354,7 +356,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                             b[j] = in[j] ? __funnelshift_l(0u, 1u, r[j]) : 0u;   // 1 << (r & 31)
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) o[j] = atoms_or(in[j] ? seen_s + ((r[j] >> 3) & ~3u) : idle_s, b[j]);
+                        for (int j = 0; j < 4; ++j) o[j] = atomicOr(seen + (in[j] ? (r[j] >> 5) : idle_w), b[j]);
                         const uint32_t dup = (o[0] & b[0]) | (o[1] & b[1]) | (o[2] & b[2]) | (o[3] & b[3]);   // seen before in this window
                         // mode 2 looks at every first sighting (its filter value decides whether it is a hit); otherwise only
                         // chunks with a later sighting leave the straight path
@@ -405,10 +407,11 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                 for (int j = 0; j < 4; ++j) {
                                     // positions count the clause's entries in the window as hits: take the later sightings back
                                     if (!FILTER && single_ok) hits -= lt[j] ? 1u : 0u;
+                                    if (!__any_sync(0xFFFFFFFFu, lt[j])) continue;   // (a chunk has one or two later sightings as a rule)
                                     // every later sighting sets its doc's bit in the hashed filter (1024 bits: bit r mod 1024, in
                                     // the word (r / 32) mod 32, the same bit of the word as in the bitmap); a bit already set: the
                                     // doc may have been seen twice before
-                                    const bool t = (atoms_or(lt[j] ? filt_s + ((r[j] >> 3) & 124u) : idle_s, lt[j] ? b[j] : 0u) & b[j]) != 0u && lt[j];
+                                    const bool t = (atomicOr(seen + (lt[j] ? filt_w + ((r[j] >> 5) & (kUnionFilterWords - 1u)) : idle_w), lt[j] ? b[j] : 0u) & b[j]) != 0u && lt[j];
                                     if (keep3) {
                                         const bool rec = lt[j] && (t || keep2);
                                         const uint32_t m = __ballot_sync(0xFFFFFFFFu, rec);
