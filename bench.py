@@ -80,6 +80,7 @@ def parse_args():
     ap.add_argument("--pipeline-chunks", type=int, default=0, help="chunks of the end-to-end text call (1 = no host/device overlap)")
     ap.add_argument("--lane-ring-entries", type=int, default=0)
     ap.add_argument("--union-window-docs", type=int, default=0, help="docs per window (bits of shared memory) of union_topk_kernel")
+    ap.add_argument("--filter-stream", type=int, default=-1, help="0: range-filter values gathered per posting; 1 (default): streamed with the runs")
     ap.add_argument("--union-max-overlap", type=int, default=-1, help="percent of expected later sightings above which a query goes to staged_merge_topk_kernel")
     ap.add_argument("--cpu-sample-docs", type=int, default=200000)
     ap.add_argument("--cpu-sample-queries", type=int, default=0,
@@ -344,6 +345,8 @@ def main():
         reader.set_option("lane_merge", args.lane_merge)
     if args.union_window_docs:
         reader.set_option("union_window_docs", args.union_window_docs)
+    if args.filter_stream >= 0:
+        reader.set_option("filter_stream", args.filter_stream)
     if args.union_max_overlap >= 0:
         reader.set_option("union_max_overlap", args.union_max_overlap)
     if args.lane_ring_entries:

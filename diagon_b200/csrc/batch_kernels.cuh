@@ -170,6 +170,8 @@ struct RunArrays {
     float* scores;
     float* cmax;   // [entry / 64]
     float* bmax;   // [entry / 128]: the larger of a block's two chunk maxima
+    int32_t* dv;   // [entry]: the batch's filter column at the entry's doc (null: the batch has no single 32-bit filter column)
+    const int32_t* dv_col;   // that column, indexed by doc - doc_lo
 };
 
 template <bool AOS, bool SOA>
@@ -271,6 +273,14 @@ decode_score_kernel(DeviceIndex ix, const DTerm* __restrict__ dterms, const DIte
                 if ((lane & 15) == 0) out.cmax[e0 >> 6] = mx;
                 mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
                 if (lane == 0) out.bmax[e0 >> 7] = mx;
+                if (out.dv) {
+                    // the filter value of every posting's doc travels with the run: gathered here once per distinct term,
+                    // streamed (coalesced) by every query that holds the term instead of gathered per query and posting
+                    int32_t fv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) fv[q] = 4u * lane + q < n ? __ldg(out.dv_col + (doc[q] - ix.doc_lo)) : 0;
+                    *reinterpret_cast<int4*>(out.dv + e0) = make_int4(fv[0], fv[1], fv[2], fv[3]);
+                }
                 if (rel + 1 == nb) {
 #pragma unroll
                     for (int pb = 1; pb <= kPadBlocks; ++pb) {
@@ -307,6 +317,8 @@ struct AccumParams {
     const float* run_scores;    //   scores,
     const float* run_cmax;      //   maximum score of every 64 entries
     const float* run_bmax;      //   ... of every 128 entries (one block)
+    const int32_t* run_dv;      //   the batch's filter column at every entry's doc (null: gather per posting)
+    int32_t run_dv_col;         //   ... which column that is
     uint64_t run_total;         // entries allocated in `runs` (bounds checks)
     int k;
     uint32_t W;                 // docs per window (multiple of 32, <= 65536)

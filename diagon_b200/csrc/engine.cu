@@ -151,6 +151,9 @@ struct dgpu_engine {
     DevBuf<float> d_run_scores;         //   scores,
     DevBuf<float> d_run_cmax;           //   maximum score of every 64 entries
     DevBuf<float> d_run_bmax;           //   ... of every 128 entries
+    DevBuf<int32_t> d_run_dv;           //   the batch's filter column along the runs (run_dv_col >= 0)
+    int32_t run_dv_col = -1;            // the one 32-bit column every range filter of the staged batch uses, or -1
+    std::vector<const int32_t*> h_dv32; // device pointers of the narrowed columns (null: the column needs 64 bits)
     bool runs_aos = true, runs_soa = false;   // which layouts decode_score_kernel writes for the staged batch
     DevBuf<uint64_t> d_part_keys;
     DevBuf<int32_t> d_part_counts;
@@ -203,6 +206,7 @@ struct dgpu_engine {
     int lane_ring_entries = 2176;   // (doc, score) entries of shared memory per warp of staged_merge_topk_kernel
     int union_window_docs = 32768;  // docs per window (one bit each in shared memory) of union_topk_kernel
     uint64_t run_entry_limit = 0xFFFFFFFFull - 4096;   // entries the decode scratch of one batch may hold (32-bit positions)
+    int filter_stream = 1;          // 1: the batch's single 32-bit filter column travels with the runs (0: gathered per posting)
     int union_max_overlap = 15;     // lane_merge = 3: a query whose expected later sightings exceed this percentage of its
                                     // postings (dense terms on a small index) is merged in registers by staged_merge_topk_kernel
     int pipeline_chunks = 3;        // dgpu_search_batch_text stages chunk i + 1 while the kernels of chunk i run (1 = off)
@@ -311,7 +315,7 @@ void dgpu_engine_destroy(dgpu_engine* e) {
     e->d_queries.release(); e->d_terms.release(); e->d_filters.release(); e->d_order.release();
     e->d_counter.release(); e->d_keys.release(); e->d_counts.release(); e->d_hits.release();
     e->d_dterms.release(); e->d_items.release(); e->d_qruns.release(); e->d_runs.release();
-    e->d_run_docs.release(); e->d_run_scores.release(); e->d_run_cmax.release(); e->d_run_bmax.release();
+    e->d_run_docs.release(); e->d_run_scores.release(); e->d_run_cmax.release(); e->d_run_bmax.release(); e->d_run_dv.release();
     e->d_part_keys.release(); e->d_part_counts.release(); e->d_part_hits.release();
     e->d_witems.release(); e->d_part_off.release(); e->d_pool.release();
     e->d_packed.release(); e->d_gathered.release();
@@ -371,6 +375,11 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
     if (!std::strcmp(name, "splits")) {
         if (value < 0 || value > 64) return fail("splits must be in [0, 64]");
         e->force_splits = static_cast<int>(value);
+        return 0;
+    }
+    if (!std::strcmp(name, "filter_stream")) {
+        if (value < 0 || value > 1) return fail("filter_stream must be 0 or 1");
+        e->filter_stream = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "batch_share_permille")) {
@@ -488,6 +497,7 @@ int dgpu_engine_upload(dgpu_engine* e, const dgpu_index_image* im) {
     e->owned.push_back(dcols32);
     if (!cols32.empty()) CU(cudaMemcpy(dcols32, cols32.data(), cols32.size() * sizeof(int32_t*), cudaMemcpyHostToDevice));
     e->ix.dv32 = static_cast<const int32_t* const*>(dcols32);
+    e->h_dv32 = cols32;
     e->ix.doc_lo = im->doc_lo;
     e->ix.doc_hi = im->doc_hi;
     return 0;
@@ -504,6 +514,7 @@ int dgpu_engine_sync_options(dgpu_engine* dst, const dgpu_engine* src) {
     dst->warps_per_sm = src->warps_per_sm;
     dst->max_parts = src->max_parts;
     dst->part_factor = src->part_factor;
+    dst->filter_stream = src->filter_stream;
     dst->decode_ctas_per_sm = src->decode_ctas_per_sm;
     dst->intersect = src->intersect;
     dst->lane_merge = src->lane_merge;
@@ -529,6 +540,7 @@ int dgpu_engine_create_shadow(dgpu_engine* primary, dgpu_engine** out) {
     e->n_blocks = primary->n_blocks;
     e->n_fields = primary->n_fields;
     e->n_dv = primary->n_dv;
+    e->h_dv32 = primary->h_dv32;
     e->h_term_block_start = primary->h_term_block_start;
     e->h_block_meta = primary->h_block_meta;
     e->h_block_off = primary->h_block_off;
@@ -606,6 +618,15 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
     e->n_queries = b->n_queries;
     e->k = k;
     e->batch_filters = b->n_filters;
+    // one 32-bit column behind every range filter of the batch (the C4 shape): its values are written along the runs by
+    // decode_score_kernel and streamed by union_topk_kernel (option filter_stream = 0: gathered per posting)
+    e->run_dv_col = -1;
+    if (b->n_filters && e->filter_stream) {
+        const int32_t c0 = b->filters[0].column;
+        bool same = c0 >= 0 && static_cast<uint32_t>(c0) < e->n_dv && static_cast<size_t>(c0) < e->h_dv32.size() && e->h_dv32[static_cast<size_t>(c0)] != nullptr;
+        for (uint32_t f = 1; f < b->n_filters && same; ++f) same = b->filters[f].column == c0;
+        if (same) e->run_dv_col = c0;
+    }
     static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
     auto tr0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -949,6 +970,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             if (ce == cudaSuccess) ce = e->d_run_scores.ensure(cap);
             if (ce == cudaSuccess) ce = e->d_run_cmax.ensure(cap / 64 + 64);
             if (ce == cudaSuccess) ce = e->d_run_bmax.ensure(cap / 128 + 64);
+            if (ce == cudaSuccess && e->run_dv_col >= 0) ce = e->d_run_dv.ensure(cap);
         }
         if (ce != cudaSuccess)
             return fail("cannot allocate %zu MB of decode scratch (%s); split the batch", cap * 8 >> 20, cudaGetErrorString(ce));
@@ -1141,6 +1163,8 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     P.run_scores = e->d_run_scores.p;
     P.run_cmax = e->d_run_cmax.p;
     P.run_bmax = e->d_run_bmax.p;
+    P.run_dv = e->run_dv_col >= 0 ? e->d_run_dv.p : nullptr;
+    P.run_dv_col = e->run_dv_col;
     P.run_total = e->runs_soa ? e->d_run_docs.cap : e->d_runs.cap;
     P.k = e->k;
     P.max_terms = (e->max_terms + 3u) & ~3u;
@@ -1165,7 +1189,9 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
     CU(cudaEventRecord(e->ev0, stream));
     if (e->n_ditems) {
         const int grid = static_cast<int>(std::min<uint64_t>(e->n_ditems, static_cast<uint64_t>(e->sm_count) * e->decode_ctas_per_sm));
-        const RunArrays out{e->d_runs.p, e->d_run_docs.p, e->d_run_scores.p, e->d_run_cmax.p, e->d_run_bmax.p};
+        const bool with_dv = e->runs_soa && e->run_dv_col >= 0;
+        const RunArrays out{e->d_runs.p, e->d_run_docs.p, e->d_run_scores.p, e->d_run_cmax.p, e->d_run_bmax.p,
+                            with_dv ? e->d_run_dv.p : nullptr, with_dv ? e->h_dv32[static_cast<size_t>(e->run_dv_col)] : nullptr};
         auto dk = e->runs_soa ? (e->runs_aos ? decode_score_kernel<true, true> : decode_score_kernel<false, true>)
                               : decode_score_kernel<true, false>;
         // on the engine's own stream the decode runs at high priority: when another engine's scoring kernel fills the GPU

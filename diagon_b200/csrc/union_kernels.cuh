@@ -86,7 +86,8 @@ __device__ __forceinline__ uint32_t opaque(uint32_t v) {
 }
 
 template <int MODE, bool BIGK>
-__global__ void __launch_bounds__(32 * kUnionWarps, 32)   // <= 64 registers: 32 one-warp CTAs per SM
+__global__ void __launch_bounds__(32 * kUnionWarps, MODE == 2 ? 24 : 32)   // <= 64 registers: 32 one-warp CTAs per SM (mode 2: 80, for
+                                                                           // the streamed filter values; its pools leave 24-28 CTAs anyway)
 union_topk_kernel(DeviceIndex ix, AccumParams P) {
     constexpr bool NEED_CNT = MODE >= 1;
     constexpr bool FILTER = MODE == 2;
@@ -204,6 +205,10 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
         }
         // the score bound on later sightings holds for plain disjunctions of non-negative scores
         const bool bounded = single_mask == 0xFFFFFFFFu && __all_sync(0xFFFFFFFFu, idf_ok);
+        // mode 2: the query's one range filter is on the column whose values decode_score_kernel wrote along the runs - they
+        // are streamed with the doc ids (coalesced) instead of gathered per posting (one L1 wavefront each)
+        const bool dv_stream = FILTER && nf == 1u && dv0n != nullptr && P.run_dv != nullptr && qf[0].column == P.run_dv_col;
+        const int32_t* __restrict__ rdv = P.run_dv;
 
         uint32_t n_cand = 0;        // entries of the pool (warp-uniform)
         uint64_t thresh = 0;        // key of the k-th best so far
@@ -290,6 +295,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
             int pf_u = -1;       // clause whose first chunk has been prefetched into pf_d / pf_cm
             uint4 pf_d = make_uint4(0u, 0u, 0u, 0u);
             float pf_cm = 0.0f;
+            int4 pf_v = make_int4(0, 0, 0, 0);   // (mode 2, dv_stream) the filter values of that chunk's docs
+            auto load_vals = [&](uint32_t at, int4& vv) { vv = __ldg(reinterpret_cast<const int4*>(rdv + at) + lane); };
             // the docs of a chunk (this lane's four) and the larger of its two chunk maxima
             auto load_chunk = [&](uint32_t at, uint4& dd, float& mx) {
                 dd = __ldg(reinterpret_cast<const uint4*>(docs + at) + lane);
@@ -302,6 +309,7 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                 while (!full) {
                     uint4 d;
                     float cm;
+                    int4 v = make_int4(0, 0, 0, 0);
                     if (u < 0) {
                         if (!act) break;
                         u = __ffs(act) - 1;
@@ -311,15 +319,20 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         if (pf_u == u) {
                             d = pf_d;
                             cm = pf_cm;
+                            if (FILTER) v = pf_v;
                         } else {
                             load_chunk(c, d, cm);
+                            if (FILTER && dv_stream) load_vals(c, v);
                         }
                         if (act) {   // the first chunk of the next clause is on its way while this one is streamed
                             pf_u = __ffs(act) - 1;
-                            load_chunk(__shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u), pf_d, pf_cm);
+                            const uint32_t pc = __shfl_sync(0xFFFFFFFFu, pos, pf_u) & ~(kUnionChunk - 1u);
+                            load_chunk(pc, pf_d, pf_cm);
+                            if (FILTER && dv_stream) load_vals(pc, pf_v);
                         }
                     } else {   // resumed after a resolve in the middle of a clause
                         load_chunk(c, d, cm);
+                        if (FILTER && dv_stream) load_vals(c, v);
                     }
                     const bool single_ok = !NEED_CNT || ((single_mask >> u) & 1u);
                     const uint32_t meta_u = static_cast<uint32_t>(u) << 25;
@@ -332,15 +345,17 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) fv[j] = (x[j] - ws < wlen) ? __ldg(dv0n + x[j]) : 0;
                     };
-                    if (FILTER && ahead) gather_ahead(d);
+                    if (FILTER && ahead && !dv_stream) gather_ahead(d);
                     for (;;) {
                         DGPU_ASSERT(static_cast<uint64_t>(c) + 2 * kUnionChunk <= P.run_total);
                         // sorted run: the chunk's last entry tells whether the clause goes on inside this window
                         const bool more = __shfl_sync(0xFFFFFFFFu, d.w, 31) - ws < wlen;
                         uint4 dn = make_uint4(0u, 0u, 0u, 0u);
                         float cmn = 0.0f;
+                        int4 vn = make_int4(0, 0, 0, 0);
                         if (more) {
                             load_chunk(c + kUnionChunk, dn, cmn);
+                            if (FILTER && dv_stream) load_vals(c + kUnionChunk, vn);
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(docs + c + 3u * kUnionChunk) + lane));
                         }
                         wm = fmaxf(wm, cm);
@@ -373,6 +388,12 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                 for (int j = 0; j < 4; ++j) nw[j] = in[j] && !lt[j];
                                 if (nf) {
                                     if (dv0n) {
+                                        if (dv_stream) {
+                                            fv[0] = v.x;
+                                            fv[1] = v.y;
+                                            fv[2] = v.z;
+                                            fv[3] = v.w;
+                                        }
 #pragma unroll
                                         for (int j = 0; j < 4; ++j) nw[j] = nw[j] && fv[j] >= lo0n && fv[j] <= hi0n;
                                     } else {
@@ -459,7 +480,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                         c += kUnionChunk;
                         d = dn;
                         cm = cmn;
-                        if (FILTER && ahead) gather_ahead(d);
+                        if (FILTER) v = vn;
+                        if (FILTER && ahead && !dv_stream) gather_ahead(d);
                         if (full) break;
                     }
                 }

@@ -77,7 +77,7 @@ def test_search_matches_reference_golden(readers, golden_dir, name, k):
 # scored by the windows whatever lane_merge says
 _DEFAULTS = {"window_docs": 0, "stage_log2": 0, "splits": 0, "warps": 4, "warps_per_sm": 20, "intersect": 1,
              "lane_merge": 3, "lane_ring_entries": 2176, "union_window_docs": 32768, "lane_ctas_per_sm": 0,
-             "union_max_overlap": 15}
+             "union_max_overlap": 15, "filter_stream": 1}
 _TUNINGS = [
     dict(lane_merge=0, warps_per_sm=16),
     dict(lane_merge=0, window_docs=1024, splits=1, warps_per_sm=16, intersect=0),
@@ -100,6 +100,9 @@ _TUNINGS = [
     dict(lane_merge=3, union_max_overlap=100000, union_window_docs=65536, splits=16, lane_ctas_per_sm=2),
     dict(lane_merge=3, union_max_overlap=100000, union_window_docs=4096, window_docs=512),
     dict(lane_merge=3, union_max_overlap=0, splits=2),   # ... and none of them
+    dict(filter_stream=0),                                # range-filter values gathered per posting, not streamed with the runs
+    dict(filter_stream=0, union_max_overlap=100000, splits=3, union_window_docs=2048),
+    dict(filter_stream=1, union_max_overlap=100000, splits=5, union_window_docs=512),
 ]
 
 
