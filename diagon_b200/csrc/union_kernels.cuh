@@ -509,6 +509,8 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                 const uint32_t cc = cb + kMaxChunk * l;
                                 const uint2 dd = __ldg(reinterpret_cast<const uint2*>(docs + cc) + lane);
                                 const float2 ss = __ldg(reinterpret_cast<const float2*>(scores + cc) + lane);
+                                int2 vv = make_int2(0, 0);   // (mode 2, dv_stream) the filter values of the two docs
+                                if (FILTER && dv_stream) vv = __ldg(reinterpret_cast<const int2*>(rdv + cc) + lane);
 #pragma unroll
                                 for (int j = 0; j < 2; ++j) {
                                     const uint32_t doc = j ? dd.y : dd.x;
@@ -519,7 +521,10 @@ union_topk_kernel(DeviceIndex ix, AccumParams P) {
                                     const uint32_t r = doc - ws;
                                     // inside the window, not looked at before (a resumed clause), able to enter the pool
                                     bool cnd = r < wlen && cc + 2u * lane + j >= c0 && sc >= thresh_f;
-                                    if (FILTER && nf && cnd) cnd = passes(doc);
+                                    if (FILTER && nf && cnd) {
+                                        const int32_t fval = j ? vv.y : vv.x;
+                                        cnd = dv_stream ? (fval >= lo0n && fval <= hi0n) : passes(doc);
+                                    }
                                     const bool again = cnd && ((filt[(r >> 5) & (kUnionFilterWords - 1u)] >> (r & 31u)) & 1u) != 0u;
                                     collect(doc, sc, cnd && !again);
                                     const uint32_t ma = __ballot_sync(0xFFFFFFFFu, again);
