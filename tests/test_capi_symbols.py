@@ -65,6 +65,22 @@ def test_no_cpu_fallback_without_gpu():
 
     with pytest.raises(DiagonError):
         IndexReader.synthetic(named_corpus("C1", 0.01), 0)
+    # a host-only reader (device -1) compiles queries and answers dictionary questions; every search entry point refuses
+    from diagon_b200 import IndexSearcher
+
+    r = IndexReader.synthetic(named_corpus("C1", 0.01), -1)
+    try:
+        s = IndexSearcher(r)
+        assert r.dictionary_frozen() and r.num_terms() > 0
+        line = b"OR body 0 " + r.term_bytes(0)[1] + b"\n"
+        assert s.compile_batch_text(line).size > 0
+        with pytest.raises(DiagonError, match="no CPU fallback"):
+            s.search_batch_text(line, 10)
+        with pytest.raises(DiagonError, match="no CPU fallback"):
+            s.submit_batch_text(line, 10)
+        s.close()
+    finally:
+        r.close()
 
 
 def test_query_objects_round_trip_through_the_c_abi():
