@@ -970,8 +970,9 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
             if (ce == cudaSuccess) ce = e->d_run_scores.ensure(cap);
             if (ce == cudaSuccess) ce = e->d_run_cmax.ensure(cap / 64 + 64);
             if (ce == cudaSuccess) ce = e->d_run_bmax.ensure(cap / 128 + 64);
-            if (ce == cudaSuccess && e->run_dv_col >= 0) ce = e->d_run_dv.ensure(cap);
         }
+        // (its own test: batches without range filters grow the arrays above and leave this one behind)
+        if (ce == cudaSuccess && e->runs_soa && e->run_dv_col >= 0 && want > e->d_run_dv.cap) ce = e->d_run_dv.ensure(cap);
         if (ce != cudaSuccess)
             return fail("cannot allocate %zu MB of decode scratch (%s); split the batch", cap * 8 >> 20, cudaGetErrorString(ce));
         if (e->runs_aos) CU(cudaMemsetAsync(e->d_runs.p, 0xFF, sizeof(uint2) * kRunPad, e->stream));

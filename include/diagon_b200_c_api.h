@@ -185,7 +185,8 @@ int dgpu_search_batch_text(DiagonIndexSearcher searcher, const char* text, int64
  * batches in flight) and returns a ticket, NULL on error; dgpu_collect_batch waits, copies the results out (same layout
  * as dgpu_search_batch_text) and frees the ticket, also when it fails; dgpu_batch_ticket_free abandons a batch. While
  * tickets are outstanding the synchronous calls of the same reader fail ("collect them first"). Results are those of
- * dgpu_search_batch_text. Sharded searchers: dgpu_sharded_submit_batch_text below. */
+ * dgpu_search_batch_text. Collect or free every ticket before the searcher or its reader is freed. Sharded searchers:
+ * dgpu_sharded_submit_batch_text below. */
 typedef void* DgpuBatchTicket;
 DgpuBatchTicket dgpu_submit_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, int32_t k);
 int32_t dgpu_batch_ticket_queries(DgpuBatchTicket ticket);

@@ -583,6 +583,40 @@ def test_submitted_batches_in_flight_equal_the_synchronous_call(readers, golden_
     assert len(empty) == 0 and len(empty.collect().counts) == 0
 
 
+def test_filter_column_scratch_follows_the_runs(g1_dump, golden_dir):
+    """The filter values that travel with the runs have a scratch array of their own; batches without range filters grow the
+    other run arrays and leave it behind. Small filter batch, large plain batch, large filter batch on one fresh reader: the
+    last one must find room for its values (and give the results of the per-posting gather)."""
+    from diagon_b200.dumpfile import build_reader_from_dump
+
+    lines = open(os.path.join(golden_dir, "g1_queries.txt"), "rb").read().strip().split(b"\n")
+    filt = [l for l in lines if l.startswith(b"ORF") or l.startswith(b"ANDF")]
+    plain = [l for l in lines if l.startswith(b"OR ") or l.startswith(b"TERM")]
+    assert len(filt) >= 10 and len(plain) >= 50
+    small = b"\n".join(filt[:1]) + b"\n"
+    big_plain = b"\n".join(plain) + b"\n"
+    # many distinct terms behind range filters: every plain disjunction with the filter of some ORF line in front
+    head = filt[0].split()[:5]    # ORF field column lo hi
+    big_filt = b"\n".join(b" ".join(head + l.split()[3:]) for l in plain if l.startswith(b"OR ")) + b"\n"
+    ref = build_reader_from_dump(g1_dump, 0)
+    try:
+        ref.set_option("filter_stream", 0)
+        want = dg.IndexSearcher(ref).search_batch_text(big_filt, 10)
+    finally:
+        ref.close()
+    r = build_reader_from_dump(g1_dump, 0)
+    try:
+        s = dg.IndexSearcher(r)
+        s.search_batch_text(small, 10)
+        s.search_batch_text(big_plain, 10)
+        got = s.search_batch_text(big_filt, 10)
+        assert np.array_equal(got.docs, want.docs) and np.array_equal(got.scores, want.scores)
+        assert np.array_equal(got.total_hits, want.total_hits) and np.array_equal(got.counts, want.counts)
+        assert int(want.total_hits.sum()) > 0
+    finally:
+        r.close()
+
+
 def test_staging_compiled_slices_equals_one_call(readers, golden_dir):
     """dgpu_compile_batch_text on slices + dgpu_stage_compiled (how the ranks of a sharded index divide the host work)
     gives the same results as dgpu_search_batch_text on the whole batch."""
