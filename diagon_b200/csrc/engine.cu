@@ -1241,10 +1241,19 @@ static int launch_batched(dgpu_engine* e, cudaStream_t stream) {
         Q.order = e->d_order.p + e->n_acc_items + e->n_lane_items + e->n_union_items;
         Q.n_items = e->n_and_items;
         Q.work_counter = e->d_counter.p + 1;
-        CU(cudaFuncSetAttribute(intersect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        const uint64_t want_ctas = (static_cast<uint64_t>(Q.n_items) + e->plan_wpc - 1) / e->plan_wpc;
-        const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * e->plan_ctas, want_ctas));
-        intersect_topk_kernel<<<grid, e->plan_wpc * 32, smem, stream>>>(e->ix, Q);
+        // the intersection keeps nothing but its candidate pool in shared memory: its own layout, as many warps per SM as
+        // registers allow (its probes are dependent random loads - more warps is what hides them)
+        constexpr int kAndWpc = 4;
+        Q.warp_smem = static_cast<uint32_t>(std::max<size_t>(16, ((e->plan_pool_global ? 0u : e->plan_cap) * sizeof(uint64_t) + 15) & ~static_cast<size_t>(15)));
+        const size_t and_smem = static_cast<size_t>(Q.warp_smem) * kAndWpc;
+        if (and_smem > 48 * 1024)
+            CU(cudaFuncSetAttribute(intersect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(and_smem)));
+        int and_per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&and_per_sm, intersect_topk_kernel, kAndWpc * 32, and_smem));
+        and_per_sm = std::max(1, std::min(and_per_sm, 64 / kAndWpc));   // (the global pool is sized for 64 warps per SM)
+        const uint64_t want_ctas = (static_cast<uint64_t>(Q.n_items) + kAndWpc - 1) / kAndWpc;
+        const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * and_per_sm, want_ctas));
+        intersect_topk_kernel<<<grid, kAndWpc * 32, and_smem, stream>>>(e->ix, Q);
         CU(cudaGetLastError());
         e->launches++;
     }
