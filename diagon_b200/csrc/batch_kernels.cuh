@@ -673,7 +673,7 @@ accumulate_topk_kernel(DeviceIndex ix, AccumParams P) {
 // the remaining terms. Hits are candidates found in every list (and passing the range filters); they go straight
 // into the top-k pool: no accumulator window, no harvest.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(128, 16)   // <= 32 registers: 64 warps per SM (the probes are dependent random loads)
 intersect_topk_kernel(DeviceIndex ix, AccumParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
