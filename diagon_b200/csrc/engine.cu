@@ -192,8 +192,6 @@ struct dgpu_engine {
     int stage_log2 = 0;      // 0 = automatic; else an upper bound on log2 of the staged entries per term (tests)
     int warps_per_sm = 20;   // independent scoring warps per SM (each owns 1/n of the shared memory)
     int max_parts = 0;       // 0 = automatic; else doc-range parts per query are capped at this (1 = never split)
-    int batch_share_permille = 1000;   // the staged batch is this share of the work the GPU has in flight (a chunk of a pipelined
-                                       // call: its neighbours run beside it, so it is cut into parts as the whole call would be)
     int part_factor = 0;     // a query is cut into doc-range parts when it costs more than 1/part_factor of a warp's fair share
                              // (0 = by kernel: 1 for batches of union_topk items - 32 warps per SM already -, 2 otherwise)
     int decode_ctas_per_sm = 64; // grid of decode_score_kernel (grid-stride over the decode work items)
@@ -380,11 +378,6 @@ int dgpu_engine_set_option(dgpu_engine* e, const char* name, int64_t value) {
     if (!std::strcmp(name, "filter_stream")) {
         if (value < 0 || value > 1) return fail("filter_stream must be 0 or 1");
         e->filter_stream = static_cast<int>(value);
-        return 0;
-    }
-    if (!std::strcmp(name, "batch_share_permille")) {
-        if (value < 1 || value > 1000) return fail("batch_share_permille must be in [1, 1000]");
-        e->batch_share_permille = static_cast<int>(value);
         return 0;
     }
     if (!std::strcmp(name, "part_factor")) {
@@ -854,8 +847,7 @@ int dgpu_engine_stage_batch(dgpu_engine* e, const dgpu_query_batch* b, int32_t k
         const uint64_t n_warps = static_cast<uint64_t>(e->sm_count) *
                                  (mostly_union ? 32u : static_cast<uint32_t>(e->plan_ctas * e->plan_wpc));
         const uint64_t part_factor = e->part_factor ? static_cast<uint64_t>(e->part_factor) : (mostly_union ? 1u : 2u);
-        const uint64_t in_flight = total_cost * 1000u / static_cast<uint64_t>(e->batch_share_permille);
-        const uint64_t target = std::max<uint64_t>(64, in_flight / (n_warps * part_factor) + 1);   // posting blocks per item
+        const uint64_t target = std::max<uint64_t>(64, total_cost / (n_warps * part_factor) + 1);   // posting blocks per item
         // every part keeps its own top-k and the merge compares all pairs of parts: large k gets fewer parts
         const uint32_t cap_parts = e->max_parts ? static_cast<uint32_t>(e->max_parts)
                                                 : std::max(2u, std::min(64u, 4096u / static_cast<uint32_t>(k)));
