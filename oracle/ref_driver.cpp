@@ -35,6 +35,7 @@
 #include "diagon/search/IndexSearcher.h"
 #include "diagon/search/NumericRangeQuery.h"
 #include "diagon/search/TermQuery.h"
+#include "diagon/search/TopScoreDocCollector.h"
 #include "diagon/store/FSDirectory.h"
 #include "diagon/store/MMapDirectory.h"
 #include "diagon/util/BitPacking.h"
@@ -314,6 +315,11 @@ int cmd_search(const Args& a) {
     int threads = static_cast<int>(a.integer("threads", 1));
     int repeat = static_cast<int>(a.integer("repeat", 1));
     int warmup = static_cast<int>(a.integer("warmup", 0));
+    // --after-doc D [--after-score S]: pagination as the reference spells it - TopScoreDocCollector::create(k, after) +
+    // IndexSearcher::search(query, collector) (TopScoreDocCollector.h:69, IndexSearcher.h:255)
+    const bool paged = a.has("after-doc");
+    const int afterDoc = static_cast<int>(a.integer("after-doc", -1));
+    const float afterScore = static_cast<float>(std::atof(a.get("after-score", "0").c_str()));
     if (threads < 1) threads = 1;
     std::vector<Result> results(lines.size());
     std::vector<double> perThreadSec(static_cast<size_t>(threads), 0.0);
@@ -338,7 +344,14 @@ int cmd_search(const Args& a) {
             auto t0 = std::chrono::steady_clock::now();
             for (size_t q = next.fetch_add(1); q < lines.size(); q = next.fetch_add(1)) {
                 auto query = parse_query(lines[q]);  // rebuilt each time, like reuters_benchmark.cpp:321-356
-                search::TopDocs td = searcher.search(*query, k);
+                search::TopDocs td;
+                if (paged) {
+                    auto collector = search::TopScoreDocCollector::create(k, search::ScoreDoc(afterDoc, afterScore));
+                    searcher.search(*query, collector.get());
+                    td = collector->topDocs();
+                } else {
+                    td = searcher.search(*query, k);
+                }
                 if (rep == repeat - 1) {
                     Result& r = results[q];
                     r.hits = td.totalHits.value;

@@ -487,6 +487,20 @@ def test_search_after_pagination(readers, g1_dump):
             r.set_option(o, v)
 
 
+@pytest.mark.parametrize("after_doc", [17, 1500, 3900])
+def test_search_after_matches_reference_golden(readers, golden_dir, after_doc):
+    """dgpu_search_after against the pages the reference itself returned (tests/golden/g1_k10_after*.res: its
+    TopScoreDocCollector::create(k, after) + IndexSearcher::search(query, collector), exhaustive mode), bit for bit."""
+    lines = read_lines(os.path.join(golden_dir, "g1_queries.txt"))
+    kk, ref = read_results(os.path.join(golden_dir, f"g1_k10_after{after_doc}.res"))
+    assert kk == 10 and len(ref) == len(lines)
+    s = dg.IndexSearcher(readers["g1"])
+    for line, (hits, rel, docs) in zip(lines, ref):
+        td = s.search_after(api.ScoreDoc(after_doc, 1.0), api.parse_line(line), 10)
+        got = [(x.doc, np.float32(x.score)) for x in td.scoreDocs]
+        assert_same_topdocs(td.totalHits.value, got, hits, docs, f"after {after_doc}: {line[:60]}")
+
+
 def test_segment_without_the_filter_column_matches_nothing(g1_dump):
     """A range clause has no scorer in a segment that lacks the doc-values column (NumericRangeQuery.cpp:225-228), so no doc
     of that segment passes the filter - even when the range holds 0, the value the reference's reader reports for a

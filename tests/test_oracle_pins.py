@@ -32,6 +32,25 @@ def test_oracle_reproduces_reference_exhaustive(golden_dir, name, k, g1_dump, g2
         assert_same_topdocs(h, sd, hits, docs, line[:60])
 
 
+@pytest.mark.parametrize("after_doc", [17, 1500, 3900])
+def test_pagination_rule_reproduces_reference_search_after(golden_dir, after_doc, g1_dump):
+    """searchAfter as the reference runs it (TopScoreDocCollector::create(k, after) + search(query, collector), results in
+    tests/golden/g1_k10_after*.res, made by make_golden_after.py): every hit is counted, the docs whose id is not above
+    after.doc never compete. The rule applied to the oracle's full ranking must give the reference's pages bit for bit -
+    it is the expectation the GPU tests use."""
+    ox = orc.OracleIndex(g1_dump)
+    lines = read_lines(os.path.join(golden_dir, "g1_queries.txt"))
+    kk, ref = read_results(os.path.join(golden_dir, f"g1_k10_after{after_doc}.res"))
+    assert kk == 10 and len(ref) == len(lines)
+    pages = 0
+    for line, (hits, rel, docs) in zip(lines, ref):
+        h, full, _ = ox.search(api.parse_line(line), g1_dump.max_doc)
+        page = [(d, sc) for d, sc in full if d > after_doc][:10]
+        assert_same_topdocs(h, page, hits, docs, f"after {after_doc}: {line[:60]}")
+        pages += 1 if docs else 0
+    assert pages > 100
+
+
 @pytest.mark.parametrize("name", ["g1", "g2"])
 def test_reference_default_mode_is_consistent_with_exhaustive(golden_dir, name, g1_dump, g2_dump):
     """The reference's DEFAULT path (MaxScore/WAND pruning) is not a usable oracle: on these small corpora it
