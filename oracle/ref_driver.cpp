@@ -116,6 +116,7 @@ int cmd_index(const Args& a) {
     config.setRAMBufferSizeMB(1e6);
     uint32_t perSeg = (last - first + spec.num_segments - 1) / spec.num_segments;
     config.setMaxBufferedDocs(static_cast<int>(perSeg));
+    const long long skipPriceSeg = a.integer("price-skip-segment", -1);
     auto policy = std::make_unique<index::TieredMergePolicy>();
     policy->setSegmentsPerTier(1e9);  // keep the flushed segments as they are
     config.setMergePolicy(std::move(policy));
@@ -134,7 +135,9 @@ int cmd_index(const Args& a) {
             }
             document::Document doc;
             doc.add(std::make_unique<document::TextField>("body", text));
-            if (spec.with_price)
+            // --price-skip-segment S: the docs of segment S carry no "price" value, so that segment has no such column
+            // (mixed schema: what NumericRangeQuery does there is pinned by tests/golden/g1_mixed_*.res)
+            if (spec.with_price && static_cast<long long>((d - first) / perSeg) != skipPriceSeg)
                 doc.add(std::make_unique<document::NumericDocValuesField>("price", corpus.price(d)));
             writer.addDocument(doc);
         }

@@ -501,7 +501,7 @@ def test_search_after_matches_reference_golden(readers, golden_dir, after_doc):
         assert_same_topdocs(td.totalHits.value, got, hits, docs, f"after {after_doc}: {line[:60]}")
 
 
-def test_segment_without_the_filter_column_matches_nothing(g1_dump):
+def test_segment_without_the_filter_column_matches_nothing(g1_dump, golden_dir):
     """A range clause has no scorer in a segment that lacks the doc-values column (NumericRangeQuery.cpp:225-228), so no doc
     of that segment passes the filter - even when the range holds 0, the value the reference's reader reports for a
     missing doc inside a segment that does have the column. The golden corpus with the column taken out of its middle
@@ -530,6 +530,13 @@ def test_segment_without_the_filter_column_matches_nothing(g1_dump):
                 assert_same_topdocs(int(res.total_hits[q]), got, h, sd, line[:60])
                 lo, hi = dump.segments[1].doc_base, dump.segments[1].doc_base + dump.segments[1].max_doc
                 assert not [d for d, _ in got if lo <= d < hi], "a doc of the segment without the column passed the filter"
+        # ... and against the reference itself over such an index (tests/golden/make_golden_mixed.py)
+        mixed = read_lines(os.path.join(golden_dir, "g1_mixed_queries.txt"))
+        kk, ref = read_results(os.path.join(golden_dir, "g1_mixed_k10.res"))
+        res = searcher.search_batch_text(("\n".join(mixed) + "\n").encode(), kk)
+        for q, (line, (hits, rel, docs)) in enumerate(zip(mixed, ref)):
+            got = [(int(res.docs[q, i]), res.scores[q, i]) for i in range(res.counts[q])]
+            assert_same_topdocs(int(res.total_hits[q]), got, hits, docs, "mixed schema: " + line[:60])
     finally:
         reader.close()
 

@@ -51,6 +51,27 @@ def test_pagination_rule_reproduces_reference_search_after(golden_dir, after_doc
     assert pages > 100
 
 
+def test_segment_without_the_filter_column_as_the_reference_treats_it(golden_dir, g1_dump):
+    """Mixed schema (tests/golden/g1_mixed_k10.res, made by make_golden_mixed.py: the reference over the g1 corpus whose
+    middle segment has no "price" column): a range clause has no scorer there, none of that segment's docs is a hit - also
+    for ranges that hold 0. The oracle over the dump with the column taken out of the middle segment reproduces the
+    reference's results bit for bit."""
+    import copy
+
+    dump = copy.deepcopy(g1_dump)
+    del dump.segments[1].dv["price"]
+    ox = orc.OracleIndex(dump)
+    lines = read_lines(os.path.join(golden_dir, "g1_mixed_queries.txt"))
+    kk, ref = read_results(os.path.join(golden_dir, "g1_mixed_k10.res"))
+    assert kk == 10 and len(ref) == len(lines)
+    lo, hi = dump.segments[1].doc_base, dump.segments[1].doc_base + dump.segments[1].max_doc
+    for line, (hits, rel, docs) in zip(lines, ref):
+        h, sd, _ = ox.search(api.parse_line(line), 10)
+        assert_same_topdocs(h, sd, hits, docs, line[:60])
+        assert not [d for d, _ in docs if lo <= d < hi]
+    assert sum(h for h, _, _ in ref) > 1000
+
+
 @pytest.mark.parametrize("name", ["g1", "g2"])
 def test_reference_default_mode_is_consistent_with_exhaustive(golden_dir, name, g1_dump, g2_dump):
     """The reference's DEFAULT path (MaxScore/WAND pruning) is not a usable oracle: on these small corpora it
