@@ -87,6 +87,7 @@ PROTOTYPES = {
     "dgpu_free_text": (None, [C.c_void_p]),
     "dgpu_open_synthetic": (C.c_void_p, [C.POINTER(CorpusSpec), C.c_int, C.c_int, C.c_int]),
     "dgpu_reader_num_terms": (C.c_int64, [C.c_void_p]),
+    "dgpu_debug_set_fast_text_compile": (None, [C.c_int]),
     "dgpu_reader_term_id": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int64]),
     "dgpu_reader_term_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
     "dgpu_reader_dictionary_frozen": (C.c_int, [C.c_void_p]),

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <filesystem>
@@ -117,8 +118,13 @@ void concat(std::vector<CompiledBatch>& parts, CompiledBatch& out) {
 // Compiles lines [lo, hi) of a text batch on all host threads: straight from the bytes where the line is one of the
 // common shapes (IndexSearcher::compile_text_line), through parse_query_line + compile otherwise (same results, same
 // errors: the first failing line's exception is rethrown).
+// The direct text compiler can be switched off (dgpu_debug_set_fast_text_compile): every line then goes through the
+// generic parser + Query objects. The two must agree on every line, well-formed or not (tests/test_capi_symbols.py).
+std::atomic<bool> g_fast_text_compile{true};
+
 void compile_lines(IndexSearcher& s, const std::vector<LineSpan>& lines, size_t lo, size_t hi, CompiledBatch& out) {
     static const bool trace = std::getenv("DGPU_TRACE") != nullptr;
+    const bool fast = g_fast_text_compile.load(std::memory_order_relaxed);
     const auto t0 = std::chrono::steady_clock::now();
     const size_t n = hi - lo;
     const int threads = n < 512 ? 1 : static_cast<int>(std::min<size_t>(std::thread::hardware_concurrency(), 32));
@@ -131,7 +137,7 @@ void compile_lines(IndexSearcher& s, const std::vector<LineSpan>& lines, size_t 
         part.terms.reserve((e - b) * 8);
         for (size_t i = b; i < e; ++i) {
             const LineSpan& l = lines[lo + i];
-            if (s.compile_text_line(l.first, l.second, part)) continue;
+            if (fast && s.compile_text_line(l.first, l.second, part)) continue;
             try {
                 s.compile(*parse_query_line(std::string(l.first, l.second)), part);
             } catch (...) {
@@ -1166,6 +1172,8 @@ int dgpu_stage_batch_text(DiagonIndexSearcher searcher, const char* text, int64_
 // A compiled batch as a relocatable blob: header {magic, n_queries, n_terms, n_filters} + the three descriptor arrays
 // with offsets local to the blob. Ranks of a sharded index compile disjoint slices of a batch and exchange the blobs;
 // every descriptor only depends on GLOBAL statistics, so it is the same whichever rank compiles it.
+void dgpu_debug_set_fast_text_compile(int on) { g_fast_text_compile.store(on != 0); }
+
 int64_t dgpu_compile_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, uint8_t* out,
                                 int64_t capacity) {
     if (!searcher || !text) { set_error("Invalid searcher or text"); return -1; }

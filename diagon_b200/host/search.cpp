@@ -364,6 +364,7 @@ bool IndexSearcher::compile_text_line(const char* p, const char* end, CompiledBa
     } else {   // ANDNOT n t1 .. tn x1 ..: the first n terms are required, the others excluded
         long long n = 0;
         if (!next_token(p, end, tb, te) || !token_int(tb, te, n)) return give_up();
+        if (n < INT32_MIN || n > INT32_MAX) return give_up();   // (what an int extraction does with it is the generic path's business)
         long long i = 0;
         std::vector<std::pair<const char*, const char*>> nots;
         while (next_token(p, end, tb, te)) {

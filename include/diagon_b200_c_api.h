@@ -238,6 +238,9 @@ int dgpu_shm_exchange_selftest(const uint8_t* id /* [128] */, int32_t rank, int3
  * query); after exchanging the blobs (one all-gather), dgpu_stage_compiled concatenates them in the order given and
  * stages the whole batch on this rank's device (returns the number of queries). */
 int64_t dgpu_compile_batch_text(DiagonIndexSearcher searcher, const char* text, int64_t text_len, uint8_t* out, int64_t capacity);
+/* Testing aid: the text calls compile the common query shapes straight from the line; 0 sends every line through the
+ * generic parser + Query objects instead (process-wide). Both must give the same descriptors and the same errors. */
+void dgpu_debug_set_fast_text_compile(int on);
 int dgpu_stage_compiled(DiagonIndexSearcher searcher, const uint8_t* const* blobs, const int64_t* sizes, int32_t n_blobs, int32_t k);
 
 DiagonQuery dgpu_create_long_range_query(const char* field, int64_t lower, int64_t upper, bool include_lower, bool include_upper);

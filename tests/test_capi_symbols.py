@@ -97,3 +97,86 @@ def test_query_objects_round_trip_through_the_c_abi():
     lib = _lib.load()
     assert lib.dgpu_parse_query(b"BOGUS body x") is None
     assert b"bad query line" in lib.diagon_last_error()
+
+
+def test_direct_text_compiler_agrees_with_the_generic_parser():
+    """The text calls compile the common shapes straight from the query line (no Query objects); everything else - and
+    every error - is the generic parser's. Line by line, well-formed or not, the two ways must produce the same descriptors
+    (byte-identical blobs) or fail with the same message. Host only (device -1)."""
+    import random
+
+    from diagon_b200 import DiagonError, IndexReader, IndexSearcher, named_corpus
+
+    spec = named_corpus("C4", 0.0005)
+    r = IndexReader.synthetic(spec, -1)
+    lib = _lib.load()
+    rnd = random.Random(int(os.environ.get("DGPU_FUZZ_SEED", "20261018")))
+
+    def term():
+        x = rnd.random()
+        if x < 0.80:
+            return "t%07d" % rnd.randrange(1, spec.vocab + 1)
+        if x < 0.88:
+            return "t9%06d" % rnd.randrange(0, 999999)            # not in the index
+        return rnd.choice(["", "x", "t", "t00000010", "T0000001", "t0000001\t", "été", "a" * 300])
+
+    def num():
+        return str(rnd.choice([0, 1, 2, 3, 5, -1, 10 ** 6, 2 ** 31, -2 ** 63, 2 ** 63 - 1, 2 ** 63, 12345, "x", "1.5", "", "+7", "07"]))
+
+    lines = []
+    for _ in range(3000):
+        kind = rnd.choice(["TERM", "OR", "AND", "ORF", "ANDF", "ANDNOT", "OR", "AND", "NOPE", "term", ""])
+        field = rnd.choice(["body", "body", "body", "title", ""])
+        terms = [term() for _ in range(rnd.choice([0, 1, 2, 2, 3, 5, 10, 33, 40]))]
+        if rnd.random() < 0.15 and terms:
+            terms.append(terms[0])                                 # a repeated clause
+        if kind == "TERM":
+            toks = [kind, field] + terms[:rnd.choice([0, 1, 1, 1, 2])]
+        elif kind == "OR":
+            toks = [kind, field, num()] + terms
+        elif kind in ("ORF", "ANDF"):
+            toks = [kind, field, rnd.choice(["price", "price", "nodv", ""]), num(), num()] + terms
+        elif kind == "ANDNOT":
+            toks = [kind, field, num()] + terms
+        else:
+            toks = [kind, field] + terms
+        if rnd.random() < 0.1:
+            toks = toks[:rnd.randrange(0, len(toks) + 1)]          # truncated
+        sep = rnd.choice([" ", " ", " ", "  ", "\t"])
+        lines.append(sep.join(t for t in toks if t != "" or rnd.random() < 0.5))
+    lines += ["ORF body price 5 4 t0000001", "OR body 0", "AND body", "TERM body", "TERM", " ", "OR body 0 t0000001 t0000001",
+              "ANDNOT body 0 t0000001 t0000002", "ANDNOT body 5 t0000001 t0000002", "OR body 99999999999 t0000001",
+              "ORF body price 0 10", "ORF body price -9223372036854775808 9223372036854775807 t0000001"]
+
+    def outcome(s, line):
+        try:
+            return ("ok", s.compile_batch_text(line.encode("utf-8") + b"\n").tobytes())
+        except DiagonError as e:
+            return ("error", str(e))
+
+    try:
+        s = IndexSearcher(r)
+        n_ok = n_err = 0
+        for line in lines:
+            if "\n" in line or line.strip() == "":
+                continue                                           # (blank lines are skipped by the line splitter)
+            lib.dgpu_debug_set_fast_text_compile(1)
+            a = outcome(s, line)
+            lib.dgpu_debug_set_fast_text_compile(0)
+            b = outcome(s, line)
+            assert a == b, (line, a[0], b[0], a[1][:80] if a[0] == "error" else "", b[1][:80] if b[0] == "error" else "")
+            n_ok += a[0] == "ok"
+            n_err += a[0] == "error"
+        assert n_ok > 500 and n_err > 200, (n_ok, n_err)
+        # ... and a whole batch of well-formed lines (the multi-threaded path)
+        good = [l for l in lines if "\n" not in l and l.strip() and outcome(s, l)[0] == "ok"]
+        text = ("\n".join(good * 3) + "\n").encode("utf-8")
+        lib.dgpu_debug_set_fast_text_compile(1)
+        fast = s.compile_batch_text(text).tobytes()
+        lib.dgpu_debug_set_fast_text_compile(0)
+        slow = s.compile_batch_text(text).tobytes()
+        assert fast == slow and len(good) * 3 >= 512
+        s.close()
+    finally:
+        lib.dgpu_debug_set_fast_text_compile(1)
+        r.close()
